@@ -1,0 +1,120 @@
+/* prego_b200 -- C ABI of the B200-native MiniROAD online step-recognition path.
+ *
+ * The reference (aleflabo/PREGO) is pure Python and has no FFI of its own; every entry
+ * point below names the reference Python interface it stands in for.  All pointers are
+ * raw CUDA device pointers unless marked "host"; torch (or any other caller) owns every
+ * buffer, the library only owns the packed copy of the weights inside prego_model_t.
+ * All functions return 0 (PREGO_OK) or a PREGO_ERR_* code; the message of the last
+ * failing call on the calling thread is available from prego_last_error().  Kernels are
+ * enqueued on the given stream (a cudaStream_t passed as void*); nothing synchronises.
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef PREGO_B200_H
+#define PREGO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PREGO_ABI_VERSION 1
+
+#define PREGO_OK 0
+#define PREGO_ERR_INVALID 1     /* bad argument / unsupported shape */
+#define PREGO_ERR_CUDA 2        /* a CUDA runtime / driver call failed */
+#define PREGO_ERR_WORKSPACE 3   /* workspace too small */
+#define PREGO_ERR_STATE 4       /* weights not loaded */
+
+/* Compute precision of the projection / recurrence / head GEMMs. */
+#define PREGO_PREC_BF16 0       /* tcgen05 kind::f16, bf16 operands, fp32 accumulate (throughput path) */
+#define PREGO_PREC_FP32 1       /* exact fp32 FFMA path (1e-4 parity mode) */
+
+typedef struct prego_model prego_model_t;
+
+/* Shapes read from the reference config dict by MROAD.__init__
+ * (step_recognition/model/rnn/rnn.py:21-47): d_rgb / d_flow are FEATURE_SIZES[...] or 0
+ * when cfg['no_rgb'] / cfg['no_flow'] is set. */
+typedef struct prego_dims {
+    int32_t d_rgb;
+    int32_t d_flow;
+    int32_t embed_dim;    /* cfg['embedding_dim'] = 2048 */
+    int32_t hidden_dim;   /* cfg['hidden_dim']    = 1024 */
+    int32_t num_classes;  /* cfg['num_classes']   = 86 | 12 */
+} prego_dims_t;
+
+/* The reference state_dict (rnn.py:38-47), fp32, torch layouts, device pointers. */
+typedef struct prego_weights {
+    const float* layer1_0_weight;          /* [E, d_rgb + d_flow] */
+    const float* layer1_0_bias;            /* [E] */
+    const float* layer1_1_weight;          /* [E]  LayerNorm gamma */
+    const float* layer1_1_bias;            /* [E]  LayerNorm beta  */
+    const float* gru_weight_ih_l0;         /* [3H, E]  rows r | z | n */
+    const float* gru_weight_hh_l0;         /* [3H, H] */
+    const float* gru_bias_ih_l0;           /* [3H] */
+    const float* gru_bias_hh_l0;           /* [3H] */
+    const float* f_classification_0_weight;/* [K, H] */
+    const float* f_classification_0_bias;  /* [K] */
+} prego_weights_t;
+
+typedef struct prego_forward_args {
+    const float* rgb;        /* [B, T, d_rgb]  fp32 contiguous (ignored when d_rgb == 0)  */
+    const float* flow;       /* [B, T, d_flow] fp32 contiguous (ignored when d_flow == 0) */
+    int64_t B;
+    int64_t T;
+    float* h_state;          /* [B, H] GRU state, read before / written after; NULL = zeros in, dropped out
+                                (rnn.py:49,60 always starts from h0 = 0) */
+    float* probs;            /* [B, T, K] softmax probabilities (eval-mode out['logits'], rnn.py:69) or NULL */
+    float* logits;           /* [B, T, K] raw logits (train-mode out['logits'], rnn.py:67) or NULL */
+    int32_t* labels;         /* [B, T] argmax labels (trainer/eval.py:53) or NULL */
+    void* workspace;         /* >= prego_workspace_bytes(model, B, chunk_T, precision) bytes, 1024-aligned */
+    size_t workspace_bytes;
+    int32_t precision;       /* PREGO_PREC_* */
+    int32_t chunk_T;         /* frames per stream processed per pass (time chunk with carried h); 0 = T */
+} prego_forward_args_t;
+
+int prego_abi_version(void);
+const char* prego_last_error(void);
+
+/* Replaces MROAD.__init__ (rnn.py:21-49) + build_model(...).to(device) (model_builder.py:7-9). */
+int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t** out);
+int prego_model_destroy(prego_model_t* model);
+
+/* Replaces model.load_state_dict(torch.load(path)) (main.py:48): packs the ten fp32 tensors into the
+ * library-owned operand formats (bf16 copies, gate-interleaved GRU rows, padded head). */
+int prego_model_load_weights(prego_model_t* model, const prego_weights_t* w, void* stream);
+
+size_t prego_workspace_bytes(const prego_model_t* model, int64_t B, int64_t chunk_T, int32_t precision);
+
+/* Replaces MROAD.forward (rnn.py:51-71) plus the label extraction of Evaluate.eval (trainer/eval.py:53). */
+int prego_forward(prego_model_t* model, const prego_forward_args_t* args, void* stream);
+
+/* Replaces the window vote of aggregate() (utils/aggregate.py:55,65-72) for a ragged batch of label
+ * sequences.  labels: concatenated int32; offsets[B+1] (frames) and win_offsets[B+1] (windows) int64 device
+ * arrays; modes[win_offsets[B]] out.  err_flag (device int, caller-zeroed) becomes 1 if a label is outside
+ * [0, num_labels). */
+int prego_window_mode(const int32_t* labels, const int64_t* offsets, const int64_t* win_offsets, int32_t B,
+                      int64_t total_windows, int32_t window, int32_t num_labels, int32_t* modes, int32_t* err_flag,
+                      void* stream);
+
+/* Replaces find_changes + eliminate_consecutive_duplicates (utils/aggregate.py:7-43) for a ragged batch.
+ * Sequence b = seq[seg_offsets[b] .. seg_offsets[b+1]).  out_vals / out_changes use the same offsets (capacity =
+ * sequence length); change indices are element index * scale, the last one is final_len[b].
+ * counts[b] = number of runs, -1 for an empty sequence (the reference raises IndexError). */
+int prego_rle(const int32_t* seq, const int64_t* seg_offsets, const int64_t* final_len, int32_t B, int64_t scale,
+              int32_t* out_vals, int64_t* out_changes, int32_t* counts, void* stream);
+
+/* Building blocks exposed for parity tests and micro-benchmarks. */
+/* C[M,N] (fp32, ldc = N) = A[M,K] (bf16) * W[N,K]^T (bf16) + bias[N]; tcgen05 path; N % tile_n == 0,
+ * tile_n in {96, 128, 192, 256}, K % 64 == 0. */
+int prego_gemm_bf16_nt(const void* A, const void* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
+                       int32_t tile_n, void* stream);
+/* Same contract in exact fp32 on CUDA cores (K % 16 == 0). */
+int prego_gemm_f32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PREGO_B200_H */

@@ -1,0 +1,82 @@
+"""ctypes binding of ``libprego_b200.so`` (the C ABI declared in ``include/prego_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C prego_b200/csrc``.
+There is no fallback: if the shared object is missing or a call fails, a ``RuntimeError``
+is raised -- the product path never routes through a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libprego_b200.so")
+
+PREC_BF16 = 0
+PREC_FP32 = 1
+PRECISIONS = {"bf16": PREC_BF16, "fp32": PREC_FP32}
+
+
+class Dims(C.Structure):
+    _fields_ = [("d_rgb", C.c_int32), ("d_flow", C.c_int32), ("embed_dim", C.c_int32),
+                ("hidden_dim", C.c_int32), ("num_classes", C.c_int32)]
+
+
+class Weights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "layer1_0_weight", "layer1_0_bias", "layer1_1_weight", "layer1_1_bias",
+        "gru_weight_ih_l0", "gru_weight_hh_l0", "gru_bias_ih_l0", "gru_bias_hh_l0",
+        "f_classification_0_weight", "f_classification_0_bias")]
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [("rgb", C.c_void_p), ("flow", C.c_void_p), ("B", C.c_int64), ("T", C.c_int64),
+                ("h_state", C.c_void_p), ("probs", C.c_void_p), ("logits", C.c_void_p),
+                ("labels", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("precision", C.c_int32), ("chunk_T", C.c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/prego_b200.h declares
+SIGNATURES = {
+    "prego_abi_version": (C.c_int, []),
+    "prego_last_error": (C.c_char_p, []),
+    "prego_model_create": (C.c_int, [C.POINTER(Dims), C.c_int32, C.POINTER(C.c_void_p)]),
+    "prego_model_destroy": (C.c_int, [C.c_void_p]),
+    "prego_model_load_weights": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_void_p]),
+    "prego_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
+    "prego_forward": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.c_void_p]),
+    "prego_window_mode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prego_rle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
+                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prego_gemm_bf16_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                     C.c_int64, C.c_int32, C.c_void_p]),
+    "prego_gemm_f32_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                    C.c_int64, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and attach prototypes.  Raises RuntimeError if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C prego_b200/csrc`. prego_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().prego_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,366 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M, N] = A[M, K] * W[N, K]^T          (bf16 operands, fp32 accumulate in TMEM)
+//
+// A and W are both K-major in global memory (W is exactly the nn.Linear / nn.GRU
+// weight layout), staged into shared memory by TMA with the 128-byte swizzle and
+// consumed by tcgen05.mma straight from shared memory.  One CTA per SM loops over
+// 128 x TILE_N output tiles; the accumulator is double-buffered in TMEM so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Warp roles (192 threads):  warp 0 = TMA producer (one elected lane),
+// warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..5 = epilogue
+// (warp w owns TMEM lanes 32*(w%4) .. +31, i.e. tile rows of that quadrant; one
+// thread per output row).
+//
+// The epilogue is a functor so the same main loop serves
+//   * the input projection  (Linear 4096->2048, rnn.py:40,58)       -> EpiStore
+//   * the GRU input gates   (weight_ih_l0, rnn.py:38,61)            -> EpiStore
+//   * one GRU time step     (weight_hh_l0 + gate math, rnn.py:61)   -> EpiGruStep
+//   * the classifier head   (f_classification + softmax/argmax,
+//                            rnn.py:62-69, trainer/eval.py:53)      -> EpiHead
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "ptx.cuh"
+
+namespace prego {
+
+constexpr int kTileM = 128;
+constexpr int kTileK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kGemmThreads = 192;
+
+template <int TILE_N>
+struct GemmCfg {
+    static constexpr int kABytes = kTileM * kTileK * 2;
+    static constexpr int kBBytes = TILE_N * kTileK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    // accumulator buffer stride in TMEM columns (power of two >= TILE_N)
+    static constexpr int kAccStride = TILE_N <= 32 ? 32 : TILE_N <= 64 ? 64 : TILE_N <= 128 ? 128 : 256;
+    static constexpr int kTmemCols = 2 * kAccStride;
+    static constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/; }
+};
+
+template <int TILE_N, int STAGES, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+               int a_c1, Epi epi) {
+    using Cfg = GemmCfg<TILE_N>;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle atoms.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
+    uint64_t* acc_full = bars + 2 * STAGES;       // [2]       MMA -> epilogue
+    uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int n_tiles = N / TILE_N;
+    const int m_tiles = (M + kTileM - 1) / kTileM;
+    const int total_tiles = n_tiles * m_tiles;
+    const int k_blocks = K / kTileK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&acc_full[b], 1);
+            ptx::mbar_init(&acc_empty[b], 4);  // one arrive per epilogue warp
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * kTileM;
+                const int n0 = (tile % n_tiles) * TILE_N;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                    uint8_t* sb = sa + Cfg::kABytes;
+                    ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    ptx::tma_load_3d(&tmA, sa, &full_bar[stage], kb * kTileK, a_c1, m0, ptx::kEvictNormal);
+                    ptx::tma_load_2d(&tmB, sb, &full_bar[stage], kb * kTileK, n0, ptx::kEvictLast);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc(1 /*bf16*/, kTileM, TILE_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t acc_parity = (it >> 1) & 1;
+                ptx::mbar_wait(&acc_empty[buf], acc_parity ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * Cfg::kAccStride;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
+                    const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+                    for (int k = 0; k < kTileK / 16; ++k) {
+                        // +32 bytes per 16-element K slice inside the 128B swizzle row (>>4 encoded)
+                        ptx::mma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::mma_commit(&acc_full[buf]);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t acc_parity = (it >> 1) & 1;
+            const int m0 = (tile / n_tiles) * kTileM;
+            const int n0 = (tile % n_tiles) * TILE_N;
+            ptx::mbar_wait(&acc_full[buf], acc_parity);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * Cfg::kAccStride + (static_cast<uint32_t>(quad * 32) << 16);
+            const int row = m0 + quad * 32 + lane;
+            epi(taddr, row, n0, row < M);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------ epilogues
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// out[row, n] = acc + bias[n], stored as OutT (float or __nv_bfloat16), row-major with ldc.
+template <int TILE_N, class OutT>
+struct EpiStore {
+    OutT* out;
+    const float* bias;  // [N]
+    int64_t ldc;
+
+    __device__ __forceinline__ void operator()(uint32_t taddr, int row, int n0, bool valid) const {
+#pragma unroll 1
+        for (int c = 0; c < TILE_N / 32; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            if (!valid) continue;
+            const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c * 32);
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 bb = __ldg(b4 + j);
+                f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+                f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+                f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+                f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+            }
+            OutT* dst = out + static_cast<int64_t>(row) * ldc + n0 + c * 32;
+            if constexpr (sizeof(OutT) == 4) {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+                uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 u;
+                    u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                    u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                    u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                    u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                    d4[j] = u;
+                }
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// One GRU time step for a 128-stream x 64-hidden-unit tile.  The accumulator tile is
+// [gh_r(64) | gh_z(64) | gh_n(64)] for hidden units u0 .. u0+63 (gate-interleaved weight
+// packing, see pack.cu).  Gate math follows ATen's order:
+//   r = sigma(gi_r + gh_r + b_hr), z = sigma(gi_z + gh_z + b_hz),
+//   n = tanh(gi_n + r * (gh_n + b_hn)),  h' = (h - n) * z + n.
+struct EpiGruStep {
+    const float* gi;         // [B*Tc, 3H] gate pre-activations (packed column order, b_ih folded in)
+    const float* bhh;        // [3H] packed order
+    float* h32;              // [B, H] fp32 master state (in/out)
+    __nv_bfloat16* hseq;     // [B, Tc+1, H] bf16 state history; slot t is this step's operand, t+1 its result
+    __nv_bfloat16* hrelu;    // [B*Tc, H] bf16 relu(h_t), operand of the classifier head
+    int t, Tc, H;
+
+    __device__ __forceinline__ void operator()(uint32_t taddr, int row, int n0, bool valid) const {
+        const int u0 = (n0 / 192) * 64;
+        const int64_t grow = static_cast<int64_t>(row) * Tc + t;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t vr[16], vz[16], vn[16];
+            ptx::tmem_ld16(taddr + c * 16, vr);
+            ptx::tmem_ld16(taddr + 64 + c * 16, vz);
+            ptx::tmem_ld16(taddr + 128 + c * 16, vn);
+            ptx::tmem_ld_wait();
+            if (!valid) continue;
+            const float* gi_p = gi + grow * (3 * H) + n0 + c * 16;
+            const float* bh_p = bhh + n0 + c * 16;
+            float* h_p = h32 + static_cast<int64_t>(row) * H + u0 + c * 16;
+            float hn[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 gr = *reinterpret_cast<const float4*>(gi_p + 4 * q);
+                const float4 gz = *reinterpret_cast<const float4*>(gi_p + 64 + 4 * q);
+                const float4 gn = *reinterpret_cast<const float4*>(gi_p + 128 + 4 * q);
+                const float4 br = __ldg(reinterpret_cast<const float4*>(bh_p + 4 * q));
+                const float4 bz = __ldg(reinterpret_cast<const float4*>(bh_p + 64 + 4 * q));
+                const float4 bn = __ldg(reinterpret_cast<const float4*>(bh_p + 128 + 4 * q));
+                const float4 hp = *reinterpret_cast<const float4*>(h_p + 4 * q);
+                const float g_r[4] = {gr.x, gr.y, gr.z, gr.w}, g_z[4] = {gz.x, gz.y, gz.z, gz.w},
+                            g_n[4] = {gn.x, gn.y, gn.z, gn.w};
+                const float b_r[4] = {br.x, br.y, br.z, br.w}, b_z[4] = {bz.x, bz.y, bz.z, bz.w},
+                            b_n[4] = {bn.x, bn.y, bn.z, bn.w};
+                const float h_o[4] = {hp.x, hp.y, hp.z, hp.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = 4 * q + j;
+                    const float r = sigmoid_f(g_r[j] + (__uint_as_float(vr[i]) + b_r[j]));
+                    const float z = sigmoid_f(g_z[j] + (__uint_as_float(vz[i]) + b_z[j]));
+                    const float n = tanhf(g_n[j] + r * (__uint_as_float(vn[i]) + b_n[j]));
+                    hn[i] = (h_o[j] - n) * z + n;
+                }
+                *reinterpret_cast<float4*>(h_p + 4 * q) = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
+            }
+            uint4 a, b, ra, rb;
+            a.x = pack_bf16x2(hn[0], hn[1]);   a.y = pack_bf16x2(hn[2], hn[3]);
+            a.z = pack_bf16x2(hn[4], hn[5]);   a.w = pack_bf16x2(hn[6], hn[7]);
+            b.x = pack_bf16x2(hn[8], hn[9]);   b.y = pack_bf16x2(hn[10], hn[11]);
+            b.z = pack_bf16x2(hn[12], hn[13]); b.w = pack_bf16x2(hn[14], hn[15]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hn[i] = fmaxf(hn[i], 0.0f);
+            ra.x = pack_bf16x2(hn[0], hn[1]);   ra.y = pack_bf16x2(hn[2], hn[3]);
+            ra.z = pack_bf16x2(hn[4], hn[5]);   ra.w = pack_bf16x2(hn[6], hn[7]);
+            rb.x = pack_bf16x2(hn[8], hn[9]);   rb.y = pack_bf16x2(hn[10], hn[11]);
+            rb.z = pack_bf16x2(hn[12], hn[13]); rb.w = pack_bf16x2(hn[14], hn[15]);
+            uint4* hs = reinterpret_cast<uint4*>(hseq + (static_cast<int64_t>(row) * (Tc + 1) + t + 1) * H + u0 + c * 16);
+            hs[0] = a;
+            hs[1] = b;
+            uint4* hr = reinterpret_cast<uint4*>(hrelu + grow * H + u0 + c * 16);
+            hr[0] = ra;
+            hr[1] = rb;
+        }
+    }
+};
+
+// Classifier head epilogue: logits = acc + bc; probs = softmax(logits); label = first
+// index of max(probs) (numpy argmax semantics of trainer/eval.py:53).  TILE_N = 96..256
+// padded class count; only the first K columns are real.
+template <int TILE_N>
+struct EpiHead {
+    const float* bias;  // [K]
+    float* probs;       // [B, T, K] or nullptr
+    float* logits;      // [B, T, K] or nullptr
+    int32_t* labels;    // [B, T] or nullptr
+    int K, Tc, T, t0;
+
+    __device__ __forceinline__ void operator()(uint32_t taddr, int row, int /*n0*/, bool valid) const {
+        float v[TILE_N];
+#pragma unroll
+        for (int c = 0; c < TILE_N / 32; ++c) {
+            uint32_t u[32];
+            ptx::tmem_ld32(taddr + c * 32, u);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(u[j]);
+        }
+        if (!valid) return;
+        const int64_t g = static_cast<int64_t>(row / Tc) * T + t0 + (row % Tc);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < TILE_N; ++j) {
+            if (j < K) {
+                v[j] += __ldg(bias + j);
+                mx = fmaxf(mx, v[j]);
+            }
+        }
+        if (logits != nullptr) {
+#pragma unroll
+            for (int j = 0; j < TILE_N; ++j)
+                if (j < K) logits[g * K + j] = v[j];
+        }
+        float sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < TILE_N; ++j) {
+            if (j < K) {
+                v[j] = expf(v[j] - mx);
+                sum += v[j];
+            }
+        }
+        float best = -1.0f;
+        int arg = 0;
+#pragma unroll
+        for (int j = 0; j < TILE_N; ++j) {
+            if (j < K) {
+                v[j] = v[j] / sum;
+                if (v[j] > best) {  // strict: first maximum wins
+                    best = v[j];
+                    arg = j;
+                }
+            }
+        }
+        if (probs != nullptr) {
+#pragma unroll
+            for (int j = 0; j < TILE_N; ++j)
+                if (j < K) probs[g * K + j] = v[j];
+        }
+        if (labels != nullptr) labels[g] = arg;
+    }
+};
+
+}  // namespace prego

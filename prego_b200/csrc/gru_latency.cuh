@@ -1,0 +1,170 @@
+// Persistent single-/few-stream GRU recurrence (rnn.py:61, the T-step hot loop) for the
+// latency regime (B <= 4 streams per pass).
+//
+// * weight_hh_l0 (3H x H fp32, 12.6 MB for H = 1024) is partitioned over H/8 CTAs and stays
+//   resident in shared memory for the whole sequence (96 KB per CTA): no weight byte is
+//   re-read from HBM/L2 after the prologue.
+// * One warp owns one hidden unit: three length-H dot products per stream (conflict-free
+//   smem reads, warp-shuffle reduction), then the fused sigmoid/tanh/state update.
+// * The per-step all-to-all exchange of h needs no separate grid barrier: every h value is
+//   published as one 8-byte word {fp32 value, step tag}; consumers poll the tagged words
+//   straight from L2 (LL-protocol style), so a time step costs one store->load round trip.
+//   Exchange slots are double-buffered by step parity.
+// * Arithmetic is exact fp32 in ATen's order:  h' = (h - n) * z + n.
+//
+// Must be launched with cudaLaunchCooperativeKernel (co-residency of all CTAs).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+
+namespace prego {
+
+constexpr int kLatUnitsPerCta = 8;
+constexpr int kLatThreads = kLatUnitsPerCta * 32;
+
+struct GruLatencyArgs {
+    const float* whh;      // [3H, H] fp32, packed gate-interleaved row order
+    const float* bhh;      // [3H] packed order
+    const float* gi;       // [B*Tc, 3H] fp32 packed column order (b_ih folded in)
+    const float* h_in;     // [B, H] state before the first step of this launch
+    float* h_out;          // [B, H] state after the last step (must not alias h_in)
+    void* hrelu;           // [B*Tc, H] relu(h_t): bf16 or fp32 (out_f32)
+    uint2* xchg;           // [2][NB][H] tagged exchange words
+    int* err_flag;         // set to 1 on spin timeout
+    int H, Tc;
+    int b0;                // first stream of this pass
+    int nb;                // streams in this pass (<= NB)
+    uint32_t tag_base;     // tags used: tag_base + 1 .. tag_base + Tc
+    int out_f32;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(kLatThreads, 1)
+gru_latency_kernel(GruLatencyArgs a) {
+    extern __shared__ float smem_f[];
+    const int H = a.H;
+    float* wsm = smem_f;                              // [3][8][H]
+    float* hbuf = smem_f + 3 * kLatUnitsPerCta * H;   // [2][NB][H]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int u = blockIdx.x * kLatUnitsPerCta + warp;      // hidden unit of this warp
+    const int pcol = (u / 64) * 192 + (u % 64);             // packed column of gate r; z: +64, n: +128
+
+    // Prologue: this CTA's 24 weight rows -> shared memory.
+    for (int idx = tid; idx < 3 * kLatUnitsPerCta * (H / 4); idx += kLatThreads) {
+        const int row = idx / (H / 4), c4 = idx % (H / 4);
+        const int g = row / kLatUnitsPerCta, w = row % kLatUnitsPerCta;
+        const int uu = blockIdx.x * kLatUnitsPerCta + w;
+        const int prow = (uu / 64) * 192 + g * 64 + (uu % 64);
+        reinterpret_cast<float4*>(wsm)[idx] = __ldg(reinterpret_cast<const float4*>(a.whh + static_cast<int64_t>(prow) * H) + c4);
+    }
+    float bh[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) bh[g] = __ldg(a.bhh + pcol + 64 * g);
+
+    for (int t = 0; t < a.Tc; ++t) {
+        // gate pre-activations of this step (independent of h: issue before polling)
+        float gv[3] = {0.f, 0.f, 0.f};
+        if (lane < a.nb) {
+            const float* gp = a.gi + (static_cast<int64_t>(a.b0 + lane) * a.Tc + t) * (3 * H) + pcol;
+            gv[0] = __ldcs(gp);
+            gv[1] = __ldcs(gp + 64);
+            gv[2] = __ldcs(gp + 128);
+        }
+        float* hb = hbuf + (t & 1) * NB * H;
+        int timed_out = 0;
+        if (t == 0) {
+            for (int idx = tid; idx < NB * H; idx += kLatThreads) {
+                const int s = idx / H, k = idx % H;
+                hb[idx] = (s < a.nb) ? a.h_in[static_cast<int64_t>(a.b0 + s) * H + k] : 0.f;
+            }
+        } else {
+            const uint32_t want = a.tag_base + static_cast<uint32_t>(t);
+            const uint2* xs = a.xchg + ((t - 1) & 1) * NB * H;
+            for (int idx = tid; idx < NB * H; idx += 4 * kLatThreads) {
+                uint2 v[4];
+                long long spins = 0;
+                bool done;
+                do {
+                    done = true;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ii = idx + j * kLatThreads;
+                        const bool live = ii < NB * H && (ii / H) < a.nb;
+                        v[j] = live ? ptx::ld_volatile_u64(xs + ii) : make_uint2(0u, want);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) done = done && (v[j].y == want);
+                    if (!done && ++spins > (1ll << 22)) {  // ~seconds: a peer CTA is missing
+                        *a.err_flag = 1;
+                        timed_out = 1;
+                        done = true;
+                    }
+                } while (!done);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ii = idx + j * kLatThreads;
+                    if (ii < NB * H) hb[ii] = __uint_as_float(v[j].x);
+                }
+            }
+        }
+        if (__syncthreads_or(timed_out)) return;  // never hang the GPU: bail out CTA-uniformly
+
+        float acc[3][NB];
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int s = 0; s < NB; ++s) acc[g][s] = 0.f;
+        const float* w0 = wsm + (0 * kLatUnitsPerCta + warp) * H;
+        const float* w1 = wsm + (1 * kLatUnitsPerCta + warp) * H;
+        const float* w2 = wsm + (2 * kLatUnitsPerCta + warp) * H;
+#pragma unroll 8
+        for (int k = lane; k < H; k += 32) {
+            const float wr = w0[k], wz = w1[k], wn = w2[k];
+#pragma unroll
+            for (int s = 0; s < NB; ++s) {
+                const float hv = hb[s * H + k];
+                acc[0][s] = fmaf(wr, hv, acc[0][s]);
+                acc[1][s] = fmaf(wz, hv, acc[1][s]);
+                acc[2][s] = fmaf(wn, hv, acc[2][s]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int s = 0; s < NB; ++s)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[g][s] += __shfl_xor_sync(0xffffffffu, acc[g][s], o);
+
+        // lane s finishes stream s
+        float ghr = 0.f, ghz = 0.f, ghn = 0.f;
+#pragma unroll
+        for (int s = 0; s < NB; ++s) {
+            if (lane == s) {
+                ghr = acc[0][s];
+                ghz = acc[1][s];
+                ghn = acc[2][s];
+            }
+        }
+        if (lane < a.nb) {
+            const float hp = hb[lane * H + u];
+            const float r = sigmoid_f(gv[0] + (ghr + bh[0]));
+            const float z = sigmoid_f(gv[1] + (ghz + bh[1]));
+            const float n = tanhf(gv[2] + r * (ghn + bh[2]));
+            const float hn = (hp - n) * z + n;
+            ptx::st_volatile_u64(a.xchg + ((t & 1) * NB + lane) * H + u, __float_as_uint(hn),
+                                 a.tag_base + static_cast<uint32_t>(t) + 1u);
+            const int64_t orow = static_cast<int64_t>(a.b0 + lane) * a.Tc + t;
+            if (a.out_f32)
+                reinterpret_cast<float*>(a.hrelu)[orow * H + u] = fmaxf(hn, 0.f);
+            else
+                reinterpret_cast<__nv_bfloat16*>(a.hrelu)[orow * H + u] = __float2bfloat16_rn(fmaxf(hn, 0.f));
+            if (t == a.Tc - 1) a.h_out[static_cast<int64_t>(a.b0 + lane) * H + u] = hn;
+        }
+    }
+}
+
+}  // namespace prego

@@ -1,0 +1,366 @@
+// CUDA-core kernels of the MiniROAD path: feature staging, LayerNorm+ReLU, the exact-fp32
+// GEMM used by the PREGO_PREC_FP32 mode, the element-wise GRU gate update of that mode,
+// and softmax/argmax.  All are HBM- or FFMA-bound helpers around the tcgen05 GEMMs.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "gemm_tc.cuh"  // pack_bf16x2, sigmoid_f
+
+namespace prego {
+
+// Row m of a time chunk -> row of the caller's [B, T, D] tensor.
+__device__ __forceinline__ int64_t chunk_row_to_global(int64_t m, int Tc, int T, int t0) {
+    return (m / Tc) * static_cast<int64_t>(T) + t0 + (m % Tc);
+}
+
+// ---------------------------------------------------------------------------------------
+// Feature staging (replaces torch.cat of rnn.py:53 and the fp32->bf16 operand rounding):
+//   xb[m, 0:Dr] = bf16(rgb[b, t0+tt, :]),  xb[m, Dr:Dr+Df] = bf16(flow[b, t0+tt, :])
+// One thread converts 8 consecutive elements (2 x 16 B loads -> one 16 B store).
+__global__ void __launch_bounds__(256)
+stage_features_bf16(const float* __restrict__ rgb, const float* __restrict__ flow, __nv_bfloat16* __restrict__ xb,
+                    int64_t Mc, int Dr, int Df, int Tc, int T, int t0) {
+    const int D = Dr + Df;
+    const int vec_per_row = D / 8;
+    const int64_t total = Mc * vec_per_row;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t m = i / vec_per_row;
+        const int c = static_cast<int>(i % vec_per_row) * 8;
+        const int64_t g = chunk_row_to_global(m, Tc, T, t0);
+        const float* src = (c < Dr) ? (rgb + g * Dr + c) : (flow + g * Df + (c - Dr));
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+        uint4 o;
+        o.x = pack_bf16x2(a.x, a.y);
+        o.y = pack_bf16x2(a.z, a.w);
+        o.z = pack_bf16x2(b.x, b.y);
+        o.w = pack_bf16x2(b.z, b.w);
+        *reinterpret_cast<uint4*>(xb + m * D + c) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm (biased variance, eps inside the sqrt) + ReLU over rows of width E
+// (rnn.py:41-42).  One warp per row, the row lives in registers; two-pass variance.
+// In-place safe (each warp reads its whole row before writing).
+template <int E>
+__global__ void __launch_bounds__(256)
+layernorm_relu_bf16(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ e, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, int64_t M, float eps) {
+    constexpr int kVec = E / (32 * 8);  // 16-byte vectors per lane
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; row < M; row += warps) {
+        const uint4* src = reinterpret_cast<const uint4*>(y + row * E);
+        float v[kVec * 8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const uint4 u = src[i * 32 + lane];
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+                v[i * 8 + 2 * j] = __low2float(p);
+                v[i * 8 + 2 * j + 1] = __high2float(p);
+                sum += v[i * 8 + 2 * j] + v[i * 8 + 2 * j + 1];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mu = sum * (1.0f / E);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec * 8; ++i) {
+            const float d = v[i] - mu;
+            sq += d * d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = 1.0f / sqrtf(sq * (1.0f / E) + eps);
+        uint4* dst = reinterpret_cast<uint4*>(e + row * E);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const int col = (i * 32 + lane) * 8;
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col) + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + col) + 1);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaxf((v[i * 8 + j] - mu) * rstd * gg[j] + bb[j], 0.0f);
+            uint4 u;
+            u.x = pack_bf16x2(o[0], o[1]);
+            u.y = pack_bf16x2(o[2], o[3]);
+            u.z = pack_bf16x2(o[4], o[5]);
+            u.w = pack_bf16x2(o[6], o[7]);
+            dst[i * 32 + lane] = u;
+        }
+    }
+}
+
+// fp32 variant for the exact mode; generic width (E multiple of 128, E <= 4096).
+__global__ void __launch_bounds__(256)
+layernorm_relu_f32(const float* __restrict__ y, float* __restrict__ e, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, int64_t M, int E, float eps) {
+    constexpr int kMaxVec = 32;  // float4 per lane -> E <= 4096
+    const int lane = threadIdx.x & 31;
+    const int nvec = E / 128;
+    const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; row < M; row += warps) {
+        const float4* src = reinterpret_cast<const float4*>(y + row * E);
+        float4 v[kMaxVec];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxVec; ++i) {
+            if (i < nvec) {
+                v[i] = src[i * 32 + lane];
+                sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mu = sum / static_cast<float>(E);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxVec; ++i) {
+            if (i < nvec) {
+                const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+                sq += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = 1.0f / sqrtf(sq / static_cast<float>(E) + eps);
+        float4* dst = reinterpret_cast<float4*>(e + row * E);
+#pragma unroll
+        for (int i = 0; i < kMaxVec; ++i) {
+            if (i < nvec) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+                float4 o;
+                o.x = fmaxf((v[i].x - mu) * rstd * g.x + b.x, 0.f);
+                o.y = fmaxf((v[i].y - mu) * rstd * g.y + b.y, 0.f);
+                o.z = fmaxf((v[i].z - mu) * rstd * g.z + b.z, 0.f);
+                o.w = fmaxf((v[i].w - mu) * rstd * g.w + b.w, 0.f);
+                dst[i * 32 + lane] = o;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Exact fp32 GEMM on CUDA cores:  C[M, N] = [A0 | A1][M, K] * W[N, K]^T + bias.
+// 128x128 tile, BK = 16, 256 threads, 8x8 register tile.  A is optionally split in two
+// column segments (rgb | flow) and its rows optionally remapped from chunk order to the
+// caller's [B, T, D] order, so no concatenated copy is ever made.
+struct SgemmA {
+    const float* a0;
+    const float* a1;  // may be nullptr
+    int k_split;      // columns [0, k_split) come from a0, the rest from a1
+    int64_t lda0, lda1;
+    int remap;        // 1: row m -> chunk_row_to_global(m, Tc, T, t0)
+    int Tc, T, t0;
+};
+
+__global__ void __launch_bounds__(256)
+sgemm_nt_f32(SgemmA A, const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ C, int M,
+             int N, int K, int64_t ldc) {
+    constexpr int BM = 128, BN = 128, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Ws[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM;
+    const int n0 = blockIdx.x * BN;
+    const int tx = tid % 16;  // column group
+    const int ty = tid / 16;  // row group
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    // each thread loads 2 float4 of A and 2 float4 of W per k-block: rows r = tid/4 (+64), k = (tid%4)*4
+    const int lr = tid / 4;
+    const int lk = (tid % 4) * 4;
+    int64_t arow[2];
+    bool aval[2], wval[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int m = m0 + lr + 64 * h;
+        aval[h] = m < M;
+        const int64_t mm = aval[h] ? m : 0;
+        arow[h] = A.remap ? chunk_row_to_global(mm, A.Tc, A.T, A.t0) : mm;
+        wval[h] = (n0 + lr + 64 * h) < N;
+    }
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        const int k = k0 + lk;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (aval[h]) {
+                const float* p = (k < A.k_split) ? (A.a0 + arow[h] * A.lda0 + k) : (A.a1 + arow[h] * A.lda1 + (k - A.k_split));
+                a = *reinterpret_cast<const float4*>(p);
+            }
+            As[lk + 0][lr + 64 * h] = a.x;
+            As[lk + 1][lr + 64 * h] = a.y;
+            As[lk + 2][lr + 64 * h] = a.z;
+            As[lk + 3][lr + 64 * h] = a.w;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (wval[h]) w = __ldg(reinterpret_cast<const float4*>(W + static_cast<int64_t>(n0 + lr + 64 * h) * K + k));
+            Ws[lk + 0][lr + 64 * h] = w.x;
+            Ws[lk + 1][lr + 64 * h] = w.y;
+            Ws[lk + 2][lr + 64 * h] = w.z;
+            Ws[lk + 3][lr + 64 * h] = w.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[8], w[8];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+            const float4 w0 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&Ws[kk][64 + tx * 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (n < N) C[static_cast<int64_t>(m) * ldc + n] = acc[i][j] + (bias != nullptr ? __ldg(bias + n) : 0.f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Element-wise GRU gate update of the exact-fp32 mode (one thread per (stream, unit)).
+// gh = h W_hh'^T + b_hh' was produced by sgemm_nt_f32 in the packed gate-interleaved order.
+__global__ void __launch_bounds__(256)
+gru_gates_f32(const float* __restrict__ gi, const float* __restrict__ gh, float* __restrict__ h32,
+              float* __restrict__ hrelu, int B, int H, int Tc, int t) {
+    const int64_t total = static_cast<int64_t>(B) * H;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int b = static_cast<int>(i / H);
+        const int u = static_cast<int>(i % H);
+        const int p = (u / 64) * 192 + (u % 64);
+        const float* gi_p = gi + (static_cast<int64_t>(b) * Tc + t) * (3 * H) + p;
+        const float* gh_p = gh + static_cast<int64_t>(b) * (3 * H) + p;
+        const float r = sigmoid_f(gi_p[0] + gh_p[0]);
+        const float z = sigmoid_f(gi_p[64] + gh_p[64]);
+        const float n = tanhf(gi_p[128] + r * gh_p[128]);
+        const float hn = (h32[i] - n) * z + n;
+        h32[i] = hn;
+        hrelu[(static_cast<int64_t>(b) * Tc + t) * H + u] = fmaxf(hn, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// softmax + first-max argmax over K classes, one warp per frame (exact-fp32 mode head).
+__global__ void __launch_bounds__(256)
+softmax_argmax_f32(const float* __restrict__ logits_chunk, float* __restrict__ probs, float* __restrict__ logits_out,
+                   int32_t* __restrict__ labels, int64_t Mc, int K, int Tc, int T, int t0) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t m = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; m < Mc; m += warps) {
+        const float* src = logits_chunk + m * K;
+        const int64_t g = chunk_row_to_global(m, Tc, T, t0);
+        float mx = -INFINITY;
+        for (int j = lane; j < K; j += 32) mx = fmaxf(mx, src[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int j = lane; j < K; j += 32) sum += expf(src[j] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        float best = -1.f;
+        int arg = 0x7fffffff;
+        for (int j = lane; j < K; j += 32) {
+            const float l = src[j];
+            const float p = expf(l - mx) / sum;
+            if (probs != nullptr) probs[g * K + j] = p;
+            if (logits_out != nullptr) logits_out[g * K + j] = l;
+            if (p > best) {
+                best = p;
+                arg = j;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg)) {
+                best = ob;
+                arg = oa;
+            }
+        }
+        if (lane == 0 && labels != nullptr) labels[g] = arg;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Weight packing helpers (run once per load).
+// Gate-interleaved row order: packed row p = nt*192 + g*64 + j  <->  original row g*H + nt*64 + j.
+__device__ __forceinline__ int packed_to_orig_row(int p, int H) {
+    const int nt = p / 192, rem = p % 192;
+    return (rem / 64) * H + nt * 64 + (rem % 64);
+}
+
+__global__ void pack_rows_f32(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int H,
+                              int permute) {
+    const int64_t total = static_cast<int64_t>(rows) * cols;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+        const int r = permute ? packed_to_orig_row(p, H) : p;
+        dst[i] = src[static_cast<int64_t>(r) * cols + c];
+    }
+}
+
+// dst rows beyond src_rows are zero (class padding of the head weight).
+__global__ void pack_rows_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int src_rows,
+                               int cols, int H, int permute) {
+    const int64_t total = static_cast<int64_t>(rows) * cols;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+        const int r = permute ? packed_to_orig_row(p, H) : p;
+        dst[i] = __float2bfloat16_rn(r < src_rows ? src[static_cast<int64_t>(r) * cols + c] : 0.f);
+    }
+}
+
+// hseq[b, 0, :] = bf16(h32[b, :]) : seeds slot 0 of the bf16 state history [B, slots, H].
+__global__ void init_hseq_slot0(const float* __restrict__ h32, __nv_bfloat16* __restrict__ hseq, int64_t B, int H,
+                                int slots) {
+    const int64_t total = B * H;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t b = i / H;
+        const int k = static_cast<int>(i % H);
+        hseq[(b * slots) * H + k] = __float2bfloat16_rn(h32[i]);
+    }
+}
+
+__global__ void f32_to_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+}  // namespace prego

@@ -1,0 +1,194 @@
+"""MiniROAD online step-recognition module backed by the sm_100a C-ABI library.
+
+Drop-in for the reference ``MROAD`` (``step_recognition/model/rnn/rnn.py:18-71``):
+
+* same constructor contract ``MROAD(cfg: dict)`` reading ``no_flow, no_rgb, rgb_type,
+  flow_type, hidden_dim, num_layers, num_classes, window_size, embedding_dim, dropout``
+  (rnn.py:23-43);
+* same ten ``state_dict`` tensors (``gru.*``, ``layer1.0.*``, ``layer1.1.*``,
+  ``f_classification.0.*``), created in the reference's order so that the same
+  ``torch.manual_seed`` gives the same default initialisation; ``h0`` is a plain attribute;
+* same ``forward(rgb_input, flow_input) -> {'logits': Tensor[B, T, K]}`` returning softmax
+  probabilities in eval mode (rnn.py:65-71).
+
+The torch sub-modules are parameter containers only -- their ``forward`` is never called.
+All arithmetic runs in ``libprego_b200.so``; there is no PyTorch / CPU fallback and CPU
+tensors are rejected loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .registry import META_ARCHITECTURES
+
+# rnn.py:6-16
+FEATURE_SIZES = {
+    "rgb_anet_resnet50": 2048,
+    "flow_anet_resnet50": 2048,
+    "rgb_kinetics_bninception": 1024,
+    "flow_kinetics_bninception": 1024,
+    "rgb_kinetics_resnet50": 2048,
+    "flow_kinetics_resnet50": 2048,
+    "flow_nv_kinetics_bninception": 1024,
+    "rgb_kinetics_i3d": 2048,
+    "flow_kinetics_i3d": 2048,
+}
+
+_STATE_KEYS = (
+    "layer1.0.weight", "layer1.0.bias", "layer1.1.weight", "layer1.1.bias",
+    "gru.weight_ih_l0", "gru.weight_hh_l0", "gru.bias_ih_l0", "gru.bias_hh_l0",
+    "f_classification.0.weight", "f_classification.0.bias",
+)
+
+
+@META_ARCHITECTURES.register("MiniROAD")
+class MROAD(nn.Module):
+    """B200-native MiniROAD.  Extra (optional) cfg keys: ``precision`` ('bf16' | 'fp32'),
+    ``chunk_frames`` (frames per pass over all streams; bounds the workspace)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.use_flow = not cfg["no_flow"]
+        self.use_rgb = not cfg["no_rgb"]
+        self.d_rgb = FEATURE_SIZES[cfg["rgb_type"]] if self.use_rgb else 0
+        self.d_flow = FEATURE_SIZES[cfg["flow_type"]] if self.use_flow else 0
+        self.input_dim = self.d_rgb + self.d_flow
+        self.hidden_dim = cfg["hidden_dim"]
+        self.num_layers = cfg["num_layers"]
+        self.out_dim = cfg["num_classes"]
+        self.window_size = cfg["window_size"]
+        self.embedding_dim = cfg["embedding_dim"]
+        if self.num_layers != 1:
+            raise ValueError("prego_b200 implements the shipped 1-layer GRU (configs/*.yaml: num_layers 1)")
+        # parameter containers, created in the reference's order (rnn.py:38-47)
+        self.gru = nn.GRU(self.embedding_dim, self.hidden_dim, self.num_layers, batch_first=True)
+        self.layer1 = nn.Sequential(
+            nn.Linear(self.input_dim, self.embedding_dim),
+            nn.LayerNorm(self.embedding_dim),
+            nn.ReLU(),
+            nn.Dropout(p=cfg["dropout"]),
+        )
+        self.f_classification = nn.Sequential(nn.Linear(self.hidden_dim, self.out_dim))
+        self.h0 = torch.zeros(self.num_layers, 1, self.hidden_dim)  # rnn.py:49 (not in state_dict)
+
+        self.precision = cfg.get("precision", "bf16")
+        self.chunk_frames = int(cfg.get("chunk_frames", 1 << 17))
+        self._handle = None
+        self._handle_device = None
+        self._packed_key = None
+        self._workspace = None
+        self.last_labels = None  # int32 [B, T] labels of the last forward (fused argmax)
+
+    # ------------------------------------------------------------------ C-ABI plumbing
+    def _release(self):
+        if self._handle is not None:
+            _lib.load().prego_model_destroy(self._handle)
+            self._handle = None
+            self._packed_key = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure_handle(self, device: torch.device):
+        lib = _lib.load()
+        if self._handle is not None and self._handle_device == device:
+            return lib
+        self._release()
+        dims = _lib.Dims(self.d_rgb, self.d_flow, self.embedding_dim, self.hidden_dim, self.out_dim)
+        h = C.c_void_p()
+        _lib.check(lib.prego_model_create(C.byref(dims), device.index or 0, C.byref(h)), "prego_model_create")
+        self._handle, self._handle_device = h, device
+        return lib
+
+    def _sync_weights(self, lib, device):
+        sd = {k: v for k, v in self.state_dict().items()}
+        tensors = []
+        for k in _STATE_KEYS:
+            t = sd[k]
+            if t.device != device or t.dtype != torch.float32:
+                raise RuntimeError(f"parameter {k} must be fp32 on {device} (got {t.dtype} on {t.device}); call model.to(device)")
+            tensors.append(t.contiguous())
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if key == self._packed_key:
+            return
+        w = _lib.Weights(*[t.data_ptr() for t in tensors])
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(lib.prego_model_load_weights(self._handle, C.byref(w), stream), "prego_model_load_weights")
+        self._packed_key = key
+
+    def _get_workspace(self, nbytes: int, device):
+        ws = self._workspace
+        if ws is None or ws.device != device or ws.numel() < nbytes + 1024:
+            self._workspace = None
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            self._workspace = ws
+        off = (-ws.data_ptr()) % 1024
+        return ws.data_ptr() + off
+
+    # ------------------------------------------------------------------------ inference
+    @torch.no_grad()
+    def infer(self, rgb_input, flow_input, h_state=None, want_probs=True, want_logits=False, want_labels=True,
+              precision=None, chunk_T=None):
+        """Run the CUDA path.  rgb/flow: fp32 CUDA tensors [B, T, D].  ``h_state`` ([B, H] fp32 CUDA)
+        is updated in place when given (streaming / time-chunked online inference)."""
+        ref = rgb_input if self.use_rgb else flow_input
+        if not isinstance(ref, torch.Tensor) or not ref.is_cuda:
+            raise RuntimeError("prego_b200.MROAD runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        device = ref.device
+        B, T = int(ref.shape[0]), int(ref.shape[1])
+
+        def prep(x, d, name):
+            if d == 0:
+                return None
+            if x.device != device or x.dtype != torch.float32 or tuple(x.shape) != (B, T, d):
+                raise RuntimeError(f"{name} must be fp32 [{B}, {T}, {d}] on {device}, got {x.dtype} {tuple(x.shape)} on {x.device}")
+            return x.contiguous()
+
+        rgb = prep(rgb_input, self.d_rgb, "rgb_input")
+        flow = prep(flow_input, self.d_flow, "flow_input")
+        prec = _lib.PRECISIONS[precision or self.precision]
+        with torch.cuda.device(device):
+            lib = self._ensure_handle(device)
+            self._sync_weights(lib, device)
+            if chunk_T is None:
+                chunk_T = max(1, min(T, self.chunk_frames // max(B, 1)))
+            chunk_T = int(min(chunk_T, T))
+            need = lib.prego_workspace_bytes(self._handle, B, chunk_T, prec)
+            ws_ptr = self._get_workspace(need, device)
+            K = self.out_dim
+            probs = torch.empty(B, T, K, dtype=torch.float32, device=device) if want_probs else None
+            logits = torch.empty(B, T, K, dtype=torch.float32, device=device) if want_logits else None
+            labels = torch.empty(B, T, dtype=torch.int32, device=device) if want_labels else None
+            if h_state is not None:
+                if h_state.device != device or h_state.dtype != torch.float32 or tuple(h_state.shape) != (B, self.hidden_dim) \
+                        or not h_state.is_contiguous():
+                    raise RuntimeError(f"h_state must be contiguous fp32 [{B}, {self.hidden_dim}] on {device}")
+            args = _lib.ForwardArgs(
+                rgb.data_ptr() if rgb is not None else None, flow.data_ptr() if flow is not None else None, B, T,
+                h_state.data_ptr() if h_state is not None else None,
+                probs.data_ptr() if probs is not None else None,
+                logits.data_ptr() if logits is not None else None,
+                labels.data_ptr() if labels is not None else None,
+                ws_ptr, need, prec, chunk_T)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(lib.prego_forward(self._handle, C.byref(args), stream), "prego_forward")
+        return {"probs": probs, "logits": logits, "labels": labels}
+
+    def forward(self, rgb_input, flow_input):
+        """rnn.py:51-71.  Eval: ``out['logits']`` = softmax probabilities [B, T, K]."""
+        if self.training:
+            # train mode returns raw logits with dropout active and needs autograd (rnn.py:66-67,
+            # trainer/train.py:20-24); the backward kernels are SURVEY 8 row a17 / config 5.
+            raise NotImplementedError(
+                "prego_b200.MROAD: the training step (BPTT backward + NCCL all-reduce) is not built yet; "
+                "call model.eval() for the online-inference path")
+        out = self.infer(rgb_input, flow_input, want_probs=True, want_labels=True)
+        self.last_labels = out["labels"]
+        return {"logits": out["probs"]}

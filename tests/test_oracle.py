@@ -1,0 +1,109 @@
+"""The oracle (CPU restatement) against the golden vectors produced by the reference itself."""
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, ROOT, case_inputs, load_gz_json, load_model_case, seeded_weights_checked
+from oracle import aggregate_np, miniroad_np
+
+MODEL_CASES = ["epic_b1_t300", "asm_b2_t160", "asm_b1_t64_zeroflow", "epic_b1_t96_rgbonly"]
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_numpy_restatement_matches_reference(golden_meta, name):
+    gold = load_model_case(name)
+    cfg, rgb, flow = case_inputs(golden_meta, name)
+    sd = seeded_weights_checked(golden_meta, name).state_dict()
+    probs, logits, h_last = miniroad_np.forward(sd, rgb.numpy(), flow.numpy(), use_rgb=not cfg["no_rgb"],
+                                                use_flow=not cfg["no_flow"], return_all=True)
+    # fp32 restatement vs ATen fp32: different summation order only
+    assert np.abs(logits - gold["logits"]).max() <= 1e-4 * np.abs(gold["logits"]).max()
+    assert np.abs(probs - gold["probs"]).max() <= 2e-6
+    assert np.abs(h_last - gold["h_last"]).max() <= 2e-5
+    ref_labels = gold["probs"].argmax(-1)
+    mine = miniroad_np.labels_from_probs(probs)
+    bad = mine != ref_labels
+    margin = miniroad_np.top2_margin(gold["logits"])
+    assert bad.mean() <= 1e-3 and np.all(margin[bad] < 1e-4)
+
+
+def test_numpy_restatement_fp64_is_tighter(golden_meta):
+    name = "epic_b1_t96_rgbonly"
+    gold = load_model_case(name)
+    cfg, rgb, flow = case_inputs(golden_meta, name)
+    sd = seeded_weights_checked(golden_meta, name).state_dict()
+    probs = miniroad_np.forward(sd, rgb.numpy(), flow.numpy(), use_flow=False, dtype=np.float64)
+    assert np.abs(probs - gold["probs"]).max() <= 1e-6
+
+
+def test_streaming_equals_whole_sequence(golden_meta):
+    """Carried-state chunking (online inference) reproduces the whole-sequence result."""
+    name = "epic_b1_t96_rgbonly"
+    cfg, rgb, flow = case_inputs(golden_meta, name)
+    sd = seeded_weights_checked(golden_meta, name).state_dict()
+    whole = miniroad_np.forward(sd, rgb.numpy(), flow.numpy(), use_flow=False)
+    h, parts = None, []
+    for s in range(0, 96, 25):
+        p, _, h = miniroad_np.forward(sd, rgb.numpy()[:, s:s + 25], flow.numpy()[:, s:s + 25], use_flow=False,
+                                      h0=h, return_all=True)
+        parts.append(p)
+    assert np.abs(np.concatenate(parts, 1) - whole).max() <= 1e-6
+
+
+# ------------------------------------------------------------------------------ aggregate
+def test_aggregate_np_golden_pair_byte_exact(golden_meta):
+    data = load_gz_json("aggregate_input_epic_tent.json.gz")
+    out = json.dumps(aggregate_np.aggregate_dict(data)).encode()
+    assert hashlib.sha256(out).hexdigest() == golden_meta["aggregate"]["expected_sha256"]
+    assert out == open(os.path.join(GOLD, "aggregate_expected_epic_tent.json"), "rb").read()
+
+
+def test_aggregate_np_kats():
+    for kat in load_gz_json("aggregate_kats.json.gz"):
+        assert aggregate_np.aggregate_video(kat["pred"], kat["gt"]) == kat["expected"]
+
+
+def test_aggregate_empty_raises():
+    with pytest.raises(IndexError):
+        aggregate_np.aggregate_video([], [])
+
+
+@pytest.fixture(scope="module")
+def c_oracle():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libaggregate_oracle.so"))
+    lib.oracle_aggregate_pred.restype = C.c_int64
+    lib.oracle_rle.restype = C.c_int64
+    return lib
+
+
+def _c_collapse(lib, seq, window=None, num_labels=None):
+    a = np.ascontiguousarray(seq, dtype=np.int32)
+    vals = np.empty(max(len(a), 1), np.int32)
+    chg = np.empty(max(len(a), 1), np.int64)
+    p = lambda x, t: x.ctypes.data_as(C.POINTER(t))
+    if window is None:
+        n = lib.oracle_rle(p(a, C.c_int32), C.c_int64(len(a)), p(vals, C.c_int32), p(chg, C.c_int64))
+    else:
+        n = lib.oracle_aggregate_pred(p(a, C.c_int32), C.c_int64(len(a)), C.c_int32(window), C.c_int32(num_labels),
+                                      p(vals, C.c_int32), p(chg, C.c_int64))
+    return n, vals[:max(n, 0)].tolist(), chg[:max(n, 0)].tolist()
+
+
+def test_aggregate_c_oracle(c_oracle):
+    data = load_gz_json("aggregate_input_epic_tent.json.gz")
+    expected = json.load(open(os.path.join(GOLD, "aggregate_expected_epic_tent.json")))
+    for vid, v in data.items():
+        n, vals, chg = _c_collapse(c_oracle, v["pred"], 200, max(v["pred"]) + 1)
+        assert vals == expected[vid]["pred"] and chg == expected[vid]["changes_pred"]
+        n, vals, chg = _c_collapse(c_oracle, v["gt"])
+        assert vals == expected[vid]["gt"] and chg == expected[vid]["changes_gt"]
+    for kat in load_gz_json("aggregate_kats.json.gz"):
+        n, vals, chg = _c_collapse(c_oracle, kat["pred"], 200, max(kat["pred"]) + 1)
+        assert vals == kat["expected"]["pred"] and chg == kat["expected"]["changes_pred"]
+    assert _c_collapse(c_oracle, [])[0] == -1
