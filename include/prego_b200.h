@@ -90,6 +90,20 @@ size_t prego_workspace_bytes(const prego_model_t* model, int64_t B, int64_t chun
 /* Replaces MROAD.forward (rnn.py:51-71) plus the label extraction of Evaluate.eval (trainer/eval.py:53). */
 int prego_forward(prego_model_t* model, const prego_forward_args_t* args, void* stream);
 
+/* Phase timing of prego_forward, measured with CUDA events on the launching stream (what bench.py's
+ * roofline uses).  prego_profile_begin arms it; prego_profile_end waits for the last recorded event and
+ * returns the summed device time (ms) and kernel-launch count of each phase since begin. */
+#define PREGO_PHASE_STAGE 0       /* feature concat + operand rounding */
+#define PREGO_PHASE_GEMM1 1       /* Linear D_in -> E (rnn.py:40) */
+#define PREGO_PHASE_LAYERNORM 2   /* LayerNorm + ReLU (rnn.py:41-42) */
+#define PREGO_PHASE_GEMM2 3       /* GRU input gates (rnn.py:61) */
+#define PREGO_PHASE_RECURRENCE 4  /* GRU time steps (rnn.py:61) */
+#define PREGO_PHASE_HEAD 5        /* classifier + softmax + argmax (rnn.py:62-69, eval.py:53) */
+#define PREGO_NUM_PHASES 6
+int prego_profile_begin(prego_model_t* model);
+int prego_profile_end(prego_model_t* model, double* phase_ms /*[PREGO_NUM_PHASES]*/,
+                      int64_t* phase_launches /*[PREGO_NUM_PHASES]*/);
+
 /* Replaces the window vote of aggregate() (utils/aggregate.py:55,65-72) for a ragged batch of label
  * sequences.  labels: concatenated int32; offsets[B+1] (frames) and win_offsets[B+1] (windows) int64 device
  * arrays; modes[win_offsets[B]] out.  err_flag (device int, caller-zeroed) becomes 1 if a label is outside

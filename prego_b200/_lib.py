@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libprego_b200.so")
 PREC_BF16 = 0
 PREC_FP32 = 1
 PRECISIONS = {"bf16": PREC_BF16, "fp32": PREC_FP32}
+PHASES = ("stage", "gemm1", "layernorm", "gemm2", "recurrence", "head")
 
 
 class Dims(C.Structure):
@@ -45,6 +46,8 @@ SIGNATURES = {
     "prego_model_load_weights": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_void_p]),
     "prego_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
     "prego_forward": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.c_void_p]),
+    "prego_profile_begin": (C.c_int, [C.c_void_p]),
+    "prego_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "prego_window_mode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "prego_rle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,

@@ -99,6 +99,7 @@ inline int grid_for(int64_t work_items, int threads, int sm_count) {
     return static_cast<int>(blocks);
 }
 
+constexpr int kProfMaxEvents = 8192;
 constexpr int kLatencyMaxB = 16;  // up to this many streams the recurrence runs on the persistent SIMT kernel
 
 }  // namespace
@@ -120,7 +121,28 @@ struct prego_model {
     uint2* xchg = nullptr;
     int* err_flag = nullptr;
     uint32_t tag_base = 0;
+    // optional phase profiling (CUDA events on the launching stream)
+    bool prof = false;
+    int prof_n = 0;
+    cudaEvent_t prof_ev[kProfMaxEvents] = {};
+    int8_t prof_phase[kProfMaxEvents] = {};
+    int64_t prof_launches[PREGO_NUM_PHASES] = {};
 };
+
+namespace {
+// Record "phase `phase` ended here" (phase < 0: start marker).
+inline void prof_mark(prego_model* m, cudaStream_t s, int phase, int launches) {
+    if (!m->prof) return;
+    if (phase >= 0) m->prof_launches[phase] += launches;
+    if (m->prof_n >= kProfMaxEvents) return;
+    if (m->prof_ev[m->prof_n] == nullptr) {
+        if (cudaEventCreate(&m->prof_ev[m->prof_n]) != cudaSuccess) return;
+    }
+    cudaEventRecord(m->prof_ev[m->prof_n], s);
+    m->prof_phase[m->prof_n] = static_cast<int8_t>(phase);
+    ++m->prof_n;
+}
+}  // namespace
 
 namespace {
 
@@ -247,6 +269,8 @@ int prego_model_destroy(prego_model_t* m) {
                     m->w1_bf, m->wih_bfp, m->whh_bfp, m->wc_bfp, m->xchg, m->err_flag};
     for (void* p : ptrs)
         if (p != nullptr) cudaFree(p);
+    for (cudaEvent_t e : m->prof_ev)
+        if (e != nullptr) cudaEventDestroy(e);
     delete m;
     return PREGO_OK;
 }
@@ -332,25 +356,30 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
         const int tc = static_cast<int>(T - t0 < Tc ? T - t0 : Tc);
         const int64_t Mc = B * tc;
         const int Mi = static_cast<int>(Mc);
+        prof_mark(m, s, -1, 0);
         if (bf) {
             // 1. stage features: concat + bf16
             stage_features_bf16<<<grid_for(Mc * (Din / 8), 256, m->sm_count), 256, 0, s>>>(a->rgb, a->flow, xb, Mc, d.d_rgb, d.d_flow, tc, (int)T, (int)t0);
             LAUNCH_CHECK("stage_features_bf16");
+            prof_mark(m, s, PREGO_PHASE_STAGE, 1);
             // 2. y = x W1^T + b1   (bf16 out)
             CUtensorMap tmA, tmB;
             if ((rc = make_tmap_bf16(&tmA, xb, Din, 1, Mc, Din, Din, kTileM)) != PREGO_OK) return rc;
             if ((rc = make_tmap_bf16_2d(&tmB, m->w1_bf, Din, E, 256)) != PREGO_OK) return rc;
             EpiStore<256, __nv_bfloat16> ep1{reinterpret_cast<__nv_bfloat16*>(ye), m->b1, E};
             if ((rc = launch_gemm_tc<256, 4>(tmA, tmB, Mi, E, Din, 0, ep1, m->sm_count, s, "gemm1")) != PREGO_OK) return rc;
+            prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
             // 3. e = relu(LN(y))   (in place)
             layernorm_relu_bf16<2048><<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(
                 reinterpret_cast<const __nv_bfloat16*>(ye), reinterpret_cast<__nv_bfloat16*>(ye), m->ln_g, m->ln_b, Mc, 1e-5f);
             LAUNCH_CHECK("layernorm_relu_bf16");
+            prof_mark(m, s, PREGO_PHASE_LAYERNORM, 1);
             // 4. gi = e W_ih'^T + b_ih'  (fp32 out, gate-interleaved columns)
             if ((rc = make_tmap_bf16(&tmA, ye, E, 1, Mc, E, E, kTileM)) != PREGO_OK) return rc;
             if ((rc = make_tmap_bf16_2d(&tmB, m->wih_bfp, E, 3 * H, 192)) != PREGO_OK) return rc;
             EpiStore<192, float> ep2{gi, m->bih_p, 3 * H};
             if ((rc = launch_gemm_tc<192, 5>(tmA, tmB, Mi, 3 * H, E, 0, ep2, m->sm_count, s, "gemm2")) != PREGO_OK) return rc;
+            prof_mark(m, s, PREGO_PHASE_GEMM2, 1);
         } else {
             SgemmA A1{a->rgb, a->flow, d.d_rgb, d.d_rgb, d.d_flow, 1, tc, (int)T, (int)t0};
             if (d.d_rgb == 0) { A1.a0 = a->flow; A1.a1 = nullptr; A1.k_split = Din; A1.lda0 = d.d_flow; }
@@ -358,11 +387,14 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
             float* y32 = reinterpret_cast<float*>(ye);
             sgemm_nt_f32<<<dim3(E / 128, (Mi + 127) / 128), 256, 0, s>>>(A1, m->w1_f32, m->b1, y32, Mi, E, Din, E);
             LAUNCH_CHECK("sgemm gemm1");
+            prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
             layernorm_relu_f32<<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(y32, y32, m->ln_g, m->ln_b, Mc, E, 1e-5f);
             LAUNCH_CHECK("layernorm_relu_f32");
+            prof_mark(m, s, PREGO_PHASE_LAYERNORM, 1);
             SgemmA A2{y32, nullptr, E, E, 0, 0, tc, (int)T, (int)t0};
             sgemm_nt_f32<<<dim3(3 * H / 128, (Mi + 127) / 128), 256, 0, s>>>(A2, m->wih_f32p, m->bih_p, gi, Mi, 3 * H, E, 3 * H);
             LAUNCH_CHECK("sgemm gemm2");
+            prof_mark(m, s, PREGO_PHASE_GEMM2, 1);
         }
 
         // 5. recurrence over the tc steps of this chunk
@@ -398,6 +430,7 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
             LAUNCH_CHECK("fp32 recurrence");
         }
 
+        prof_mark(m, s, PREGO_PHASE_RECURRENCE, tensor_rec ? (bf ? tc + 1 : 2 * tc) : (int)((B + 3) / 4));
         // 6. head
         if (bf) {
             CUtensorMap tmA, tmB;
@@ -417,9 +450,40 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
             softmax_argmax_f32<<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(logits_ws, a->probs, a->logits, a->labels, Mc, K, tc, (int)T, (int)t0);
             LAUNCH_CHECK("fp32 head");
         }
+        prof_mark(m, s, PREGO_PHASE_HEAD, bf ? 1 : 2);
     }
     if (a->h_state != nullptr)
         CUDA_TRY(cudaMemcpyAsync(a->h_state, h_cur, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, s));
+    return PREGO_OK;
+}
+
+int prego_profile_begin(prego_model_t* m) {
+    int rc = check_model(m, false);
+    if (rc != PREGO_OK) return rc;
+    m->prof = true;
+    m->prof_n = 0;
+    for (auto& l : m->prof_launches) l = 0;
+    return PREGO_OK;
+}
+
+int prego_profile_end(prego_model_t* m, double* phase_ms, int64_t* phase_launches) {
+    int rc = check_model(m, false);
+    if (rc != PREGO_OK) return rc;
+    if (phase_ms == nullptr || phase_launches == nullptr) return fail(PREGO_ERR_INVALID, "NULL output pointer");
+    m->prof = false;
+    for (int i = 0; i < PREGO_NUM_PHASES; ++i) {
+        phase_ms[i] = 0.0;
+        phase_launches[i] = m->prof_launches[i];
+    }
+    if (m->prof_n > 0) CUDA_TRY(cudaEventSynchronize(m->prof_ev[m->prof_n - 1]));
+    for (int i = 1; i < m->prof_n; ++i) {
+        const int ph = m->prof_phase[i];
+        if (ph < 0) continue;
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, m->prof_ev[i - 1], m->prof_ev[i]));
+        phase_ms[ph] += ms;
+    }
+    m->prof_n = 0;
     return PREGO_OK;
 }
 

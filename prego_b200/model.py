@@ -181,6 +181,20 @@ class MROAD(nn.Module):
             _lib.check(lib.prego_forward(self._handle, C.byref(args), stream), "prego_forward")
         return {"probs": probs, "logits": logits, "labels": labels}
 
+    def profile_begin(self):
+        """Arm per-phase CUDA-event timing inside the library (used by bench.py's roofline)."""
+        if self._handle is None:
+            raise RuntimeError("run one inference first (the handle is created lazily)")
+        _lib.check(_lib.load().prego_profile_begin(self._handle), "prego_profile_begin")
+
+    def profile_end(self):
+        """-> {phase: {"ms": device time, "launches": kernel launches}} since profile_begin()."""
+        n = len(_lib.PHASES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        _lib.check(_lib.load().prego_profile_end(self._handle, ms, cnt), "prego_profile_end")
+        return {p: {"ms": ms[i], "launches": int(cnt[i])} for i, p in enumerate(_lib.PHASES)}
+
     def forward(self, rgb_input, flow_input):
         """rnn.py:51-71.  Eval: ``out['logits']`` = softmax probabilities [B, T, K]."""
         if self.training:
