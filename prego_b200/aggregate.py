@@ -51,59 +51,80 @@ def _rle_call(lib, seq, seg_off_dev, final_len_dev, B, scale, stream):
     return vals, changes, counts
 
 
-def aggregate_labels(preds: Sequence, gts: Sequence, window: int = WINDOW_SIZE, device=None) -> List[Dict[str, List[int]]]:
-    """Collapse a ragged batch of per-frame label sequences.  Returns one dict per video with the
-    reference's four keys.  Raises IndexError on an empty video (aggregate.py:18 does)."""
+def aggregate_device(pred: torch.Tensor, plens: List[int], gt: torch.Tensor, glens: List[int], window: int,
+                     num_labels: int):
+    """Device-resident core: concatenated int32 label tensors + per-video lengths in, device result
+    tensors out (no host sync except none).  Returns a dict of device tensors and host offsets."""
+    device = pred.device
+    lib = _lib.load()
+    B = len(plens)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    p_off_dev, _ = _offsets(plens, device)
+    g_off_dev, g_off = _offsets(glens, device)
+    wlens = [(n + window - 1) // window for n in plens]
+    w_off_dev, w_off = _offsets(wlens, device)
+    total_windows = int(w_off[-1])
+    modes = torch.empty(max(total_windows, 1), dtype=torch.int32, device=device)
+    err = torch.zeros(1, dtype=torch.int32, device=device)
+    _lib.check(lib.prego_window_mode(pred.data_ptr(), p_off_dev.data_ptr(), w_off_dev.data_ptr(), B,
+                                     total_windows, window, num_labels, modes.data_ptr(), err.data_ptr(), stream),
+               "prego_window_mode")
+    plen_dev = torch.tensor(plens, dtype=torch.int64).to(device, non_blocking=True)
+    glen_dev = torch.tensor(glens, dtype=torch.int64).to(device, non_blocking=True)
+    pv, pc, pn = _rle_call(lib, modes, w_off_dev, plen_dev, B, window, stream)
+    gv, gc, gn = _rle_call(lib, gt, g_off_dev, glen_dev, B, 1, stream)
+    return {"pred_vals": pv, "pred_changes": pc, "pred_counts": pn, "pred_offsets": w_off,
+            "gt_vals": gv, "gt_changes": gc, "gt_counts": gn, "gt_offsets": g_off, "err": err}
+
+
+def aggregate_labels(preds, gts, window: int = WINDOW_SIZE, device=None, num_labels=None) -> List[Dict[str, List[int]]]:
+    """Collapse a ragged batch of per-frame label sequences.  ``preds`` / ``gts``: lists of sequences
+    (lists, numpy, torch; host or device) or 2-D integer tensors [B, T].  Returns one dict per video
+    with the reference's four keys.  Raises IndexError on an empty video (aggregate.py:18 does)."""
     if len(preds) != len(gts):
         raise ValueError("preds and gts must have the same number of videos")
     B = len(preds)
     if B == 0:
         return []
     if device is None:
-        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        if isinstance(preds, torch.Tensor) and preds.is_cuda:
+            device = preds.device
+        elif torch.cuda.is_available():
+            device = torch.device("cuda", torch.cuda.current_device())
     if device is None or torch.device(device).type != "cuda":
         raise RuntimeError("prego_b200.aggregate runs on a CUDA (sm_100a) device; there is no CPU fallback")
     device = torch.device(device)
-    lib = _lib.load()
     with torch.cuda.device(device):
-        stream = torch.cuda.current_stream(device).cuda_stream
-        pred, plens = _as_device_labels(preds, device)
-        gt, glens = _as_device_labels(gts, device)
+        if isinstance(preds, torch.Tensor) and preds.dim() == 2:
+            pred, plens = preds.to(device=device, dtype=torch.int32).reshape(-1), [int(preds.shape[1])] * B
+        else:
+            pred, plens = _as_device_labels(preds, device)
+        if isinstance(gts, torch.Tensor) and gts.dim() == 2:
+            gt, glens = gts.to(device=device, dtype=torch.int32).reshape(-1), [int(gts.shape[1])] * B
+        else:
+            gt, glens = _as_device_labels(gts, device)
         if min(plens) == 0 or min(glens) == 0:
             raise IndexError("index 0 is out of bounds for axis 0 with size 0")
-        lo, hi = int(pred.min()), int(pred.max())
-        if lo < 0:
-            raise ValueError("'list' argument must have no negative elements")  # np.bincount's message
-        num_labels = hi + 1
-        p_off_dev, p_off = _offsets(plens, device)
-        g_off_dev, _ = _offsets(glens, device)
-        wlens = [(n + window - 1) // window for n in plens]
-        w_off_dev, w_off = _offsets(wlens, device)
-        total_windows = int(w_off[-1])
-        modes = torch.empty(total_windows, dtype=torch.int32, device=device)
-        err = torch.zeros(1, dtype=torch.int32, device=device)
-        _lib.check(lib.prego_window_mode(pred.data_ptr(), p_off_dev.data_ptr(), w_off_dev.data_ptr(), B,
-                                         total_windows, window, num_labels, modes.data_ptr(), err.data_ptr(), stream),
-                   "prego_window_mode")
-        plen_dev = torch.tensor(plens, dtype=torch.int64, device=device)
-        glen_dev = torch.tensor(glens, dtype=torch.int64, device=device)
-        pv, pc, pn = _rle_call(lib, modes, w_off_dev, plen_dev, B, window, stream)
-        gv, gc, gn = _rle_call(lib, gt, g_off_dev, glen_dev, B, 1, stream)
-        pv, pc, pn, gv, gc, gn, err = (t.cpu() for t in (pv, pc, pn, gv, gc, gn, err))
+        if num_labels is None:
+            lo, hi = int(pred.min()), int(pred.max())
+            if lo < 0:
+                raise ValueError("'list' argument must have no negative elements")  # np.bincount's message
+            num_labels = hi + 1
+        r = aggregate_device(pred, plens, gt, glens, window, num_labels)
+        pv, pc, pn, gv, gc, gn, err = (r[k].cpu() for k in ("pred_vals", "pred_changes", "pred_counts", "gt_vals",
+                                                             "gt_changes", "gt_counts", "err"))
     if int(err) != 0:
-        raise RuntimeError("prego_window_mode: label outside [0, num_labels)")
-    g_off = torch.zeros(B + 1, dtype=torch.int64)
-    g_off[1:] = torch.cumsum(torch.tensor(glens, dtype=torch.int64), 0)
+        raise ValueError("label outside [0, num_labels)")
+    w_off, g_off = r["pred_offsets"], r["gt_offsets"]
+    pv, pc, gv, gc = pv.tolist(), pc.tolist(), gv.tolist(), gc.tolist()
+    pn, gn = pn.tolist(), gn.tolist()
+    w_off, g_off = w_off.tolist(), g_off.tolist()
     out = []
     for b in range(B):
-        ps, pk = int(w_off[b]), int(pn[b])
-        gs, gk = int(g_off[b]), int(gn[b])
-        out.append({
-            "pred": pv[ps:ps + pk].tolist(),
-            "gt": gv[gs:gs + gk].tolist(),
-            "changes_pred": pc[ps:ps + pk].tolist(),
-            "changes_gt": gc[gs:gs + gk].tolist(),
-        })
+        ps, pk = w_off[b], pn[b]
+        gs, gk = g_off[b], gn[b]
+        out.append({"pred": pv[ps:ps + pk], "gt": gv[gs:gs + gk],
+                    "changes_pred": pc[ps:ps + pk], "changes_gt": gc[gs:gs + gk]})
     return out
 
 
