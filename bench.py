@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native MiniROAD online-inference path.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+One rank per GPU (torchrun env for N > 1).  Prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json configs[2], "Assembly101-O-shaped, 4096 concurrent streams ... on 1xB200"):
+a STEP is one pass of the hot path -- feature staging, Linear+LayerNorm+ReLU, GRU input gates,
+GRU recurrence with carried state, classifier+softmax+argmax -- over one time chunk of
+`--chunk` (64) frames for each of `--streams` (4096) concurrent streams per GPU, i.e. 262 144 frames
+(4 GiB of fp32 features, far larger than the 126 MB L2) per GPU per step.  After the K timed steps
+the per-frame labels of all K chunks are collapsed to step sequences (200-frame window vote + RLE,
+utils/aggregate.py) inside the timed region.  Streams shard by GPU with no data-path collective
+(weak scaling: per-GPU work is fixed).  value = frames / s over all GPUs, inputs resident in HBM.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_GEMM1 = 2 * 4096 * 2048          # per frame
+FLOP_GEMM2 = 2 * 2048 * 3072
+FLOP_REC = 2 * 1024 * 3072
+BYTES_FEATURES = 16384                # fp32 rgb + flow per frame
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
+    ap.add_argument("--chunk", type=int, default=64, help="frames per stream per step")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-stream latency leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def dist_env(n):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_baseline_run(streams, chunk, target_seconds=12.0, repeats=1):
+    """Time the ATen-based CPU port of the reference path (oracle/miniroad_torch_cpu.py) on a bounded
+    sample of the workload, all host threads.  Returns (frames/s, description, cores)."""
+    from oracle.miniroad_torch_cpu import CpuMiniROAD
+    from oracle import aggregate_np
+    from prego_b200 import synthetic
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = synthetic.seeded_model(dict(synthetic.ASSEMBLY101_O), seed=20)
+    port = CpuMiniROAD(model.state_dict())
+    bs = min(streams, 64)
+    g = torch.Generator().manual_seed(1)
+    rgb = torch.randn(bs, chunk, 2048, generator=g).abs_()
+    flow = torch.randn(bs, chunk, 2048, generator=g).abs_()
+    t0 = time.perf_counter()
+    labels = port.labels(rgb, flow)  # warm-up + calibration
+    t1 = time.perf_counter() - t0
+    reps = max(1, min(64, int(target_seconds / max(t1, 1e-3))))
+    best = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            labels = port.labels(rgb, flow)
+            for b in range(bs):
+                aggregate_np.aggregate_video(labels[b], labels[b])
+        best.append((time.perf_counter() - t0) / reps)
+    dt = float(np.median(best))
+    return bs * chunk / dt, f"{bs} of {streams} streams x {chunk} frames per pass, {reps} passes, torch {torch.__version__} CPU (ATen/oneDNN), + aggregate", cores
+
+
+def run_reference(args, world, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference's Python
+    files cannot travel to the GPU box and it has no compiled sources), rank 0 only."""
+    if rank != 0:
+        return
+    from oracle.miniroad_torch_cpu import CpuMiniROAD
+    from oracle import aggregate_np
+    from prego_b200 import synthetic
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = synthetic.seeded_model(dict(synthetic.ASSEMBLY101_O), seed=20)
+    port = CpuMiniROAD(model.state_dict())
+    bs = 64
+    g = torch.Generator().manual_seed(1)
+    rgb = torch.randn(bs, args.chunk, 2048, generator=g).abs_()
+    flow = torch.randn(bs, args.chunk, 2048, generator=g).abs_()
+
+    def step():
+        labels = port.labels(rgb, flow)
+        for b in range(bs):
+            aggregate_np.aggregate_video(labels[b], labels[b])
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    fps = bs * args.chunk * args.steps / dt
+    sample = f"{bs} of {args.streams} streams x {args.chunk} frames per step (bounded sample of the same workload)"
+    line = {"impl": "reference", "metric": "frames/sec MiniROAD online inference", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"Assembly101-O-shaped, {args.streams} streams x {args.chunk}-frame chunks (K=86)", "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- single-stream latency leg
+def latency_leg(dev, precision):
+    """BASELINE configs[1]: Epic-tent-O shape, one stream, on one B200."""
+    from prego_b200 import synthetic
+    model = synthetic.seeded_model(dict(synthetic.EPIC_TENT_O), seed=20, device=dev)
+    out = {}
+    # (a) whole video, T = 12 531 (dataset mean): projections batched over the video, recurrence sequential
+    T = 12531
+    rgb, flow = synthetic.device_features(1, T, dev, seed=3)
+    for _ in range(2):
+        model.infer(rgb, flow, want_probs=False, precision=precision)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(3):
+        e0.record()
+        model.infer(rgb, flow, want_probs=False, precision=precision)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    out["whole_video"] = {"T": T, "ms_per_video": ms, "ms_per_frame": ms / T, "frames_per_s": T / ms * 1e3}
+    model.profile_begin()
+    model.infer(rgb, flow, want_probs=False, precision=precision)
+    prof = model.profile_end()
+    out["whole_video"]["recurrence_us_per_step"] = prof["recurrence"]["ms"] / T * 1e3
+    # (b) strict per-frame online stepping: one frame per call, carried h, label read back each frame
+    h = torch.zeros(1, 1024, device=dev)
+    n = 300
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    for t in range(20):
+        model.infer(rgb[:, t:t + 1], flow[:, t:t + 1], h_state=h, want_probs=False, precision=precision)
+    torch.cuda.synchronize()
+    wall = []
+    for t in range(n):
+        t0 = time.perf_counter()
+        lab = model.infer(rgb[:, t:t + 1], flow[:, t:t + 1], h_state=h, want_probs=False, precision=precision)["labels"]
+        lab.cpu()
+        wall.append((time.perf_counter() - t0) * 1e3)
+    out["per_frame_online"] = {"frames": n, "p50_ms": float(np.percentile(wall, 50)), "p99_ms": float(np.percentile(wall, 99)),
+                               "note": "one prego_forward call per frame incl. host launch + label D2H"}
+    return out
+
+
+# ----------------------------------------------------------------------------- main arm
+def run_ours(args, world, rank, local):
+    import torch.distributed as dist
+    from prego_b200 import _lib, synthetic
+    from prego_b200.aggregate import aggregate_device
+
+    assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback)"
+    _lib.load()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, Tc, K, W = args.streams, args.chunk, args.steps, args.warmup
+    model = synthetic.seeded_model(dict(synthetic.ASSEMBLY101_O), seed=20, device=dev)
+    # per-rank shard of the stream population: distinct seeds per rank, features resident in HBM
+    rgb, flow = synthetic.device_features(B, Tc, dev, seed=1234 + rank)
+    h = torch.zeros(B, 1024, device=dev)
+    labels_all = torch.empty(K, B, Tc, dtype=torch.int32, device=dev)
+
+    def step(i):
+        out = model.infer(rgb, flow, h_state=h, want_probs=False, want_labels=True, precision=args.precision, chunk_T=Tc)
+        labels_all[i % K].copy_(out["labels"])
+
+    def collapse():
+        seq = labels_all.permute(1, 0, 2).reshape(B, K * Tc).contiguous()
+        flat = seq.reshape(-1)
+        r = aggregate_device(flat, [K * Tc] * B, flat, [K * Tc] * B, 200, 86)
+        return r["pred_counts"].sum() + r["gt_counts"].sum()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    collapse()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        step(i)
+    total_runs = collapse()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = float(ms)
+    frames = world * B * Tc * K
+    value = frames / ms * 1e3
+    _ = int(total_runs)
+
+    # phase profile over K more steps (CUDA events on the launching stream inside the library)
+    model.profile_begin()
+    for i in range(K):
+        step(i)
+    prof = model.profile_end()
+    # end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hr, hf = rgb.cpu().pin_memory(), flow.cpu().pin_memory()
+        drgb, dflow = torch.empty_like(rgb), torch.empty_like(flow)
+        hl = torch.empty(B, Tc, dtype=torch.int32).pin_memory()
+        h2 = torch.zeros(B, 1024, device=dev)
+
+        def e2e_step():
+            drgb.copy_(hr, non_blocking=True)
+            dflow.copy_(hf, non_blocking=True)
+            out = model.infer(drgb, dflow, h_state=h2, want_probs=False, precision=args.precision, chunk_T=Tc)
+            hl.copy_(out["labels"], non_blocking=True)
+
+        e2e_step()
+        barrier()
+        n_e2e = max(2, min(K, 4))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt)
+        e2e = {"value": B * Tc * n_e2e / dt * world, "unit": "frames/s", "h2d_bytes_per_step": hr.numel() * 4 + hf.numel() * 4,
+               "d2h_bytes_per_step": hl.numel() * 4, "steps": n_e2e,
+               "note": "pinned host fp32 features -> H2D -> prego_forward -> int32 labels D2H; PCIe-bound (16 KiB/frame); all ranks concurrently, max over ranks"}
+        del hr, hf, drgb, dflow
+
+    if rank != 0:
+        if world > 1:
+            # keep ranks alive until rank 0 finished its extra legs
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    Mc = B * Tc
+    g1_ms = prof["gemm1"]["ms"] / max(prof["gemm1"]["launches"], 1)
+    achieved = FLOP_GEMM1 * Mc / (g1_ms * 1e-3) / 1e12
+    phase_share = {p: round(v["ms"] / sum(x["ms"] for x in prof.values()), 4) for p, v in prof.items()}
+    phase_tflops = {
+        "gemm1": FLOP_GEMM1 * Mc * K / (prof["gemm1"]["ms"] * 1e-3) / 1e12,
+        "gemm2": FLOP_GEMM2 * Mc * K / (prof["gemm2"]["ms"] * 1e-3) / 1e12,
+        "recurrence": FLOP_REC * Mc * K / (prof["recurrence"]["ms"] * 1e-3) / 1e12,
+    }
+    stage_gbs = (BYTES_FEATURES + 8192) * Mc * K / (prof["stage"]["ms"] * 1e-3) / 1e9
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<256,4,...> (Linear 4096->2048, tcgen05 kind::f16)",
+                "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": f"{pk['source']} bf16 sustained (kernel timed inside a long step)",
+                "per_launch_ms": g1_ms, "flops_per_launch": FLOP_GEMM1 * Mc,
+                "phase_share": phase_share, "phase_tflops": phase_tflops,
+                "stage_features_gbs": stage_gbs, "stage_frac_of_hbm": stage_gbs / pk["hbm_gbs"],
+                "whole_step_tflops": (FLOP_GEMM1 + FLOP_GEMM2 + FLOP_REC + 2 * 1024 * 86) * value / world / 1e12}
+    launches = sum(v["launches"] for v in prof.values()) + 3  # + window_mode, 2 x rle
+
+    lat = None
+    if not args.no_latency and world == 1:
+        del rgb, flow
+        torch.cuda.empty_cache()
+        lat = latency_leg(dev, args.precision)
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        v, sample, cores = cpu_baseline_run(B, Tc)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+
+    line = {"metric": "frames/sec MiniROAD online inference", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "config": {"workload": f"Assembly101-O-shaped MiniROAD eval, {B} concurrent streams/GPU x {Tc}-frame chunks with carried GRU state (K=86), + window-vote/RLE collapse",
+                       "streams_per_gpu": B, "chunk_frames": Tc, "frames_per_step_per_gpu": Mc, "precision": args.precision,
+                       "l2_policy": "inputs larger than L2 (4 GiB of features per step vs 126 MB L2)",
+                       "weights": "seed-20 default init (no checkpoint ships with the reference)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "single_stream": lat}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    world, rank, local = dist_env(args.gpus)
+    if args.impl == "reference":
+        run_reference(args, world, rank)
+        return
+    run_ours(args, world, rank, local)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,8 @@ extern "C" {
 /* Compute precision of the projection / recurrence / head GEMMs. */
 #define PREGO_PREC_BF16 0       /* tcgen05 kind::f16, bf16 operands, fp32 accumulate (throughput path) */
 #define PREGO_PREC_FP32 1       /* exact fp32 FFMA path (1e-4 parity mode) */
+#define PREGO_PREC_F16 2        /* tcgen05 kind::f16, fp16 operands (10-bit mantissa = TF32 accuracy at the bf16 rate),
+                                   fp32 accumulate; inputs saturate at +-65504 (default throughput path) */
 
 typedef struct prego_model prego_model_t;
 
@@ -120,10 +122,10 @@ int prego_rle(const int32_t* seq, const int64_t* seg_offsets, const int64_t* fin
               int32_t* out_vals, int64_t* out_changes, int32_t* counts, void* stream);
 
 /* Building blocks exposed for parity tests and micro-benchmarks. */
-/* C[M,N] (fp32, ldc = N) = A[M,K] (bf16) * W[N,K]^T (bf16) + bias[N]; tcgen05 path; N % tile_n == 0,
- * tile_n in {96, 128, 192, 256}, K % 64 == 0. */
-int prego_gemm_bf16_nt(const void* A, const void* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
-                       int32_t tile_n, void* stream);
+/* C[M,N] (fp32, ldc = N) = A[M,K] * W[N,K]^T + bias[N] with 16-bit operands (precision = PREGO_PREC_F16 or
+ * PREGO_PREC_BF16) on the tcgen05 path; N % tile_n == 0, tile_n in {96, 128, 192, 256}, K % 64 == 0. */
+int prego_gemm16_nt(const void* A, const void* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
+                    int32_t tile_n, int32_t precision, void* stream);
 /* Same contract in exact fp32 on CUDA cores (K % 16 == 0). */
 int prego_gemm_f32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
                       void* stream);

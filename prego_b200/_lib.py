@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libprego_b200.so")
 
 PREC_BF16 = 0
 PREC_FP32 = 1
-PRECISIONS = {"bf16": PREC_BF16, "fp32": PREC_FP32}
+PREC_F16 = 2
+PRECISIONS = {"bf16": PREC_BF16, "fp32": PREC_FP32, "fp16": PREC_F16}
 PHASES = ("stage", "gemm1", "layernorm", "gemm2", "recurrence", "head")
 
 
@@ -52,8 +53,8 @@ SIGNATURES = {
                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "prego_rle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                             C.c_void_p, C.c_void_p, C.c_void_p]),
-    "prego_gemm_bf16_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
-                                     C.c_int64, C.c_int32, C.c_void_p]),
+    "prego_gemm16_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                  C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "prego_gemm_f32_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                     C.c_int64, C.c_void_p]),
 }

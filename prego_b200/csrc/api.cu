@@ -2,6 +2,7 @@
 // pipeline (time-chunked, carried GRU state) and the aggregation entry points.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -13,6 +14,7 @@
 #include "aggregate.cuh"
 #include "gemm_tc.cuh"
 #include "gru_latency.cuh"
+#include "gru_step.cuh"
 #include "simt_kernels.cuh"
 
 using namespace prego;
@@ -43,6 +45,12 @@ int fail(int code, const char* fmt, ...) {
             return fail(PREGO_ERR_CUDA, "launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
+#define RC_TRY(expr)                     \
+    do {                                 \
+        int _rc = (expr);                \
+        if (_rc != PREGO_OK) return _rc; \
+    } while (0)
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -60,34 +68,45 @@ int get_encode_fn() {
     return PREGO_OK;
 }
 
-// bf16 K-major operand map, 128B swizzle.  3-D view (k, inner, outer): box (64, 1, box_rows).
-int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t k, uint64_t inner, uint64_t outer,
-                   uint64_t inner_stride_elems, uint64_t outer_stride_elems, uint32_t box_rows) {
-    int rc = get_encode_fn();
-    if (rc != PREGO_OK) return rc;
-    cuuint64_t dims[3] = {k, inner, outer};
-    cuuint64_t strides[2] = {inner_stride_elems * 2, outer_stride_elems * 2};
-    cuuint32_t box[3] = {static_cast<cuuint32_t>(kTileK), 1, box_rows};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(PREGO_ERR_CUDA, "cuTensorMapEncodeTiled (3d) failed with CUresult %d", (int)r);
+enum DType { kF16 = 0, kBF16 = 1, kF32 = 2 };
+
+// Generic tiled map with the 128-byte swizzle (inner box extent is always 128 bytes).
+// dims / box: innermost first; strides_bytes: for dims 1..rank-1.
+int make_tmap(CUtensorMap* tm, DType dt, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
+    RC_TRY(get_encode_fn());
+    cuuint64_t d[3], s[2];
+    cuuint32_t b[3], e[3] = {1, 1, 1};
+    for (int i = 0; i < rank; ++i) {
+        d[i] = dims[i];
+        b[i] = box[i];
+        if (i > 0) s[i - 1] = strides_bytes[i - 1];
+    }
+    const CUtensorMapDataType cdt = dt == kF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                  : dt == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = g_encode(tm, cdt, rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PREGO_ERR_CUDA, "cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)r);
     return PREGO_OK;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t k, uint64_t rows, uint32_t box_rows) {
-    int rc = get_encode_fn();
-    if (rc != PREGO_OK) return rc;
-    cuuint64_t dims[2] = {k, rows};
-    cuuint64_t strides[1] = {k * 2};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(kTileK), box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(PREGO_ERR_CUDA, "cuTensorMapEncodeTiled (2d) failed with CUresult %d", (int)r);
-    return PREGO_OK;
+// A operand of the generic GEMM: row-major [rows, k] 16-bit, viewed as (k, 1, rows), box (64, 1, 128).
+int make_tmap_a(CUtensorMap* tm, DType dt, const void* base, uint64_t k, uint64_t rows) {
+    const uint64_t dims[3] = {k, 1, rows}, str[2] = {k * 2, k * 2};
+    const uint32_t box[3] = {kTileK, 1, kTileM};
+    return make_tmap(tm, dt, 3, base, dims, str, box);
+}
+// W operand: row-major [n, k] 16-bit, box (64, tile_n).
+int make_tmap_w(CUtensorMap* tm, DType dt, const void* base, uint64_t k, uint64_t n, uint32_t tile_n) {
+    const uint64_t dims[2] = {k, n}, str[1] = {k * 2};
+    const uint32_t box[2] = {kTileK, tile_n};
+    return make_tmap(tm, dt, 2, base, dims, str, box);
+}
+// time-major activation [slots, B, cols] (elem_bytes each), box (128 B worth of cols, 128 rows, 1).
+int make_tmap_tm(CUtensorMap* tm, DType dt, const void* base, uint64_t cols, uint64_t B, uint64_t slots, int elem_bytes) {
+    const uint64_t dims[3] = {cols, B, slots}, str[2] = {cols * elem_bytes, B * cols * elem_bytes};
+    const uint32_t box[3] = {128u / elem_bytes, kTileM, 1};
+    return make_tmap(tm, dt, 3, base, dims, str, box);
 }
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -115,8 +134,9 @@ struct prego_model {
     float *w1_f32 = nullptr, *b1 = nullptr, *ln_g = nullptr, *ln_b = nullptr;
     float *wih_f32p = nullptr, *whh_f32p = nullptr, *bih_p = nullptr, *bhh_p = nullptr;
     float *wc_f32 = nullptr, *bc = nullptr;
-    // bf16 operands of the tcgen05 path
-    __nv_bfloat16 *w1_bf = nullptr, *wih_bfp = nullptr, *whh_bfp = nullptr, *wc_bfp = nullptr;
+    // 16-bit operands of the tcgen05 path, [0] = fp16, [1] = bf16
+    void *w1_16[2] = {nullptr, nullptr}, *wih_16p[2] = {nullptr, nullptr}, *whh_16p[2] = {nullptr, nullptr},
+         *wc_16p[2] = {nullptr, nullptr};
     // latency-kernel exchange
     uint2* xchg = nullptr;
     int* err_flag = nullptr;
@@ -130,6 +150,7 @@ struct prego_model {
 };
 
 namespace {
+
 // Record "phase `phase` ended here" (phase < 0: start marker).
 inline void prof_mark(prego_model* m, cudaStream_t s, int phase, int launches) {
     if (!m->prof) return;
@@ -142,19 +163,16 @@ inline void prof_mark(prego_model* m, cudaStream_t s, int phase, int launches) {
     m->prof_phase[m->prof_n] = static_cast<int8_t>(phase);
     ++m->prof_n;
 }
-}  // namespace
-
-namespace {
 
 struct Plan {
-    int64_t h32_a, h32_b;     // [B, H] fp32 state ping-pong
-    int64_t xb;               // bf16 [Mc, Din]
-    int64_t ye;               // bf16 or fp32 [Mc, E]  (y, normalised in place to e)
-    int64_t gi;               // fp32 [Mc, 3H]
-    int64_t hseq;             // bf16 [B, Tc+1, H]   (tensor-core recurrence only)
-    int64_t hrelu;            // bf16 or fp32 [Mc, H]
-    int64_t gh;               // fp32 [B, 3H]        (fp32 batched recurrence only)
-    int64_t logits;           // fp32 [Mc, K]        (fp32 head only)
+    int64_t h32_a, h32_b;  // [B, H] fp32 state ping-pong
+    int64_t xb;            // 16-bit [Mc, Din]                      (16-bit modes)
+    int64_t ye;            // fp16 y -> 16-bit e in place, or fp32  [Mc, E]
+    int64_t gi;            // [Mc, 3H] fp16 (batched 16-bit recurrence) or fp32
+    int64_t hseq;          // 16-bit [Tc+1, B, H]                   (batched 16-bit recurrence)
+    int64_t hrelu;         // 16-bit or fp32 [Mc, H]
+    int64_t gh;            // fp32 [B, 3H]                          (fp32 batched recurrence)
+    int64_t logits;        // fp32 [Mc, K]                          (fp32 head)
     int64_t total;
 };
 
@@ -169,23 +187,24 @@ Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec) {
     };
     p.h32_a = take(B * H * 4);
     p.h32_b = take(B * H * 4);
-    const bool bf = prec == PREGO_PREC_BF16;
-    p.xb = bf ? take(Mc * Din * 2) : 0;
-    p.ye = take(Mc * E * (bf ? 2 : 4));
-    p.gi = take(Mc * 3 * H * 4);
-    p.hseq = (bf && B > kLatencyMaxB) ? take(B * (Tc + 1) * H * 2) : 0;
-    p.hrelu = take(Mc * H * (bf ? 2 : 4));
-    p.gh = (!bf && B > kLatencyMaxB) ? take(B * 3 * H * 4) : 0;
-    p.logits = bf ? 0 : take(Mc * K * 4);
+    const bool h16 = prec != PREGO_PREC_FP32;
+    const bool batched = B > kLatencyMaxB;
+    p.xb = h16 ? take(Mc * Din * 2) : 0;
+    p.ye = take(Mc * E * (h16 ? 2 : 4));
+    p.gi = take(Mc * 3 * H * ((h16 && batched) ? 2 : 4));
+    p.hseq = (h16 && batched) ? take(B * (Tc + 1) * H * 2) : 0;
+    p.hrelu = take(Mc * H * (h16 ? 2 : 4));
+    p.gh = (!h16 && batched) ? take(B * 3 * H * 4) : 0;
+    p.logits = h16 ? 0 : take(Mc * K * 4);
     p.total = off;
     return p;
 }
 
-template <int TILE_N, int STAGES, class Epi>
+template <int TILE_N, int STAGES, int FMT, class Epi>
 int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int a_c1, const Epi& epi,
                    int sm_count, cudaStream_t stream, const char* name) {
     using Cfg = GemmCfg<TILE_N>;
-    auto kfn = gemm_tc_kernel<TILE_N, STAGES, Epi>;
+    auto kfn = gemm_tc_kernel<TILE_N, STAGES, FMT, Epi>;
     static bool attr_set = false;  // per instantiation
     const int smem = Cfg::smem_bytes(STAGES);
     if (!attr_set) {
@@ -220,6 +239,187 @@ int launch_latency(const GruLatencyArgs& a, int H, cudaStream_t stream) {
     return PREGO_OK;
 }
 
+// Few-stream recurrence on the persistent SIMT kernel (passes of <= 4 streams).
+int run_latency_recurrence(prego_model* m, const float* gi, float*& h_cur, float*& h_alt, void* hrelu, int64_t B, int tc,
+                           int out_fmt, int64_t row_sb, int64_t row_st, cudaStream_t s) {
+    const int H = m->d.hidden_dim;
+    for (int b0 = 0; b0 < B; b0 += 4) {
+        const int nb = (int)(B - b0 < 4 ? B - b0 : 4);
+        GruLatencyArgs la{m->whh_f32p, m->bhh_p, gi, h_cur, h_alt, hrelu, m->xchg, m->err_flag, H, tc, b0, nb, m->tag_base,
+                          out_fmt, row_sb, row_st};
+        m->tag_base += static_cast<uint32_t>(tc);
+        if (nb == 1) RC_TRY(launch_latency<1>(la, H, s));
+        else if (nb == 2) RC_TRY(launch_latency<2>(la, H, s));
+        else RC_TRY(launch_latency<4>(la, H, s));
+    }
+    float* tmp = h_cur;
+    h_cur = h_alt;
+    h_alt = tmp;
+    return PREGO_OK;
+}
+
+// One time chunk of the 16-bit tensor-core path.
+template <int FMT>
+int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt,
+             int64_t t0, int tc, cudaStream_t s) {
+    using OpT = typename Op16<FMT>::T;
+    const DType dt = FMT == 0 ? kF16 : kBF16;
+    const prego_dims_t& d = m->d;
+    const int64_t B = a->B, T = a->T, Mc = B * tc;
+    const int Mi = static_cast<int>(Mc);
+    const int H = d.hidden_dim, E = d.embed_dim, K = d.num_classes, Din = m->din;
+    const bool batched = B > kLatencyMaxB;
+    OpT* xb = reinterpret_cast<OpT*>(ws + p.xb);
+    void* ye = ws + p.ye;
+    void* gi = ws + p.gi;
+    OpT* hseq = reinterpret_cast<OpT*>(ws + p.hseq);
+    OpT* hrelu = reinterpret_cast<OpT*>(ws + p.hrelu);
+    CUtensorMap tmA, tmB;
+
+    // 1. stage features: concat + operand rounding (replaces torch.cat, rnn.py:53)
+    stage_features_16<FMT><<<grid_for(Mc * (Din / 8), 256, m->sm_count), 256, 0, s>>>(a->rgb, a->flow, xb, Mc, d.d_rgb, d.d_flow, tc, (int)T, (int)t0);
+    LAUNCH_CHECK("stage_features_16");
+    prof_mark(m, s, PREGO_PHASE_STAGE, 1);
+    // 2. y = x W1^T + b1  (fp16 out, stream-major rows)
+    RC_TRY(make_tmap_a(&tmA, dt, xb, Din, Mc));
+    RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 256));
+    RC_TRY((launch_gemm_tc<256, 4, FMT>(tmA, tmB, Mi, E, Din, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1")));
+    prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
+    // 3. e = relu(LN(y))  (in place, operand format)
+    layernorm_relu_16<2048, FMT><<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(
+        reinterpret_cast<const __half*>(ye), reinterpret_cast<OpT*>(ye), m->ln_g, m->ln_b, Mc, 1e-5f);
+    LAUNCH_CHECK("layernorm_relu_16");
+    prof_mark(m, s, PREGO_PHASE_LAYERNORM, 1);
+    // 4. gi = e W_ih'^T + b_ih'  (gate-interleaved columns, rows re-ordered to time-major)
+    RC_TRY(make_tmap_a(&tmA, dt, ye, E, Mc));
+    RC_TRY(make_tmap_w(&tmB, dt, m->wih_16p[FMT], E, 3 * H, 192));
+    if (batched)
+        RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, 0>{gi, m->bih_p, 3 * H, tc, (int)B}, m->sm_count, s, "gemm2")));
+    else
+        RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, -1>{gi, m->bih_p, 3 * H, tc, (int)B}, m->sm_count, s, "gemm2")));
+    prof_mark(m, s, PREGO_PHASE_GEMM2, 1);
+
+    // 5. recurrence
+    if (batched) {
+        f32_to_16<FMT><<<grid_for(B * H, 256, m->sm_count), 256, 0, s>>>(h_cur, hseq, B * H);  // history slot 0 = carried state
+        LAUNCH_CHECK("f32_to_16 (hseq slot 0)");
+        CUtensorMap tmHseq, tmW, tmGi, tmH32, tmHrelu;
+        RC_TRY(make_tmap_tm(&tmHseq, dt, hseq, H, B, tc + 1, 2));
+        RC_TRY(make_tmap_w(&tmW, dt, m->whh_16p[FMT], H, 3 * H, kGruTileN));
+        RC_TRY(make_tmap_tm(&tmGi, kF16, gi, 3 * H, B, tc, 2));
+        {
+            const uint64_t dims[2] = {(uint64_t)H, (uint64_t)B}, str[1] = {(uint64_t)H * 4};
+            const uint32_t box[2] = {32, kTileM};
+            RC_TRY(make_tmap(&tmH32, kF32, 2, h_cur, dims, str, box));
+        }
+        RC_TRY(make_tmap_tm(&tmHrelu, dt, hrelu, H, B, tc, 2));
+        auto kfn = gru_step_kernel<FMT>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmemBytes));
+            attr_set = true;
+        }
+        const int tiles = (3 * H / kGruTileN) * (int)((B + kTileM - 1) / kTileM);
+        const int grid = tiles < m->sm_count ? tiles : m->sm_count;
+        for (int t = 0; t < tc; ++t)
+            kfn<<<grid, kGruThreads, kGruSmemBytes, s>>>(tmHseq, tmW, tmGi, tmH32, tmHrelu, m->bhh_p, (int)B, H, t);
+        LAUNCH_CHECK("gru_step_kernel");
+        prof_mark(m, s, PREGO_PHASE_RECURRENCE, tc + 1);
+    } else {
+        RC_TRY(run_latency_recurrence(m, reinterpret_cast<const float*>(gi), h_cur, h_alt, hrelu, B, tc, FMT, 1, B, s));
+        prof_mark(m, s, PREGO_PHASE_RECURRENCE, (int)((B + 3) / 4));
+    }
+
+    // 6. head: logits, softmax, argmax (rows are time-major)
+    RC_TRY(make_tmap_a(&tmA, dt, hrelu, H, Mc));
+    RC_TRY(make_tmap_w(&tmB, dt, m->wc_16p[FMT], H, m->kpad, m->kpad));
+    if (m->kpad == 96)
+        RC_TRY((launch_gemm_tc<96, 6, FMT>(tmA, tmB, Mi, 96, H, 0, EpiHead<96>{m->bc, a->probs, a->logits, a->labels, K, (int)B, (int)T, (int)t0}, m->sm_count, s, "head96")));
+    else
+        RC_TRY((launch_gemm_tc<128, 6, FMT>(tmA, tmB, Mi, 128, H, 0, EpiHead<128>{m->bc, a->probs, a->logits, a->labels, K, (int)B, (int)T, (int)t0}, m->sm_count, s, "head128")));
+    prof_mark(m, s, PREGO_PHASE_HEAD, 1);
+    return PREGO_OK;
+}
+
+// One time chunk of the exact-fp32 CUDA-core path (stream-major rows throughout).
+int chunk_f32(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt,
+              int64_t t0, int tc, cudaStream_t s) {
+    const prego_dims_t& d = m->d;
+    const int64_t B = a->B, T = a->T, Mc = B * tc;
+    const int Mi = static_cast<int>(Mc);
+    const int H = d.hidden_dim, E = d.embed_dim, K = d.num_classes, Din = m->din;
+    float* y32 = reinterpret_cast<float*>(ws + p.ye);
+    float* gi = reinterpret_cast<float*>(ws + p.gi);
+    float* hr32 = reinterpret_cast<float*>(ws + p.hrelu);
+    float* gh = reinterpret_cast<float*>(ws + p.gh);
+    float* logits_ws = reinterpret_cast<float*>(ws + p.logits);
+
+    SgemmA A1{a->rgb, a->flow, d.d_rgb, d.d_rgb, d.d_flow, 1, tc, (int)T, (int)t0};
+    if (d.d_rgb == 0) { A1.a0 = a->flow; A1.a1 = nullptr; A1.k_split = Din; A1.lda0 = d.d_flow; }
+    if (d.d_flow == 0) { A1.a1 = nullptr; A1.k_split = Din; }
+    sgemm_nt_f32<<<dim3(E / 128, (Mi + 127) / 128), 256, 0, s>>>(A1, m->w1_f32, m->b1, y32, Mi, E, Din, E);
+    LAUNCH_CHECK("sgemm gemm1");
+    prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
+    layernorm_relu_f32<<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(y32, y32, m->ln_g, m->ln_b, Mc, E, 1e-5f);
+    LAUNCH_CHECK("layernorm_relu_f32");
+    prof_mark(m, s, PREGO_PHASE_LAYERNORM, 1);
+    SgemmA A2{y32, nullptr, E, E, 0, 0, tc, (int)T, (int)t0};
+    sgemm_nt_f32<<<dim3(3 * H / 128, (Mi + 127) / 128), 256, 0, s>>>(A2, m->wih_f32p, m->bih_p, gi, Mi, 3 * H, E, 3 * H);
+    LAUNCH_CHECK("sgemm gemm2");
+    prof_mark(m, s, PREGO_PHASE_GEMM2, 1);
+
+    if (B <= kLatencyMaxB) {
+        RC_TRY(run_latency_recurrence(m, gi, h_cur, h_alt, hr32, B, tc, -1, tc, 1, s));
+        prof_mark(m, s, PREGO_PHASE_RECURRENCE, (int)((B + 3) / 4));
+    } else {
+        for (int t = 0; t < tc; ++t) {
+            SgemmA Ah{h_cur, nullptr, H, H, 0, 0, tc, (int)T, (int)t0};
+            sgemm_nt_f32<<<dim3(3 * H / 128, (int)((B + 127) / 128)), 256, 0, s>>>(Ah, m->whh_f32p, m->bhh_p, gh, (int)B, 3 * H, H, 3 * H);
+            gru_gates_f32<<<grid_for(B * H, 256, m->sm_count), 256, 0, s>>>(gi, gh, h_cur, hr32, (int)B, H, tc, t);
+        }
+        LAUNCH_CHECK("fp32 recurrence");
+        prof_mark(m, s, PREGO_PHASE_RECURRENCE, 2 * tc);
+    }
+
+    SgemmA Ah{hr32, nullptr, H, H, 0, 0, tc, (int)T, (int)t0};
+    sgemm_nt_f32<<<dim3((K + 127) / 128, (Mi + 127) / 128), 256, 0, s>>>(Ah, m->wc_f32, m->bc, logits_ws, Mi, K, H, K);
+    softmax_argmax_f32<<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(logits_ws, a->probs, a->logits, a->labels, Mc, K, tc, (int)T, (int)t0);
+    LAUNCH_CHECK("fp32 head");
+    prof_mark(m, s, PREGO_PHASE_HEAD, 2);
+    return PREGO_OK;
+}
+
+template <int FMT>
+int pack16(prego_model* m, const prego_weights_t* w, cudaStream_t s) {
+    using OpT = typename Op16<FMT>::T;
+    const int H = m->d.hidden_dim, E = m->d.embed_dim, K = m->d.num_classes, din = m->din;
+    const int T = 256;
+    auto g = [&](int64_t n) { return grid_for(n, T, m->sm_count); };
+    f32_to_16<FMT><<<g((int64_t)E * din), T, 0, s>>>(w->layer1_0_weight, reinterpret_cast<OpT*>(m->w1_16[FMT]), (int64_t)E * din);
+    pack_rows_16<FMT><<<g((int64_t)3 * H * E), T, 0, s>>>(w->gru_weight_ih_l0, reinterpret_cast<OpT*>(m->wih_16p[FMT]), 3 * H, 3 * H, E, H, 1);
+    pack_rows_16<FMT><<<g((int64_t)3 * H * H), T, 0, s>>>(w->gru_weight_hh_l0, reinterpret_cast<OpT*>(m->whh_16p[FMT]), 3 * H, 3 * H, H, H, 1);
+    if (m->kpad)
+        pack_rows_16<FMT><<<g((int64_t)m->kpad * H), T, 0, s>>>(w->f_classification_0_weight, reinterpret_cast<OpT*>(m->wc_16p[FMT]), m->kpad, K, H, H, 0);
+    LAUNCH_CHECK("16-bit weight packing");
+    return PREGO_OK;
+}
+
+template <int FMT>
+int gemm16_test(const void* A, const void* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K, int tile_n,
+                int sms, cudaStream_t s) {
+    const DType dt = FMT == 0 ? kF16 : kBF16;
+    CUtensorMap tmA, tmB;
+    RC_TRY(make_tmap_a(&tmA, dt, A, K, M));
+    RC_TRY(make_tmap_w(&tmB, dt, W, K, N, tile_n));
+    switch (tile_n) {
+        case 96: return launch_gemm_tc<96, 6, FMT>(tmA, tmB, (int)M, (int)N, (int)K, 0, EpiStore<96, -1>{C, bias, N, 0, 0}, sms, s, "gemm96");
+        case 128: return launch_gemm_tc<128, 6, FMT>(tmA, tmB, (int)M, (int)N, (int)K, 0, EpiStore<128, -1>{C, bias, N, 0, 0}, sms, s, "gemm128");
+        case 192: return launch_gemm_tc<192, 5, FMT>(tmA, tmB, (int)M, (int)N, (int)K, 0, EpiStore<192, -1>{C, bias, N, 0, 0}, sms, s, "gemm192");
+        case 256: return launch_gemm_tc<256, 4, FMT>(tmA, tmB, (int)M, (int)N, (int)K, 0, EpiStore<256, -1>{C, bias, N, 0, 0}, sms, s, "gemm256");
+        default: return fail(PREGO_ERR_INVALID, "tile_n must be 96, 128, 192 or 256 (got %d)", tile_n);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -252,8 +452,10 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
     ALLOC(m->w1_f32, E * din * 4); ALLOC(m->b1, E * 4); ALLOC(m->ln_g, E * 4); ALLOC(m->ln_b, E * 4);
     ALLOC(m->wih_f32p, 3 * H * E * 4); ALLOC(m->whh_f32p, 3 * H * H * 4); ALLOC(m->bih_p, 3 * H * 4); ALLOC(m->bhh_p, 3 * H * 4);
     ALLOC(m->wc_f32, K * H * 4); ALLOC(m->bc, K * 4);
-    ALLOC(m->w1_bf, E * din * 2); ALLOC(m->wih_bfp, 3 * H * E * 2); ALLOC(m->whh_bfp, 3 * H * H * 2);
-    if (m->kpad) ALLOC(m->wc_bfp, (int64_t)m->kpad * H * 2);
+    for (int f = 0; f < 2; ++f) {
+        ALLOC(m->w1_16[f], E * din * 2); ALLOC(m->wih_16p[f], 3 * H * E * 2); ALLOC(m->whh_16p[f], 3 * H * H * 2);
+        if (m->kpad) ALLOC(m->wc_16p[f], (int64_t)m->kpad * H * 2);
+    }
     ALLOC(m->xchg, 2 * 4 * H * sizeof(uint2)); ALLOC(m->err_flag, sizeof(int));
 #undef ALLOC
     CUDA_TRY(cudaMemset(m->xchg, 0, 2 * 4 * H * sizeof(uint2)));
@@ -266,7 +468,8 @@ int prego_model_destroy(prego_model_t* m) {
     if (m == nullptr) return PREGO_OK;
     cudaSetDevice(m->device);
     void* ptrs[] = {m->w1_f32, m->b1, m->ln_g, m->ln_b, m->wih_f32p, m->whh_f32p, m->bih_p, m->bhh_p, m->wc_f32, m->bc,
-                    m->w1_bf, m->wih_bfp, m->whh_bfp, m->wc_bfp, m->xchg, m->err_flag};
+                    m->w1_16[0], m->w1_16[1], m->wih_16p[0], m->wih_16p[1], m->whh_16p[0], m->whh_16p[1], m->wc_16p[0],
+                    m->wc_16p[1], m->xchg, m->err_flag};
     for (void* p : ptrs)
         if (p != nullptr) cudaFree(p);
     for (cudaEvent_t e : m->prof_ev)
@@ -276,8 +479,7 @@ int prego_model_destroy(prego_model_t* m) {
 }
 
 int prego_model_load_weights(prego_model_t* m, const prego_weights_t* w, void* stream_) {
-    int rc = check_model(m, false);
-    if (rc != PREGO_OK) return rc;
+    RC_TRY(check_model(m, false));
     if (w == nullptr) return fail(PREGO_ERR_INVALID, "weights is NULL");
     const void* all[] = {w->layer1_0_weight, w->layer1_0_bias, w->layer1_1_weight, w->layer1_1_bias, w->gru_weight_ih_l0,
                          w->gru_weight_hh_l0, w->gru_bias_ih_l0, w->gru_bias_hh_l0, w->f_classification_0_weight,
@@ -299,12 +501,9 @@ int prego_model_load_weights(prego_model_t* m, const prego_weights_t* w, void* s
     pack_rows_f32<<<g((int64_t)3 * H * H), T, 0, s>>>(w->gru_weight_hh_l0, m->whh_f32p, 3 * H, H, H, 1);
     pack_rows_f32<<<g(3 * H), T, 0, s>>>(w->gru_bias_ih_l0, m->bih_p, 3 * H, 1, H, 1);
     pack_rows_f32<<<g(3 * H), T, 0, s>>>(w->gru_bias_hh_l0, m->bhh_p, 3 * H, 1, H, 1);
-    f32_to_bf16<<<g((int64_t)E * din), T, 0, s>>>(w->layer1_0_weight, m->w1_bf, (int64_t)E * din);
-    pack_rows_bf16<<<g((int64_t)3 * H * E), T, 0, s>>>(w->gru_weight_ih_l0, m->wih_bfp, 3 * H, 3 * H, E, H, 1);
-    pack_rows_bf16<<<g((int64_t)3 * H * H), T, 0, s>>>(w->gru_weight_hh_l0, m->whh_bfp, 3 * H, 3 * H, H, H, 1);
-    if (m->kpad)
-        pack_rows_bf16<<<g((int64_t)m->kpad * H), T, 0, s>>>(w->f_classification_0_weight, m->wc_bfp, m->kpad, K, H, H, 0);
-    LAUNCH_CHECK("weight packing");
+    LAUNCH_CHECK("fp32 weight packing");
+    RC_TRY(pack16<0>(m, w, s));
+    RC_TRY(pack16<1>(m, w, s));
     m->loaded = true;
     return PREGO_OK;
 }
@@ -315,16 +514,16 @@ size_t prego_workspace_bytes(const prego_model_t* m, int64_t B, int64_t chunk_T,
 }
 
 int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_) {
-    int rc = check_model(m, true);
-    if (rc != PREGO_OK) return rc;
+    RC_TRY(check_model(m, true));
     if (a == nullptr) return fail(PREGO_ERR_INVALID, "args is NULL");
     const prego_dims_t& d = m->d;
     const int64_t B = a->B, T = a->T;
     if (B <= 0 || T <= 0) return fail(PREGO_ERR_INVALID, "B and T must be positive (got B=%lld, T=%lld)", (long long)B, (long long)T);
     if ((d.d_rgb > 0 && a->rgb == nullptr) || (d.d_flow > 0 && a->flow == nullptr)) return fail(PREGO_ERR_INVALID, "rgb / flow pointer is NULL");
-    if (a->precision != PREGO_PREC_BF16 && a->precision != PREGO_PREC_FP32) return fail(PREGO_ERR_INVALID, "unknown precision %d", a->precision);
-    const bool bf = a->precision == PREGO_PREC_BF16;
-    if (bf && m->kpad == 0) return fail(PREGO_ERR_INVALID, "bf16 path supports num_classes <= 128 (got %d); use PREGO_PREC_FP32", d.num_classes);
+    if (a->precision != PREGO_PREC_BF16 && a->precision != PREGO_PREC_FP32 && a->precision != PREGO_PREC_F16)
+        return fail(PREGO_ERR_INVALID, "unknown precision %d", a->precision);
+    const bool h16 = a->precision != PREGO_PREC_FP32;
+    if (h16 && m->kpad == 0) return fail(PREGO_ERR_INVALID, "16-bit paths support num_classes <= 128 (got %d); use PREGO_PREC_FP32", d.num_classes);
     const int64_t Tc = (a->chunk_T > 0 && a->chunk_T < T) ? a->chunk_T : T;
     if (B * Tc >= (int64_t(1) << 31) / 4) return fail(PREGO_ERR_INVALID, "B * chunk_T = %lld is too large for one pass; lower chunk_T", (long long)(B * Tc));
     const Plan p = make_plan(d, B, Tc, a->precision);
@@ -335,17 +534,9 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     CUDA_TRY(cudaSetDevice(m->device));
     uint8_t* ws = static_cast<uint8_t*>(a->workspace);
-    const int H = d.hidden_dim, E = d.embed_dim, K = d.num_classes, Din = m->din;
+    const int H = d.hidden_dim;
     float* h_cur = reinterpret_cast<float*>(ws + p.h32_a);
     float* h_alt = reinterpret_cast<float*>(ws + p.h32_b);
-    __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + p.xb);
-    void* ye = ws + p.ye;
-    float* gi = reinterpret_cast<float*>(ws + p.gi);
-    __nv_bfloat16* hseq = reinterpret_cast<__nv_bfloat16*>(ws + p.hseq);
-    void* hrelu = ws + p.hrelu;
-    float* gh = reinterpret_cast<float*>(ws + p.gh);
-    float* logits_ws = reinterpret_cast<float*>(ws + p.logits);
-    const bool tensor_rec = B > kLatencyMaxB;
 
     if (a->h_state != nullptr)
         CUDA_TRY(cudaMemcpyAsync(h_cur, a->h_state, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, s));
@@ -354,103 +545,10 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
 
     for (int64_t t0 = 0; t0 < T; t0 += Tc) {
         const int tc = static_cast<int>(T - t0 < Tc ? T - t0 : Tc);
-        const int64_t Mc = B * tc;
-        const int Mi = static_cast<int>(Mc);
         prof_mark(m, s, -1, 0);
-        if (bf) {
-            // 1. stage features: concat + bf16
-            stage_features_bf16<<<grid_for(Mc * (Din / 8), 256, m->sm_count), 256, 0, s>>>(a->rgb, a->flow, xb, Mc, d.d_rgb, d.d_flow, tc, (int)T, (int)t0);
-            LAUNCH_CHECK("stage_features_bf16");
-            prof_mark(m, s, PREGO_PHASE_STAGE, 1);
-            // 2. y = x W1^T + b1   (bf16 out)
-            CUtensorMap tmA, tmB;
-            if ((rc = make_tmap_bf16(&tmA, xb, Din, 1, Mc, Din, Din, kTileM)) != PREGO_OK) return rc;
-            if ((rc = make_tmap_bf16_2d(&tmB, m->w1_bf, Din, E, 256)) != PREGO_OK) return rc;
-            EpiStore<256, __nv_bfloat16> ep1{reinterpret_cast<__nv_bfloat16*>(ye), m->b1, E};
-            if ((rc = launch_gemm_tc<256, 4>(tmA, tmB, Mi, E, Din, 0, ep1, m->sm_count, s, "gemm1")) != PREGO_OK) return rc;
-            prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
-            // 3. e = relu(LN(y))   (in place)
-            layernorm_relu_bf16<2048><<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(
-                reinterpret_cast<const __nv_bfloat16*>(ye), reinterpret_cast<__nv_bfloat16*>(ye), m->ln_g, m->ln_b, Mc, 1e-5f);
-            LAUNCH_CHECK("layernorm_relu_bf16");
-            prof_mark(m, s, PREGO_PHASE_LAYERNORM, 1);
-            // 4. gi = e W_ih'^T + b_ih'  (fp32 out, gate-interleaved columns)
-            if ((rc = make_tmap_bf16(&tmA, ye, E, 1, Mc, E, E, kTileM)) != PREGO_OK) return rc;
-            if ((rc = make_tmap_bf16_2d(&tmB, m->wih_bfp, E, 3 * H, 192)) != PREGO_OK) return rc;
-            EpiStore<192, float> ep2{gi, m->bih_p, 3 * H};
-            if ((rc = launch_gemm_tc<192, 5>(tmA, tmB, Mi, 3 * H, E, 0, ep2, m->sm_count, s, "gemm2")) != PREGO_OK) return rc;
-            prof_mark(m, s, PREGO_PHASE_GEMM2, 1);
-        } else {
-            SgemmA A1{a->rgb, a->flow, d.d_rgb, d.d_rgb, d.d_flow, 1, tc, (int)T, (int)t0};
-            if (d.d_rgb == 0) { A1.a0 = a->flow; A1.a1 = nullptr; A1.k_split = Din; A1.lda0 = d.d_flow; }
-            if (d.d_flow == 0) { A1.a1 = nullptr; A1.k_split = Din; }
-            float* y32 = reinterpret_cast<float*>(ye);
-            sgemm_nt_f32<<<dim3(E / 128, (Mi + 127) / 128), 256, 0, s>>>(A1, m->w1_f32, m->b1, y32, Mi, E, Din, E);
-            LAUNCH_CHECK("sgemm gemm1");
-            prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
-            layernorm_relu_f32<<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(y32, y32, m->ln_g, m->ln_b, Mc, E, 1e-5f);
-            LAUNCH_CHECK("layernorm_relu_f32");
-            prof_mark(m, s, PREGO_PHASE_LAYERNORM, 1);
-            SgemmA A2{y32, nullptr, E, E, 0, 0, tc, (int)T, (int)t0};
-            sgemm_nt_f32<<<dim3(3 * H / 128, (Mi + 127) / 128), 256, 0, s>>>(A2, m->wih_f32p, m->bih_p, gi, Mi, 3 * H, E, 3 * H);
-            LAUNCH_CHECK("sgemm gemm2");
-            prof_mark(m, s, PREGO_PHASE_GEMM2, 1);
-        }
-
-        // 5. recurrence over the tc steps of this chunk
-        if (!tensor_rec) {
-            for (int b0 = 0; b0 < B; b0 += 4) {
-                const int nb = (int)(B - b0 < 4 ? B - b0 : 4);
-                GruLatencyArgs la{m->whh_f32p, m->bhh_p, gi, h_cur, h_alt, hrelu, m->xchg, m->err_flag, H, tc, b0, nb, m->tag_base, bf ? 0 : 1};
-                m->tag_base += static_cast<uint32_t>(tc);
-                if (nb == 1) rc = launch_latency<1>(la, H, s);
-                else if (nb == 2) rc = launch_latency<2>(la, H, s);
-                else rc = launch_latency<4>(la, H, s);
-                if (rc != PREGO_OK) return rc;
-            }
-            float* tmp = h_cur; h_cur = h_alt; h_alt = tmp;
-        } else if (bf) {
-            // slot 0 of the bf16 state history = bf16(carried state); step t reads slot t, writes slot t+1
-            init_hseq_slot0<<<grid_for(B * H, 256, m->sm_count), 256, 0, s>>>(h_cur, hseq, B, H, tc + 1);
-            LAUNCH_CHECK("init_hseq_slot0");
-            CUtensorMap tmA, tmB;
-            if ((rc = make_tmap_bf16(&tmA, hseq, H, tc + 1, B, H, (uint64_t)(tc + 1) * H, kTileM)) != PREGO_OK) return rc;
-            if ((rc = make_tmap_bf16_2d(&tmB, m->whh_bfp, H, 3 * H, 192)) != PREGO_OK) return rc;
-            for (int t = 0; t < tc; ++t) {
-                EpiGruStep eg{gi, m->bhh_p, h_cur, hseq, reinterpret_cast<__nv_bfloat16*>(hrelu), t, tc, H};
-                if ((rc = launch_gemm_tc<192, 5>(tmA, tmB, (int)B, 3 * H, H, t, eg, m->sm_count, s, "gru_step")) != PREGO_OK) return rc;
-            }
-        } else {
-            float* hr32 = reinterpret_cast<float*>(hrelu);
-            for (int t = 0; t < tc; ++t) {
-                SgemmA Ah{h_cur, nullptr, H, H, 0, 0, tc, (int)T, (int)t0};
-                sgemm_nt_f32<<<dim3(3 * H / 128, (int)((B + 127) / 128)), 256, 0, s>>>(Ah, m->whh_f32p, m->bhh_p, gh, (int)B, 3 * H, H, 3 * H);
-                gru_gates_f32<<<grid_for(B * H, 256, m->sm_count), 256, 0, s>>>(gi, gh, h_cur, hr32, (int)B, H, tc, t);
-            }
-            LAUNCH_CHECK("fp32 recurrence");
-        }
-
-        prof_mark(m, s, PREGO_PHASE_RECURRENCE, tensor_rec ? (bf ? tc + 1 : 2 * tc) : (int)((B + 3) / 4));
-        // 6. head
-        if (bf) {
-            CUtensorMap tmA, tmB;
-            if ((rc = make_tmap_bf16(&tmA, hrelu, H, 1, Mc, H, H, kTileM)) != PREGO_OK) return rc;
-            if ((rc = make_tmap_bf16_2d(&tmB, m->wc_bfp, H, m->kpad, m->kpad)) != PREGO_OK) return rc;
-            if (m->kpad == 96) {
-                EpiHead<96> eh{m->bc, a->probs, a->logits, a->labels, K, tc, (int)T, (int)t0};
-                rc = launch_gemm_tc<96, 6>(tmA, tmB, Mi, 96, H, 0, eh, m->sm_count, s, "head96");
-            } else {
-                EpiHead<128> eh{m->bc, a->probs, a->logits, a->labels, K, tc, (int)T, (int)t0};
-                rc = launch_gemm_tc<128, 6>(tmA, tmB, Mi, 128, H, 0, eh, m->sm_count, s, "head128");
-            }
-            if (rc != PREGO_OK) return rc;
-        } else {
-            SgemmA Ah{reinterpret_cast<const float*>(hrelu), nullptr, H, H, 0, 0, tc, (int)T, (int)t0};
-            sgemm_nt_f32<<<dim3((K + 127) / 128, (Mi + 127) / 128), 256, 0, s>>>(Ah, m->wc_f32, m->bc, logits_ws, Mi, K, H, K);
-            softmax_argmax_f32<<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(logits_ws, a->probs, a->logits, a->labels, Mc, K, tc, (int)T, (int)t0);
-            LAUNCH_CHECK("fp32 head");
-        }
-        prof_mark(m, s, PREGO_PHASE_HEAD, bf ? 1 : 2);
+        if (a->precision == PREGO_PREC_F16) RC_TRY(chunk_16<0>(m, a, p, ws, h_cur, h_alt, t0, tc, s));
+        else if (a->precision == PREGO_PREC_BF16) RC_TRY(chunk_16<1>(m, a, p, ws, h_cur, h_alt, t0, tc, s));
+        else RC_TRY(chunk_f32(m, a, p, ws, h_cur, h_alt, t0, tc, s));
     }
     if (a->h_state != nullptr)
         CUDA_TRY(cudaMemcpyAsync(a->h_state, h_cur, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, s));
@@ -458,8 +556,7 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
 }
 
 int prego_profile_begin(prego_model_t* m) {
-    int rc = check_model(m, false);
-    if (rc != PREGO_OK) return rc;
+    RC_TRY(check_model(m, false));
     m->prof = true;
     m->prof_n = 0;
     for (auto& l : m->prof_launches) l = 0;
@@ -467,8 +564,7 @@ int prego_profile_begin(prego_model_t* m) {
 }
 
 int prego_profile_end(prego_model_t* m, double* phase_ms, int64_t* phase_launches) {
-    int rc = check_model(m, false);
-    if (rc != PREGO_OK) return rc;
+    RC_TRY(check_model(m, false));
     if (phase_ms == nullptr || phase_launches == nullptr) return fail(PREGO_ERR_INVALID, "NULL output pointer");
     m->prof = false;
     for (int i = 0; i < PREGO_NUM_PHASES; ++i) {
@@ -515,25 +611,17 @@ int prego_rle(const int32_t* seq, const int64_t* seg_offsets, const int64_t* fin
     return PREGO_OK;
 }
 
-int prego_gemm_bf16_nt(const void* A, const void* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
-                       int32_t tile_n, void* stream) {
+int prego_gemm16_nt(const void* A, const void* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
+                    int32_t tile_n, int32_t precision, void* stream) {
     if (A == nullptr || W == nullptr || bias == nullptr || C == nullptr) return fail(PREGO_ERR_INVALID, "NULL pointer argument");
-    if (M <= 0 || N <= 0 || K <= 0 || K % kTileK != 0 || N % tile_n != 0) return fail(PREGO_ERR_INVALID, "need K %% 64 == 0 and N %% tile_n == 0");
+    if (M <= 0 || N <= 0 || K <= 0 || K % kTileK != 0 || tile_n <= 0 || N % tile_n != 0) return fail(PREGO_ERR_INVALID, "need K %% 64 == 0 and N %% tile_n == 0");
     int dev = 0, sms = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    CUtensorMap tmA, tmB;
-    int rc;
-    if ((rc = make_tmap_bf16(&tmA, A, K, 1, M, K, K, kTileM)) != PREGO_OK) return rc;
-    if ((rc = make_tmap_bf16_2d(&tmB, W, K, N, tile_n)) != PREGO_OK) return rc;
-    switch (tile_n) {
-        case 96: return launch_gemm_tc<96, 6>(tmA, tmB, (int)M, (int)N, (int)K, 0, EpiStore<96, float>{C, bias, N}, sms, s, "gemm96");
-        case 128: return launch_gemm_tc<128, 6>(tmA, tmB, (int)M, (int)N, (int)K, 0, EpiStore<128, float>{C, bias, N}, sms, s, "gemm128");
-        case 192: return launch_gemm_tc<192, 5>(tmA, tmB, (int)M, (int)N, (int)K, 0, EpiStore<192, float>{C, bias, N}, sms, s, "gemm192");
-        case 256: return launch_gemm_tc<256, 4>(tmA, tmB, (int)M, (int)N, (int)K, 0, EpiStore<256, float>{C, bias, N}, sms, s, "gemm256");
-        default: return fail(PREGO_ERR_INVALID, "tile_n must be 96, 128, 192 or 256 (got %d)", tile_n);
-    }
+    if (precision == PREGO_PREC_F16) return gemm16_test<0>(A, W, bias, C, M, N, K, tile_n, sms, s);
+    if (precision == PREGO_PREC_BF16) return gemm16_test<1>(A, W, bias, C, M, N, K, tile_n, sms, s);
+    return fail(PREGO_ERR_INVALID, "precision must be PREGO_PREC_F16 or PREGO_PREC_BF16");
 }
 
 int prego_gemm_f32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,

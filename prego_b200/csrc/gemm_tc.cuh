@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 #include "ptx.cuh"
@@ -43,7 +44,32 @@ struct GemmCfg {
     static constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/; }
 };
 
-template <int TILE_N, int STAGES, class Epi>
+// 16-bit operand formats of tcgen05 kind::f16.  FMT 0 = fp16 (10-bit mantissa, the accuracy of TF32 at
+// twice its rate; features / activations / weights of this model are far inside its range and the
+// converters saturate), FMT 1 = bf16.
+template <int FMT> struct Op16;
+template <> struct Op16<0> {
+    using T = __half;
+    static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+        a = fminf(fmaxf(a, -65504.f), 65504.f);
+        b = fminf(fmaxf(b, -65504.f), 65504.f);
+        __half2 v = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    static __device__ __forceinline__ T from_float(float a) { return __float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f)); }
+    static __device__ __forceinline__ float2 unpack2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+};
+template <> struct Op16<1> {
+    using T = __nv_bfloat16;
+    static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    static __device__ __forceinline__ T from_float(float a) { return __float2bfloat16_rn(a); }
+    static __device__ __forceinline__ float2 unpack2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
+};
+
+template <int TILE_N, int STAGES, int FMT, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                int a_c1, Epi epi) {
@@ -113,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc(1 /*bf16*/, kTileM, TILE_N);
+            constexpr uint32_t idesc = ptx::make_idesc(FMT, kTileM, TILE_N);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -173,19 +199,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ------------------------------------------------------------------ epilogues
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// out[row, n] = acc + bias[n], stored as OutT (float or __nv_bfloat16), row-major with ldc.
-template <int TILE_N, class OutT>
+// out[orow, n] = acc + bias[n].  OUT_FMT: -1 = fp32, 0 = fp16, 1 = bf16.  Row-major with ldc.
+// With Tc > 0 the rows are re-ordered from stream-major (m = b*Tc + t) to time-major (t*B + b),
+// the layout the recurrence consumes.
+template <int TILE_N, int OUT_FMT>
 struct EpiStore {
-    OutT* out;
+    void* out;
     const float* bias;  // [N]
     int64_t ldc;
+    int Tc, B;          // Tc == 0: no re-ordering
 
     __device__ __forceinline__ void operator()(uint32_t taddr, int row, int n0, bool valid) const {
+        const int64_t orow = Tc > 0 ? static_cast<int64_t>(row % Tc) * B + row / Tc : row;
 #pragma unroll 1
         for (int c = 0; c < TILE_N / 32; ++c) {
             uint32_t v[32];
@@ -202,20 +229,20 @@ struct EpiStore {
                 f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
                 f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
             }
-            OutT* dst = out + static_cast<int64_t>(row) * ldc + n0 + c * 32;
-            if constexpr (sizeof(OutT) == 4) {
-                float4* d4 = reinterpret_cast<float4*>(dst);
+            if constexpr (OUT_FMT < 0) {
+                float4* d4 = reinterpret_cast<float4*>(static_cast<float*>(out) + orow * ldc + n0 + c * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) d4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             } else {
-                uint4* d4 = reinterpret_cast<uint4*>(dst);
+                using O = Op16<OUT_FMT>;
+                uint4* d4 = reinterpret_cast<uint4*>(static_cast<typename O::T*>(out) + orow * ldc + n0 + c * 32);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint4 u;
-                    u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                    u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                    u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                    u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                    u.x = O::pack2(f[8 * j + 0], f[8 * j + 1]);
+                    u.y = O::pack2(f[8 * j + 2], f[8 * j + 3]);
+                    u.z = O::pack2(f[8 * j + 4], f[8 * j + 5]);
+                    u.w = O::pack2(f[8 * j + 6], f[8 * j + 7]);
                     d4[j] = u;
                 }
             }
@@ -223,91 +250,17 @@ struct EpiStore {
     }
 };
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-// One GRU time step for a 128-stream x 64-hidden-unit tile.  The accumulator tile is
-// [gh_r(64) | gh_z(64) | gh_n(64)] for hidden units u0 .. u0+63 (gate-interleaved weight
-// packing, see pack.cu).  Gate math follows ATen's order:
-//   r = sigma(gi_r + gh_r + b_hr), z = sigma(gi_z + gh_z + b_hz),
-//   n = tanh(gi_n + r * (gh_n + b_hn)),  h' = (h - n) * z + n.
-struct EpiGruStep {
-    const float* gi;         // [B*Tc, 3H] gate pre-activations (packed column order, b_ih folded in)
-    const float* bhh;        // [3H] packed order
-    float* h32;              // [B, H] fp32 master state (in/out)
-    __nv_bfloat16* hseq;     // [B, Tc+1, H] bf16 state history; slot t is this step's operand, t+1 its result
-    __nv_bfloat16* hrelu;    // [B*Tc, H] bf16 relu(h_t), operand of the classifier head
-    int t, Tc, H;
-
-    __device__ __forceinline__ void operator()(uint32_t taddr, int row, int n0, bool valid) const {
-        const int u0 = (n0 / 192) * 64;
-        const int64_t grow = static_cast<int64_t>(row) * Tc + t;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            uint32_t vr[16], vz[16], vn[16];
-            ptx::tmem_ld16(taddr + c * 16, vr);
-            ptx::tmem_ld16(taddr + 64 + c * 16, vz);
-            ptx::tmem_ld16(taddr + 128 + c * 16, vn);
-            ptx::tmem_ld_wait();
-            if (!valid) continue;
-            const float* gi_p = gi + grow * (3 * H) + n0 + c * 16;
-            const float* bh_p = bhh + n0 + c * 16;
-            float* h_p = h32 + static_cast<int64_t>(row) * H + u0 + c * 16;
-            float hn[16];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 gr = *reinterpret_cast<const float4*>(gi_p + 4 * q);
-                const float4 gz = *reinterpret_cast<const float4*>(gi_p + 64 + 4 * q);
-                const float4 gn = *reinterpret_cast<const float4*>(gi_p + 128 + 4 * q);
-                const float4 br = __ldg(reinterpret_cast<const float4*>(bh_p + 4 * q));
-                const float4 bz = __ldg(reinterpret_cast<const float4*>(bh_p + 64 + 4 * q));
-                const float4 bn = __ldg(reinterpret_cast<const float4*>(bh_p + 128 + 4 * q));
-                const float4 hp = *reinterpret_cast<const float4*>(h_p + 4 * q);
-                const float g_r[4] = {gr.x, gr.y, gr.z, gr.w}, g_z[4] = {gz.x, gz.y, gz.z, gz.w},
-                            g_n[4] = {gn.x, gn.y, gn.z, gn.w};
-                const float b_r[4] = {br.x, br.y, br.z, br.w}, b_z[4] = {bz.x, bz.y, bz.z, bz.w},
-                            b_n[4] = {bn.x, bn.y, bn.z, bn.w};
-                const float h_o[4] = {hp.x, hp.y, hp.z, hp.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = 4 * q + j;
-                    const float r = sigmoid_f(g_r[j] + (__uint_as_float(vr[i]) + b_r[j]));
-                    const float z = sigmoid_f(g_z[j] + (__uint_as_float(vz[i]) + b_z[j]));
-                    const float n = tanhf(g_n[j] + r * (__uint_as_float(vn[i]) + b_n[j]));
-                    hn[i] = (h_o[j] - n) * z + n;
-                }
-                *reinterpret_cast<float4*>(h_p + 4 * q) = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
-            }
-            uint4 a, b, ra, rb;
-            a.x = pack_bf16x2(hn[0], hn[1]);   a.y = pack_bf16x2(hn[2], hn[3]);
-            a.z = pack_bf16x2(hn[4], hn[5]);   a.w = pack_bf16x2(hn[6], hn[7]);
-            b.x = pack_bf16x2(hn[8], hn[9]);   b.y = pack_bf16x2(hn[10], hn[11]);
-            b.z = pack_bf16x2(hn[12], hn[13]); b.w = pack_bf16x2(hn[14], hn[15]);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) hn[i] = fmaxf(hn[i], 0.0f);
-            ra.x = pack_bf16x2(hn[0], hn[1]);   ra.y = pack_bf16x2(hn[2], hn[3]);
-            ra.z = pack_bf16x2(hn[4], hn[5]);   ra.w = pack_bf16x2(hn[6], hn[7]);
-            rb.x = pack_bf16x2(hn[8], hn[9]);   rb.y = pack_bf16x2(hn[10], hn[11]);
-            rb.z = pack_bf16x2(hn[12], hn[13]); rb.w = pack_bf16x2(hn[14], hn[15]);
-            uint4* hs = reinterpret_cast<uint4*>(hseq + (static_cast<int64_t>(row) * (Tc + 1) + t + 1) * H + u0 + c * 16);
-            hs[0] = a;
-            hs[1] = b;
-            uint4* hr = reinterpret_cast<uint4*>(hrelu + grow * H + u0 + c * 16);
-            hr[0] = ra;
-            hr[1] = rb;
-        }
-    }
-};
-
 // Classifier head epilogue: logits = acc + bc; probs = softmax(logits); label = first
-// index of max(probs) (numpy argmax semantics of trainer/eval.py:53).  TILE_N = 96..256
-// padded class count; only the first K columns are real.
+// index of max(probs) (numpy argmax semantics of trainer/eval.py:53).  TILE_N = padded class
+// count; only the first K columns are real.  Input rows are time-major (m = t*B + b); outputs go
+// to the caller's [B, T, .] tensors.
 template <int TILE_N>
 struct EpiHead {
     const float* bias;  // [K]
     float* probs;       // [B, T, K] or nullptr
     float* logits;      // [B, T, K] or nullptr
     int32_t* labels;    // [B, T] or nullptr
-    int K, Tc, T, t0;
+    int K, B, T, t0;
 
     __device__ __forceinline__ void operator()(uint32_t taddr, int row, int /*n0*/, bool valid) const {
         float v[TILE_N];
@@ -320,7 +273,7 @@ struct EpiHead {
             for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(u[j]);
         }
         if (!valid) return;
-        const int64_t g = static_cast<int64_t>(row / Tc) * T + t0 + (row % Tc);
+        const int64_t g = static_cast<int64_t>(row % B) * T + t0 + (row / B);
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < TILE_N; ++j) {

@@ -29,17 +29,19 @@ constexpr int kLatThreads = kLatUnitsPerCta * 32;
 struct GruLatencyArgs {
     const float* whh;      // [3H, H] fp32, packed gate-interleaved row order
     const float* bhh;      // [3H] packed order
-    const float* gi;       // [B*Tc, 3H] fp32 packed column order (b_ih folded in)
+    const float* gi;       // fp32 gate pre-activations, packed column order (b_ih folded in);
+                           // row of (stream b, step t) = b * row_sb + t * row_st
     const float* h_in;     // [B, H] state before the first step of this launch
     float* h_out;          // [B, H] state after the last step (must not alias h_in)
-    void* hrelu;           // [B*Tc, H] relu(h_t): bf16 or fp32 (out_f32)
+    void* hrelu;           // relu(h_t), same row indexing; fp32 / fp16 / bf16 (out_fmt -1 / 0 / 1)
     uint2* xchg;           // [2][NB][H] tagged exchange words
     int* err_flag;         // set to 1 on spin timeout
     int H, Tc;
     int b0;                // first stream of this pass
     int nb;                // streams in this pass (<= NB)
     uint32_t tag_base;     // tags used: tag_base + 1 .. tag_base + Tc
-    int out_f32;
+    int out_fmt;
+    int64_t row_sb, row_st;
 };
 
 template <int NB>
@@ -69,7 +71,7 @@ gru_latency_kernel(GruLatencyArgs a) {
         // gate pre-activations of this step (independent of h: issue before polling)
         float gv[3] = {0.f, 0.f, 0.f};
         if (lane < a.nb) {
-            const float* gp = a.gi + (static_cast<int64_t>(a.b0 + lane) * a.Tc + t) * (3 * H) + pcol;
+            const float* gp = a.gi + ((a.b0 + lane) * a.row_sb + t * a.row_st) * (3 * H) + pcol;
             gv[0] = __ldcs(gp);
             gv[1] = __ldcs(gp + 64);
             gv[2] = __ldcs(gp + 128);
@@ -157,9 +159,11 @@ gru_latency_kernel(GruLatencyArgs a) {
             const float hn = (hp - n) * z + n;
             ptx::st_volatile_u64(a.xchg + ((t & 1) * NB + lane) * H + u, __float_as_uint(hn),
                                  a.tag_base + static_cast<uint32_t>(t) + 1u);
-            const int64_t orow = static_cast<int64_t>(a.b0 + lane) * a.Tc + t;
-            if (a.out_f32)
+            const int64_t orow = (a.b0 + lane) * a.row_sb + t * a.row_st;
+            if (a.out_fmt < 0)
                 reinterpret_cast<float*>(a.hrelu)[orow * H + u] = fmaxf(hn, 0.f);
+            else if (a.out_fmt == 0)
+                reinterpret_cast<__half*>(a.hrelu)[orow * H + u] = __float2half_rn(fmaxf(hn, 0.f));
             else
                 reinterpret_cast<__nv_bfloat16*>(a.hrelu)[orow * H + u] = __float2bfloat16_rn(fmaxf(hn, 0.f));
             if (t == a.Tc - 1) a.h_out[static_cast<int64_t>(a.b0 + lane) * H + u] = hn;

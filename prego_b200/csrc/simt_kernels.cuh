@@ -6,7 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
-#include "gemm_tc.cuh"  // pack_bf16x2, sigmoid_f
+#include "gemm_tc.cuh"  // Op16, sigmoid_f
 
 namespace prego {
 
@@ -19,9 +19,11 @@ __device__ __forceinline__ int64_t chunk_row_to_global(int64_t m, int Tc, int T,
 // Feature staging (replaces torch.cat of rnn.py:53 and the fp32->bf16 operand rounding):
 //   xb[m, 0:Dr] = bf16(rgb[b, t0+tt, :]),  xb[m, Dr:Dr+Df] = bf16(flow[b, t0+tt, :])
 // One thread converts 8 consecutive elements (2 x 16 B loads -> one 16 B store).
+template <int FMT>
 __global__ void __launch_bounds__(256)
-stage_features_bf16(const float* __restrict__ rgb, const float* __restrict__ flow, __nv_bfloat16* __restrict__ xb,
-                    int64_t Mc, int Dr, int Df, int Tc, int T, int t0) {
+stage_features_16(const float* __restrict__ rgb, const float* __restrict__ flow, typename Op16<FMT>::T* __restrict__ xb,
+                  int64_t Mc, int Dr, int Df, int Tc, int T, int t0) {
+    using Op = Op16<FMT>;
     const int D = Dr + Df;
     const int vec_per_row = D / 8;
     const int64_t total = Mc * vec_per_row;
@@ -34,10 +36,10 @@ stage_features_bf16(const float* __restrict__ rgb, const float* __restrict__ flo
         const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
         const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 1);
         uint4 o;
-        o.x = pack_bf16x2(a.x, a.y);
-        o.y = pack_bf16x2(a.z, a.w);
-        o.z = pack_bf16x2(b.x, b.y);
-        o.w = pack_bf16x2(b.z, b.w);
+        o.x = Op::pack2(a.x, a.y);
+        o.y = Op::pack2(a.z, a.w);
+        o.z = Op::pack2(b.x, b.y);
+        o.w = Op::pack2(b.z, b.w);
         *reinterpret_cast<uint4*>(xb + m * D + c) = o;
     }
 }
@@ -46,10 +48,12 @@ stage_features_bf16(const float* __restrict__ rgb, const float* __restrict__ flo
 // LayerNorm (biased variance, eps inside the sqrt) + ReLU over rows of width E
 // (rnn.py:41-42).  One warp per row, the row lives in registers; two-pass variance.
 // In-place safe (each warp reads its whole row before writing).
-template <int E>
+// y is stored as fp16 (pre-activation, |y| = O(1..10)); e is written in the operand format FMT.
+template <int E, int FMT>
 __global__ void __launch_bounds__(256)
-layernorm_relu_bf16(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ e, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, int64_t M, float eps) {
+layernorm_relu_16(const __half* __restrict__ y, typename Op16<FMT>::T* __restrict__ e, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, int64_t M, float eps) {
+    using Op = Op16<FMT>;
     constexpr int kVec = E / (32 * 8);  // 16-byte vectors per lane
     const int lane = threadIdx.x & 31;
     const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -63,10 +67,10 @@ layernorm_relu_bf16(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restri
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-                v[i * 8 + 2 * j] = __low2float(p);
-                v[i * 8 + 2 * j + 1] = __high2float(p);
-                sum += v[i * 8 + 2 * j] + v[i * 8 + 2 * j + 1];
+                const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+                v[i * 8 + 2 * j] = p.x;
+                v[i * 8 + 2 * j + 1] = p.y;
+                sum += p.x + p.y;
             }
         }
 #pragma unroll
@@ -95,10 +99,10 @@ layernorm_relu_bf16(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restri
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = fmaxf((v[i * 8 + j] - mu) * rstd * gg[j] + bb[j], 0.0f);
             uint4 u;
-            u.x = pack_bf16x2(o[0], o[1]);
-            u.y = pack_bf16x2(o[2], o[3]);
-            u.z = pack_bf16x2(o[4], o[5]);
-            u.w = pack_bf16x2(o[6], o[7]);
+            u.x = Op::pack2(o[0], o[1]);
+            u.y = Op::pack2(o[2], o[3]);
+            u.z = Op::pack2(o[4], o[5]);
+            u.w = Op::pack2(o[6], o[7]);
             dst[i * 32 + lane] = u;
         }
     }
@@ -334,33 +338,24 @@ __global__ void pack_rows_f32(const float* __restrict__ src, float* __restrict__
 }
 
 // dst rows beyond src_rows are zero (class padding of the head weight).
-__global__ void pack_rows_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int src_rows,
-                               int cols, int H, int permute) {
+template <int FMT>
+__global__ void pack_rows_16(const float* __restrict__ src, typename Op16<FMT>::T* __restrict__ dst, int rows,
+                             int src_rows, int cols, int H, int permute) {
     const int64_t total = static_cast<int64_t>(rows) * cols;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int p = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
         const int r = permute ? packed_to_orig_row(p, H) : p;
-        dst[i] = __float2bfloat16_rn(r < src_rows ? src[static_cast<int64_t>(r) * cols + c] : 0.f);
+        dst[i] = Op16<FMT>::from_float(r < src_rows ? src[static_cast<int64_t>(r) * cols + c] : 0.f);
     }
 }
 
-// hseq[b, 0, :] = bf16(h32[b, :]) : seeds slot 0 of the bf16 state history [B, slots, H].
-__global__ void init_hseq_slot0(const float* __restrict__ h32, __nv_bfloat16* __restrict__ hseq, int64_t B, int H,
-                                int slots) {
-    const int64_t total = B * H;
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int64_t b = i / H;
-        const int k = static_cast<int>(i % H);
-        hseq[(b * slots) * H + k] = __float2bfloat16_rn(h32[i]);
-    }
-}
-
-__global__ void f32_to_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+// Plain fp32 -> 16-bit operand conversion (weights; slot 0 of the state history = carried h).
+template <int FMT>
+__global__ void f32_to_16(const float* __restrict__ src, typename Op16<FMT>::T* __restrict__ dst, int64_t n) {
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-        dst[i] = __float2bfloat16_rn(src[i]);
+        dst[i] = Op16<FMT>::from_float(src[i]);
 }
 
 }  // namespace prego

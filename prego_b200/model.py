@@ -47,7 +47,7 @@ _STATE_KEYS = (
 
 @META_ARCHITECTURES.register("MiniROAD")
 class MROAD(nn.Module):
-    """B200-native MiniROAD.  Extra (optional) cfg keys: ``precision`` ('bf16' | 'fp32'),
+    """B200-native MiniROAD.  Extra (optional) cfg keys: ``precision`` ('fp16' default | 'bf16' | 'fp32'),
     ``chunk_frames`` (frames per pass over all streams; bounds the workspace)."""
 
     def __init__(self, cfg):
@@ -75,7 +75,7 @@ class MROAD(nn.Module):
         self.f_classification = nn.Sequential(nn.Linear(self.hidden_dim, self.out_dim))
         self.h0 = torch.zeros(self.num_layers, 1, self.hidden_dim)  # rnn.py:49 (not in state_dict)
 
-        self.precision = cfg.get("precision", "bf16")
+        self.precision = cfg.get("precision", "fp16")
         self.chunk_frames = int(cfg.get("chunk_frames", 1 << 17))
         self._handle = None
         self._handle_device = None

@@ -12,9 +12,9 @@ run() {  # name, timeout, pytest -k expr
     echo "rc=$rc $(tail -n 1 gpurun_out/ci_$1.log)" | tee -a gpurun_out/ci_summary.txt
 }
 : > gpurun_out/ci_summary.txt
-run gemm_tc 300 "gemm_bf16"
+run gemm_tc 300 "gemm16"
 run simt 300 "gemm_f32 or forward_fp32"
 run aggregate 300 "aggregate"
-run bf16 400 "forward_bf16 or chunking or carried or single_frame or big_batch or module_forward or evaluate"
+run bf16 400 "forward_bf16 or forward_fp16 or chunking or carried or single_frame or big_batch or module_forward or evaluate"
 run fullsize 400 "full_size"
 cat gpurun_out/ci_summary.txt
