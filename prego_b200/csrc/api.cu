@@ -277,10 +277,10 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     CUtensorMap tmA, tmB;
 
     // 1. stage features: concat + operand rounding (replaces torch.cat, rnn.py:53)
-    stage_features_16<FMT><<<grid_for(Mc * (Din / 8), 256, m->sm_count), 256, 0, s>>>(a->rgb, a->flow, xb, Mc, d.d_rgb, d.d_flow, tc, (int)T, (int)t0);
+    stage_features_16<FMT><<<grid_for(Mc * (Din / 8), 256, m->sm_count), 256, 0, s>>>(a->rgb, a->flow, xb, Mc, d.d_rgb, d.d_flow, (int)B, (int)T, (int)t0);
     LAUNCH_CHECK("stage_features_16");
     prof_mark(m, s, PREGO_PHASE_STAGE, 1);
-    // 2. y = x W1^T + b1  (fp16 out, stream-major rows)
+    // 2. y = x W1^T + b1  (fp16 out; rows stay time-major, m = t*B + b)
     RC_TRY(make_tmap_a(&tmA, dt, xb, Din, Mc));
     RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 256));
     RC_TRY((launch_gemm_tc<256, 4, FMT>(tmA, tmB, Mi, E, Din, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1")));
@@ -290,13 +290,13 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
         reinterpret_cast<const __half*>(ye), reinterpret_cast<OpT*>(ye), m->ln_g, m->ln_b, Mc, 1e-5f);
     LAUNCH_CHECK("layernorm_relu_16");
     prof_mark(m, s, PREGO_PHASE_LAYERNORM, 1);
-    // 4. gi = e W_ih'^T + b_ih'  (gate-interleaved columns, rows re-ordered to time-major)
+    // 4. gi = e W_ih'^T + b_ih'  (gate-interleaved columns, time-major rows)
     RC_TRY(make_tmap_a(&tmA, dt, ye, E, Mc));
     RC_TRY(make_tmap_w(&tmB, dt, m->wih_16p[FMT], E, 3 * H, 192));
     if (batched)
-        RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, 0>{gi, m->bih_p, 3 * H, tc, (int)B}, m->sm_count, s, "gemm2")));
+        RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, 0>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2")));
     else
-        RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, -1>{gi, m->bih_p, 3 * H, tc, (int)B}, m->sm_count, s, "gemm2")));
+        RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, -1>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2")));
     prof_mark(m, s, PREGO_PHASE_GEMM2, 1);
 
     // 5. recurrence

@@ -17,12 +17,14 @@ __device__ __forceinline__ int64_t chunk_row_to_global(int64_t m, int Tc, int T,
 
 // ---------------------------------------------------------------------------------------
 // Feature staging (replaces torch.cat of rnn.py:53 and the fp32->bf16 operand rounding):
-//   xb[m, 0:Dr] = bf16(rgb[b, t0+tt, :]),  xb[m, Dr:Dr+Df] = bf16(flow[b, t0+tt, :])
-// One thread converts 8 consecutive elements (2 x 16 B loads -> one 16 B store).
+//   xb[m, 0:Dr] = op16(rgb[b, t0+t, :]),  xb[m, Dr:Dr+Df] = op16(flow[b, t0+t, :]),  m = t*B + b
+// Rows are written TIME-MAJOR inside the chunk so that every later stage (both projections, the
+// per-step recurrence tiles) touches contiguous rows.  One thread converts 8 consecutive elements
+// (2 x 16 B loads -> one 16 B store).
 template <int FMT>
 __global__ void __launch_bounds__(256)
 stage_features_16(const float* __restrict__ rgb, const float* __restrict__ flow, typename Op16<FMT>::T* __restrict__ xb,
-                  int64_t Mc, int Dr, int Df, int Tc, int T, int t0) {
+                  int64_t Mc, int Dr, int Df, int B, int T, int t0) {
     using Op = Op16<FMT>;
     const int D = Dr + Df;
     const int vec_per_row = D / 8;
@@ -31,7 +33,7 @@ stage_features_16(const float* __restrict__ rgb, const float* __restrict__ flow,
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t m = i / vec_per_row;
         const int c = static_cast<int>(i % vec_per_row) * 8;
-        const int64_t g = chunk_row_to_global(m, Tc, T, t0);
+        const int64_t g = (m % B) * static_cast<int64_t>(T) + t0 + (m / B);
         const float* src = (c < Dr) ? (rgb + g * Dr + c) : (flow + g * Df + (c - Dr));
         const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
         const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 1);
