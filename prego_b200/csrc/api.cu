@@ -303,15 +303,10 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     if (batched) {
         f32_to_16<FMT><<<grid_for(B * H, 256, m->sm_count), 256, 0, s>>>(h_cur, hseq, B * H);  // history slot 0 = carried state
         LAUNCH_CHECK("f32_to_16 (hseq slot 0)");
-        CUtensorMap tmHseq, tmW, tmGi, tmH32, tmHrelu;
+        CUtensorMap tmHseq, tmW, tmGi, tmHrelu;
         RC_TRY(make_tmap_tm(&tmHseq, dt, hseq, H, B, tc + 1, 2));
         RC_TRY(make_tmap_w(&tmW, dt, m->whh_16p[FMT], H, 3 * H, kGruTileN));
         RC_TRY(make_tmap_tm(&tmGi, kF16, gi, 3 * H, B, tc, 2));
-        {
-            const uint64_t dims[2] = {(uint64_t)H, (uint64_t)B}, str[1] = {(uint64_t)H * 4};
-            const uint32_t box[2] = {32, kTileM};
-            RC_TRY(make_tmap(&tmH32, kF32, 2, h_cur, dims, str, box));
-        }
         RC_TRY(make_tmap_tm(&tmHrelu, dt, hrelu, H, B, tc, 2));
         auto kfn = gru_step_kernel<FMT>;
         static bool attr_set = false;
@@ -322,7 +317,7 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
         const int tiles = (3 * H / kGruTileN) * (int)((B + kTileM - 1) / kTileM);
         const int grid = tiles < m->sm_count ? tiles : m->sm_count;
         for (int t = 0; t < tc; ++t)
-            kfn<<<grid, kGruThreads, kGruSmemBytes, s>>>(tmHseq, tmW, tmGi, tmH32, tmHrelu, m->bhh_p, (int)B, H, t);
+            kfn<<<grid, kGruThreads, kGruSmemBytes, s>>>(tmHseq, tmW, tmGi, tmHrelu, m->bhh_p, h_cur, (int)B, H, t);
         LAUNCH_CHECK("gru_step_kernel");
         prof_mark(m, s, PREGO_PHASE_RECURRENCE, tc + 1);
     } else {

@@ -4,14 +4,17 @@
 //   r = sigma(gi_r + gh_r + b_hr),  z = sigma(gi_z + gh_z + b_hz)
 //   n = tanh(gi_n + r * (gh_n + b_hn)),  h_t = (h_{t-1} - n) * z + n       (ATen's order)
 //
-// fused in one persistent kernel.  Every byte the epilogue touches moves by TMA: the gate
-// pre-activations gi[t] (fp16, 3 x [128 x 64] boxes) and the fp32 master state (2 x [128 x 32]
-// boxes) are bulk-loaded into swizzled shared memory by a dedicated producer warp while the
-// tensor core works on the tile, and the three results -- fp32 state (in place), the 16-bit
-// operand copy of h_t for the next step (history slot t+1) and relu(h_t) for the classifier --
-// leave through TMA stores.  No epilogue thread issues a global load or store, so the step is
-// not exposed to DRAM latency (the first version, with per-thread global accesses, spent 74 %
-// of its samples in long-scoreboard stalls: profiles/r01_gru_step_v1_ncu.txt).
+// fused in one persistent kernel.  The epilogue never waits on DRAM:
+//   * the gate pre-activations gi[t] of a tile (3 fp16 boxes of [128 x 64]) are bulk-loaded by TMA into a
+//     DOUBLE-BUFFERED swizzled shared-memory area by a dedicated warp, two tiles ahead of their use;
+//   * the fp32 master state of the NEXT tile is prefetched into registers while the current tile is
+//     being computed;
+//   * the 16-bit operand copy of h_t (history slot t+1, the next step's MMA operand) and relu(h_t) (the
+//     classifier's operand) are written over the consumed gi boxes and leave through TMA stores issued by
+//     the same dedicated warp; the fp32 state is stored straight from registers.
+// History: v1 (per-thread global loads in the epilogue) 292 us/step, 74 % long-scoreboard stalls; v2
+// (single-buffered TMA operands) 43 us/step with the epilogue waiting on its operand load for 24 % of the
+// samples; this is v3.  See profiles/r01_ncu_full_summary.txt.
 //
 // Layouts (time-major inside a chunk so one step touches contiguous rows):
 //   hseq  [Tc+1, B, H]  16-bit operand history, slot t = h_{t-1}
@@ -19,8 +22,9 @@
 //   hrelu [Tc,   B, H]  16-bit relu(h_t)
 //   h32   [B, H]        fp32 master state
 //
-// Warp roles (224 threads): warp 0 = operand TMA producer, warp 1 = TMEM alloc + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quadrant = warp % 4), warp 6 = epilogue-operand TMA producer.
+// Warp roles (352 threads): warp 0 = operand TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp % 4; warps 2-5 take hidden units 0-31 of the tile,
+// warps 6-9 units 32-63), warp 10 = gi loader + result storer.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -32,13 +36,14 @@
 
 namespace prego {
 
-constexpr int kGruThreads = 224;
+constexpr int kGruThreads = 352;
+constexpr int kGruEpiWarps = 8;
 constexpr int kGruTileN = 192;
 constexpr int kGruStages = 3;
 constexpr int kGruStageBytes = kTileM * kTileK * 2 + kGruTileN * kTileK * 2;  // 40960
 constexpr int kGruBoxBytes = 128 * 128;                                       // one [128 rows x 128 B] box
-constexpr int kGruEpiBytes = 5 * kGruBoxBytes;                                // gi r,z,n + h32 lo,hi
-constexpr int kGruSmemBytes = kGruStages * kGruStageBytes + kGruEpiBytes + 256 + 1024;
+constexpr int kGruGiBytes = 3 * kGruBoxBytes;                                 // gi r, z, n of one tile
+constexpr int kGruSmemBytes = kGruStages * kGruStageBytes + 2 * kGruGiBytes + 256 + 1024;
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
@@ -57,21 +62,20 @@ __global__ void __launch_bounds__(kGruThreads, 1)
 gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1) 16-bit, box (64, 128, 1)
                 const __grid_constant__ CUtensorMap tmW,      // 2-D (H, 3H) 16-bit, box (64, 192)
                 const __grid_constant__ CUtensorMap tmGi,     // 3-D (3H, B, Tc) fp16, box (64, 128, 1)
-                const __grid_constant__ CUtensorMap tmH32,    // 2-D (H, B) fp32, box (32, 128)
                 const __grid_constant__ CUtensorMap tmHrelu,  // 3-D (H, B, Tc) 16-bit, box (64, 128, 1)
-                const float* __restrict__ bhh, int B, int H, int t) {
+                const float* __restrict__ bhh, float* __restrict__ h32, int B, int H, int t) {
     using Op = Op16<FMT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* epi_smem = smem + kGruStages * kGruStageBytes;  // gi_r, gi_z, gi_n, h_lo, h_hi boxes
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kGruEpiBytes);
-    uint64_t* full_bar = bars;                        // [3]
-    uint64_t* empty_bar = bars + kGruStages;          // [3]
-    uint64_t* acc_full = bars + 2 * kGruStages;       // [2]
-    uint64_t* acc_empty = bars + 2 * kGruStages + 2;  // [2]
-    uint64_t* epi_full = bars + 2 * kGruStages + 4;   // [1]
-    uint64_t* epi_empty = bars + 2 * kGruStages + 5;  // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGruStages + 6);
+    uint8_t* gi_smem = smem + kGruStages * kGruStageBytes;  // [2][3] boxes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gi_smem + 2 * kGruGiBytes);
+    uint64_t* full_bar = bars;                        // [3]  operand stage landed
+    uint64_t* empty_bar = bars + kGruStages;          // [3]  operand stage consumed
+    uint64_t* acc_full = bars + 2 * kGruStages;       // [2]  accumulator complete
+    uint64_t* acc_empty = bars + 2 * kGruStages + 2;  // [2]  accumulator drained
+    uint64_t* gi_full = bars + 2 * kGruStages + 4;    // [2]  gi boxes landed
+    uint64_t* res_ready = bars + 2 * kGruStages + 6;  // [2]  results written over the gi boxes
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGruStages + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -84,7 +88,6 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
         ptx::prefetch_tmap(&tmHseq);
         ptx::prefetch_tmap(&tmW);
         ptx::prefetch_tmap(&tmGi);
-        ptx::prefetch_tmap(&tmH32);
         ptx::prefetch_tmap(&tmHrelu);
         for (int s = 0; s < kGruStages; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
@@ -92,10 +95,10 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
         }
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(&acc_full[b], 1);
-            ptx::mbar_init(&acc_empty[b], 4);
+            ptx::mbar_init(&acc_empty[b], kGruEpiWarps);
+            ptx::mbar_init(&gi_full[b], 1);
+            ptx::mbar_init(&res_ready[b], kGruEpiWarps);
         }
-        ptx::mbar_init(epi_full, 1);
-        ptx::mbar_init(epi_empty, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -108,6 +111,7 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        // ---------------------------------------------------------------- operand producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -128,6 +132,7 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
             }
         }
     } else if (warp == 1) {
+        // -------------------------------------------------------------------- MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc(FMT, kTileM, kGruTileN);
             int stage = 0, it = 0;
@@ -155,56 +160,100 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
                 ptx::mma_commit(&acc_full[buf]);
             }
         }
-    } else if (warp == 6) {
-        // ------------------------------------------- epilogue-operand producer (gi[t] + fp32 state)
+    } else if (warp == 10) {
+        // ------------------------------- gi loader (two tiles ahead) + result storer (TMA both ways)
         if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int m0 = (tile / n_tiles) * kTileM;
-                const int nt = tile % n_tiles;
-                ptx::mbar_wait(epi_empty, (it & 1) ^ 1);
-                ptx::mbar_expect_tx(epi_full, kGruEpiBytes);
+                const int p = it & 1;
+                uint8_t* box = gi_smem + p * kGruGiBytes;
+                if (it >= 2) {
+                    // results of tile it-2 sit in this buffer: store them, then the buffer is free
+                    const int ptile = tile - 2 * gridDim.x;
+                    const int pm0 = (ptile / n_tiles) * kTileM, pnt = ptile % n_tiles;
+                    ptx::mbar_wait(&res_ready[p], ((it - 2) >> 1) & 1);
+                    ptx::tma_store_3d(&tmHseq, box, pnt * 64, pm0, t + 1);
+                    ptx::tma_store_3d(&tmHrelu, box + kGruBoxBytes, pnt * 64, pm0, t);
+                    ptx::tma_store_commit();
+                    ptx::tma_store_wait_read();
+                }
+                const int m0 = (tile / n_tiles) * kTileM, nt = tile % n_tiles;
+                ptx::mbar_expect_tx(&gi_full[p], kGruGiBytes);
 #pragma unroll
                 for (int g = 0; g < 3; ++g)
-                    ptx::tma_load_3d(&tmGi, epi_smem + g * kGruBoxBytes, epi_full, nt * kGruTileN + g * 64, m0, t, ptx::kEvictFirst);
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    ptx::tma_load_2d(&tmH32, epi_smem + (3 + j) * kGruBoxBytes, epi_full, nt * 64 + j * 32, m0, ptx::kEvictNormal);
+                    ptx::tma_load_3d(&tmGi, box + g * kGruBoxBytes, &gi_full[p], nt * kGruTileN + g * 64, m0, t, ptx::kEvictFirst);
             }
+            // drain: the last (up to) two tiles
+            const int n_mine = it;
+            for (int j = (n_mine >= 2 ? n_mine - 2 : 0); j < n_mine; ++j) {
+                const int p = j & 1;
+                const int ptile = blockIdx.x + j * gridDim.x;
+                const int pm0 = (ptile / n_tiles) * kTileM, pnt = ptile % n_tiles;
+                uint8_t* box = gi_smem + p * kGruGiBytes;
+                ptx::mbar_wait(&res_ready[p], (j >> 1) & 1);
+                ptx::tma_store_3d(&tmHseq, box, pnt * 64, pm0, t + 1);
+                ptx::tma_store_3d(&tmHrelu, box + kGruBoxBytes, pnt * 64, pm0, t);
+                ptx::tma_store_commit();
+            }
+            ptx::tma_store_wait_all();
         }
     } else {
         // -------------------------------------------------------------------------- epilogue
         const int quad = warp & 3;
-        const int r = quad * 32 + lane;  // row of the tile = TMEM lane
+        const int half = (warp - 2) >> 2;  // which 32 hidden units of the tile
+        const int r = quad * 32 + lane;    // row of the tile = TMEM lane
         const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
         const uint32_t sw = static_cast<uint32_t>(r & 7);
-        const uint32_t s_gi = ptx::smem_u32(epi_smem);
-        const bool store_thread = (warp == 2 && lane == 0);
+        const uint32_t s_gi = ptx::smem_u32(gi_smem);
+
+        // fp32 state of the first tile -> registers
+        float4 hnext[8];
+        {
+            const int tile = blockIdx.x;
+            if (tile < total_tiles) {
+                const int row = (tile / n_tiles) * kTileM + r;
+                const float4* src = reinterpret_cast<const float4*>(h32 + static_cast<int64_t>(row) * H + (tile % n_tiles) * 64 + half * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hnext[i] = row < B ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
+            const uint32_t par = (it >> 1) & 1;
             const int m0 = (tile / n_tiles) * kTileM;
             const int nt = tile % n_tiles;
-            ptx::mbar_wait(epi_full, it & 1);
-            ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            const int row = m0 + r;
+            float4 hcur[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hcur[i] = hnext[i];
+            {   // prefetch the next tile's state while this one is computed
+                const int ntile = tile + gridDim.x;
+                if (ntile < total_tiles) {
+                    const int nrow = (ntile / n_tiles) * kTileM + r;
+                    const float4* src = reinterpret_cast<const float4*>(h32 + static_cast<int64_t>(nrow) * H + (ntile % n_tiles) * 64 + half * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) hnext[i] = nrow < B ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            ptx::mbar_wait(&gi_full[buf], par);
+            ptx::mbar_wait(&acc_full[buf], par);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + buf * 256 + (static_cast<uint32_t>(quad * 32) << 16);
+            const uint32_t s_box = s_gi + buf * kGruGiBytes + row_off;
             const float* bh = bhh + nt * kGruTileN;
-#pragma unroll 1
-            for (int c = 0; c < 8; ++c) {  // 8 hidden units per iteration
+            float4* hdst = reinterpret_cast<float4*>(h32 + static_cast<int64_t>(row) * H + nt * 64 + half * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {  // 8 hidden units per iteration
+                const int c = half * 4 + i;
                 uint32_t vr[8], vz[8], vn[8];
                 ptx::tmem_ld8(taddr + c * 8, vr);
                 ptx::tmem_ld8(taddr + 64 + c * 8, vz);
                 ptx::tmem_ld8(taddr + 128 + c * 8, vn);
-                const uint32_t a_gi = s_gi + row_off + ((static_cast<uint32_t>(c) ^ sw) << 4);
+                const uint32_t a_gi = s_box + ((static_cast<uint32_t>(c) ^ sw) << 4);
                 const uint4 qr = lds128(a_gi);
                 const uint4 qz = lds128(a_gi + kGruBoxBytes);
                 const uint4 qn = lds128(a_gi + 2 * kGruBoxBytes);
-                const uint32_t hbox = s_gi + (3 + (c >> 2)) * kGruBoxBytes + row_off;
-                const uint32_t a_h0 = hbox + ((static_cast<uint32_t>((c & 3) * 2) ^ sw) << 4);
-                const uint32_t a_h1 = hbox + ((static_cast<uint32_t>((c & 3) * 2 + 1) ^ sw) << 4);
-                const uint4 h0 = lds128(a_h0);
-                const uint4 h1 = lds128(a_h1);
                 float br[8], bz[8], bn[8];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
@@ -217,7 +266,8 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
                 }
                 const uint32_t gr[4] = {qr.x, qr.y, qr.z, qr.w}, gz[4] = {qz.x, qz.y, qz.z, qz.w},
                                gn[4] = {qn.x, qn.y, qn.z, qn.w};
-                const uint32_t hp[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                const float hp[8] = {hcur[2 * i].x, hcur[2 * i].y, hcur[2 * i].z, hcur[2 * i].w,
+                                     hcur[2 * i + 1].x, hcur[2 * i + 1].y, hcur[2 * i + 1].z, hcur[2 * i + 1].w};
                 ptx::tmem_ld_wait_dep8(vr);
                 ptx::tmem_ld_wait_dep8(vz);
                 ptx::tmem_ld_wait_dep8(vn);
@@ -230,45 +280,35 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
                     const float gir[2] = {fr.x, fr.y}, giz[2] = {fz.x, fz.y}, gin[2] = {fn.x, fn.y};
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int i = 2 * j + e;
-                        const float rr = fast_sigmoid(gir[e] + (__uint_as_float(vr[i]) + br[i]));
-                        const float zz = fast_sigmoid(giz[e] + (__uint_as_float(vz[i]) + bz[i]));
-                        const float nn = fast_tanh(gin[e] + rr * (__uint_as_float(vn[i]) + bn[i]));
-                        hn[i] = (__uint_as_float(hp[i]) - nn) * zz + nn;
+                        const int u = 2 * j + e;
+                        const float rr = fast_sigmoid(gir[e] + (__uint_as_float(vr[u]) + br[u]));
+                        const float zz = fast_sigmoid(giz[e] + (__uint_as_float(vz[u]) + bz[u]));
+                        const float nn = fast_tanh(gin[e] + rr * (__uint_as_float(vn[u]) + bn[u]));
+                        hn[u] = (hp[u] - nn) * zz + nn;
                     }
                 }
-                uint4 o0, o1, os, orl;
-                o0.x = __float_as_uint(hn[0]); o0.y = __float_as_uint(hn[1]); o0.z = __float_as_uint(hn[2]); o0.w = __float_as_uint(hn[3]);
-                o1.x = __float_as_uint(hn[4]); o1.y = __float_as_uint(hn[5]); o1.z = __float_as_uint(hn[6]); o1.w = __float_as_uint(hn[7]);
+                if (row < B) {  // fp32 master state straight from registers
+                    hdst[2 * i] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                    hdst[2 * i + 1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                }
+                uint4 os, orl;
                 os.x = Op::pack2(hn[0], hn[1]); os.y = Op::pack2(hn[2], hn[3]);
                 os.z = Op::pack2(hn[4], hn[5]); os.w = Op::pack2(hn[6], hn[7]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) hn[i] = fmaxf(hn[i], 0.0f);
+                for (int u = 0; u < 8; ++u) hn[u] = fmaxf(hn[u], 0.0f);
                 orl.x = Op::pack2(hn[0], hn[1]); orl.y = Op::pack2(hn[2], hn[3]);
                 orl.z = Op::pack2(hn[4], hn[5]); orl.w = Op::pack2(hn[6], hn[7]);
-                sts128(a_h0, o0);                      // fp32 state, in place
-                sts128(a_h1, o1);
-                sts128(a_gi, os);                      // operand copy of h_t  (over the consumed gi_r chunk)
-                sts128(a_gi + kGruBoxBytes, orl);      // relu(h_t)            (over the consumed gi_z chunk)
+                sts128(a_gi, os);                  // operand copy of h_t (over the consumed gi_r chunk)
+                sts128(a_gi + kGruBoxBytes, orl);  // relu(h_t)           (over the consumed gi_z chunk)
             }
-            // accumulator buffer is free again
             ptx::tc_fence_before();
+            ptx::fence_proxy_async_smem();  // make the st.shared results visible to the TMA store
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
-            // results: shared memory -> global by TMA
-            ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(1, 128);
-            if (store_thread) {
-                ptx::tma_store_2d(&tmH32, epi_smem + 3 * kGruBoxBytes, nt * 64, m0);
-                ptx::tma_store_2d(&tmH32, epi_smem + 4 * kGruBoxBytes, nt * 64 + 32, m0);
-                ptx::tma_store_3d(&tmHseq, epi_smem, nt * 64, m0, t + 1);
-                ptx::tma_store_3d(&tmHrelu, epi_smem + kGruBoxBytes, nt * 64, m0, t);
-                ptx::tma_store_commit();
-                ptx::tma_store_wait_read();
-                ptx::mbar_arrive(epi_empty);  // operand buffers may be refilled
+            if (lane == 0) {
+                ptx::mbar_arrive(&acc_empty[buf]);
+                ptx::mbar_arrive(&res_ready[buf]);
             }
         }
-        if (store_thread) ptx::tma_store_wait_all();
     }
 
     ptx::tc_fence_before();
