@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -218,6 +219,34 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N,
     return PREGO_OK;
 }
 
+// CTA-pair (cta_group::2) launch of the same GEMM contract; tmB must be encoded with box rows TILE_N / 2.
+template <int TILE_N, int STAGES, int FMT, class Epi>
+int launch_gemm_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int a_c1, const Epi& epi,
+                    int sm_count, cudaStream_t stream, const char* name) {
+    using Cfg = Gemm2Cfg<TILE_N>;
+    auto kfn = gemm_tc2_kernel<TILE_N, STAGES, FMT, Epi>;
+    static bool attr_set = false;
+    const int smem = Cfg::smem_bytes(STAGES);
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int tiles = (N / TILE_N) * ((M + 2 * kTileM - 1) / (2 * kTileM));
+    int grid = 2 * tiles < sm_count ? 2 * tiles : (sm_count & ~1);
+    kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, a_c1, epi);
+    LAUNCH_CHECK(name);
+    return PREGO_OK;
+}
+
+bool use_2cta() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PREGO_GEMM_2CTA");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 int check_model(const prego_model* m, bool need_weights) {
     if (m == nullptr) return fail(PREGO_ERR_INVALID, "model handle is NULL");
     if (need_weights && !m->loaded) return fail(PREGO_ERR_STATE, "weights not loaded: call prego_model_load_weights first");
@@ -282,8 +311,13 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     prof_mark(m, s, PREGO_PHASE_STAGE, 1);
     // 2. y = x W1^T + b1  (fp16 out; rows stay time-major, m = t*B + b)
     RC_TRY(make_tmap_a(&tmA, dt, xb, Din, Mc));
-    RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 256));
-    RC_TRY((launch_gemm_tc<256, 4, FMT>(tmA, tmB, Mi, E, Din, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1")));
+    if (use_2cta()) {
+        RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 128));
+        RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, E, Din, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1 (2cta)")));
+    } else {
+        RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 256));
+        RC_TRY((launch_gemm_tc<256, 4, FMT>(tmA, tmB, Mi, E, Din, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1")));
+    }
     prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
     // 3. e = relu(LN(y))  (in place, operand format)
     layernorm_relu_16<2048, FMT><<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(
@@ -292,11 +326,19 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     prof_mark(m, s, PREGO_PHASE_LAYERNORM, 1);
     // 4. gi = e W_ih'^T + b_ih'  (gate-interleaved columns, time-major rows)
     RC_TRY(make_tmap_a(&tmA, dt, ye, E, Mc));
-    RC_TRY(make_tmap_w(&tmB, dt, m->wih_16p[FMT], E, 3 * H, 192));
-    if (batched)
-        RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, 0>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2")));
-    else
-        RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, -1>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2")));
+    if (use_2cta()) {
+        RC_TRY(make_tmap_w(&tmB, dt, m->wih_16p[FMT], E, 3 * H, 128));
+        if (batched)
+            RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<256, 0>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2 (2cta)")));
+        else
+            RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<256, -1>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2 (2cta)")));
+    } else {
+        RC_TRY(make_tmap_w(&tmB, dt, m->wih_16p[FMT], E, 3 * H, 192));
+        if (batched)
+            RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, 0>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2")));
+        else
+            RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, -1>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2")));
+    }
     prof_mark(m, s, PREGO_PHASE_GEMM2, 1);
 
     // 5. recurrence
@@ -405,6 +447,12 @@ int gemm16_test(const void* A, const void* W, const float* bias, float* C, int64
     const DType dt = FMT == 0 ? kF16 : kBF16;
     CUtensorMap tmA, tmB;
     RC_TRY(make_tmap_a(&tmA, dt, A, K, M));
+    if (tile_n < 0) {  // CTA-pair kernels: tile_n = -256 / -192
+        RC_TRY(make_tmap_w(&tmB, dt, W, K, N, -tile_n / 2));
+        if (tile_n == -256) return launch_gemm_tc2<256, 6, FMT>(tmA, tmB, (int)M, (int)N, (int)K, 0, EpiStore<256, -1>{C, bias, N, 0, 0}, sms, s, "gemm256 (2cta)");
+        if (tile_n == -192) return launch_gemm_tc2<192, 7, FMT>(tmA, tmB, (int)M, (int)N, (int)K, 0, EpiStore<192, -1>{C, bias, N, 0, 0}, sms, s, "gemm192 (2cta)");
+        return fail(PREGO_ERR_INVALID, "CTA-pair tile_n must be -256 or -192 (got %d)", tile_n);
+    }
     RC_TRY(make_tmap_w(&tmB, dt, W, K, N, tile_n));
     switch (tile_n) {
         case 96: return launch_gemm_tc<96, 6, FMT>(tmA, tmB, (int)M, (int)N, (int)K, 0, EpiStore<96, -1>{C, bias, N, 0, 0}, sms, s, "gemm96");
@@ -609,7 +657,7 @@ int prego_rle(const int32_t* seq, const int64_t* seg_offsets, const int64_t* fin
 int prego_gemm16_nt(const void* A, const void* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
                     int32_t tile_n, int32_t precision, void* stream) {
     if (A == nullptr || W == nullptr || bias == nullptr || C == nullptr) return fail(PREGO_ERR_INVALID, "NULL pointer argument");
-    if (M <= 0 || N <= 0 || K <= 0 || K % kTileK != 0 || tile_n <= 0 || N % tile_n != 0) return fail(PREGO_ERR_INVALID, "need K %% 64 == 0 and N %% tile_n == 0");
+    if (M <= 0 || N <= 0 || K <= 0 || K % kTileK != 0 || tile_n == 0 || N % (tile_n < 0 ? -tile_n : tile_n) != 0) return fail(PREGO_ERR_INVALID, "need K %% 64 == 0 and N %% tile_n == 0");
     int dev = 0, sms = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -197,6 +197,143 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------ CTA-pair variant
+// Same contract as gemm_tc_kernel, executed by clusters of two CTAs (cta_group::2): one 256 x TILE_N
+// tile per pair, each CTA stages its own 128 rows of A but only HALF of the W tile, and the leader
+// issues one M = 256 MMA for both.  Per CTA a k-block costs 16 KB + TILE_N*64 B instead of
+// 16 KB + TILE_N*128 B, so the same shared memory holds more stages: the single-CTA kernel is bound
+// by (bytes in flight) / (TMA latency ~1 us), not by the tensor pipe (profiles/r01_ncu_full_summary.txt).
+template <int TILE_N>
+struct Gemm2Cfg {
+    static constexpr int kABytes = kTileM * kTileK * 2;
+    static constexpr int kBBytes = (TILE_N / 2) * kTileK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kAccStride = GemmCfg<TILE_N>::kAccStride;
+    static constexpr int kTmemCols = 2 * kAccStride;
+    static constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024 + 256; }
+};
+
+template <int TILE_N, int STAGES, int FMT, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                int a_c1, Epi epi) {
+    using Cfg = Gemm2Cfg<TILE_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;                    // [STAGES]  used in the leader CTA only
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]  per CTA, released by the multicast commit
+    uint64_t* acc_full = bars + 2 * STAGES;       // [2]       per CTA, multicast commit
+    uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]       leader only: 4 epilogue warps x 2 CTAs
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_tiles = N / TILE_N;
+    const int m_tiles = (M + 2 * kTileM - 1) / (2 * kTileM);
+    const int total_tiles = n_tiles * m_tiles;
+    const int k_blocks = K / kTileK;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(&acc_full[b], 1);
+            ptx::mbar_init(&acc_empty[b], 8);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+        ptx::tmem_relinquish2();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();  // barriers of both CTAs initialised before any remote signal
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+                const int m0 = (tile / n_tiles) * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+                const int n0 = (tile % n_tiles) * TILE_N + static_cast<int>(rank) * (TILE_N / 2);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                    if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                    ptx::tma_load_3d_2sm(&tmA, sa, &full_bar[stage], kb * kTileK, a_c1, m0, ptx::kEvictNormal);
+                    ptx::tma_load_2d_2sm(&tmB, sa + Cfg::kABytes, &full_bar[stage], kb * kTileK, n0, ptx::kEvictLast);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc(FMT, 2 * kTileM, TILE_N);
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+                const int buf = it & 1;
+                ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * Cfg::kAccStride;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
+                    const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+                    for (int k = 0; k < kTileK / 16; ++k)
+                        ptx::mma_f16_ss_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::mma_commit_2sm(&empty_bar[stage], 3);  // frees this stage in both CTAs
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::mma_commit_2sm(&acc_full[buf], 3);  // accumulators of both CTAs complete
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        int it = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+            const int buf = it & 1;
+            const int m0 = (tile / n_tiles) * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+            const int n0 = (tile % n_tiles) * TILE_N;
+            ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * Cfg::kAccStride + (static_cast<uint32_t>(quad * 32) << 16);
+            const int row = m0 + quad * 32 + lane;
+            epi(taddr, row, n0, row < M);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_leader(&acc_empty[buf]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    ptx::cluster_sync();  // nobody exits (or frees TMEM) while the peer may still signal into this CTA
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+    }
+}
+
 // ------------------------------------------------------------------ epilogues
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }

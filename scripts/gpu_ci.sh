@@ -12,7 +12,8 @@ run() {  # name, timeout, pytest -k expr
     echo "rc=$rc $(tail -n 1 gpurun_out/ci_$1.log)" | tee -a gpurun_out/ci_summary.txt
 }
 : > gpurun_out/ci_summary.txt
-run gemm_tc 300 "gemm16"
+run gemm_tc 300 "gemm16_tcgen05"
+run gemm_2cta 300 "gemm16_2cta"
 run simt 300 "gemm_f32 or forward_fp32"
 run aggregate 300 "aggregate"
 run bf16 400 "forward_bf16 or forward_fp16 or pooled or chunking or carried or single_frame or big_batch or module_forward or evaluate"

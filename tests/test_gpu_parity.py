@@ -67,6 +67,27 @@ def test_gemm16_tcgen05(dev, lib, tile_n, N, M, K, prec):
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
 
 
+@pytest.mark.parametrize("tile_n,N", [(-256, 2048), (-256, 3072), (-192, 3072)])
+@pytest.mark.parametrize("M,K", [(256, 64), (300, 1024), (5120, 4096), (40000, 2048)])
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_gemm16_2cta(dev, lib, tile_n, N, M, K, prec):
+    """CTA-pair (cta_group::2) kernels: 256-row tiles, W tile split over the pair, multicast commits."""
+    from prego_b200 import _lib
+    g = torch.Generator(device=dev).manual_seed(M * 7 + K + N)
+    dt = torch.float16 if prec == "fp16" else torch.bfloat16
+    A = (torch.randn(M, K, generator=g, device=dev) * 0.5).to(dt)
+    W = (torch.randn(N, K, generator=g, device=dev) * 0.05).to(dt)
+    bias = torch.randn(N, generator=g, device=dev)
+    Cout = torch.full((M, N), float("nan"), device=dev)
+    _lib.check(lib.prego_gemm16_nt(A.data_ptr(), W.data_ptr(), bias.data_ptr(), Cout.data_ptr(), M, N, K, tile_n,
+                                   _lib.PRECISIONS[prec], _stream()), "prego_gemm16_nt")
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().T + bias
+    assert torch.isfinite(Cout).all(), "unwritten / non-finite outputs"
+    err = (Cout - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
 @pytest.mark.parametrize("M,N,K", [(77, 86, 1024), (300, 3072, 2048), (129, 2048, 4096)])
 def test_gemm_f32_simt(dev, lib, M, N, K):
     from prego_b200 import _lib
