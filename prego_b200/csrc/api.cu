@@ -347,7 +347,7 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
         LAUNCH_CHECK("f32_to_16 (hseq slot 0)");
         CUtensorMap tmHseq, tmW, tmGi, tmHrelu;
         RC_TRY(make_tmap_tm(&tmHseq, dt, hseq, H, B, tc + 1, 2));
-        RC_TRY(make_tmap_w(&tmW, dt, m->whh_16p[FMT], H, 3 * H, kGruTileN));
+        RC_TRY(make_tmap_w(&tmW, dt, m->whh_16p[FMT], H, 3 * H, kGruTileN / 2));
         RC_TRY(make_tmap_tm(&tmGi, kF16, gi, 3 * H, B, tc, 2));
         RC_TRY(make_tmap_tm(&tmHrelu, dt, hrelu, H, B, tc, 2));
         auto kfn = gru_step_kernel<FMT>;
@@ -356,8 +356,8 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
             CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmemBytes));
             attr_set = true;
         }
-        const int tiles = (3 * H / kGruTileN) * (int)((B + kTileM - 1) / kTileM);
-        const int grid = tiles < m->sm_count ? tiles : m->sm_count;
+        const int tiles = (3 * H / kGruTileN) * (int)((B + 2 * kTileM - 1) / (2 * kTileM));  // CTA-pair tiles
+        const int grid = 2 * tiles < m->sm_count ? 2 * tiles : (m->sm_count & ~1);
         for (int t = 0; t < tc; ++t)
             kfn<<<grid, kGruThreads, kGruSmemBytes, s>>>(tmHseq, tmW, tmGi, tmHrelu, m->bhh_p, h_cur, (int)B, H, t);
         LAUNCH_CHECK("gru_step_kernel");

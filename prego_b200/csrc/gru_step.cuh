@@ -12,9 +12,13 @@
 //   * the 16-bit operand copy of h_t (history slot t+1, the next step's MMA operand) and relu(h_t) (the
 //     classifier's operand) are written over the consumed gi boxes and leave through TMA stores issued by
 //     the same dedicated warp; the fp32 state is stored straight from registers.
+// The GEMM runs on CTA PAIRS (cta_group::2): one 256-stream x 192-column tile per pair, each CTA stages its
+// own 128 rows of h_{t-1} and half of the W_hh' tile (28 KB per k-block instead of 40 KB), which buys a
+// 6-deep operand pipeline -- the step is bound by bytes in flight / TMA latency, not by the tensor pipe.
 // History: v1 (per-thread global loads in the epilogue) 292 us/step, 74 % long-scoreboard stalls; v2
 // (single-buffered TMA operands) 43 us/step with the epilogue waiting on its operand load for 24 % of the
-// samples; this is v3.  See profiles/r01_ncu_full_summary.txt.
+// samples; v3 (double-buffered gi, 3 x 40 KB stages) 41 us/step; this is v4 (CTA pairs, 6 x 28 KB stages,
+// single gi buffer refilled behind the next tile's main loop).  See profiles/r01_ncu_full_summary.txt.
 //
 // Layouts (time-major inside a chunk so one step touches contiguous rows):
 //   hseq  [Tc+1, B, H]  16-bit operand history, slot t = h_{t-1}
@@ -39,11 +43,12 @@ namespace prego {
 constexpr int kGruThreads = 352;
 constexpr int kGruEpiWarps = 8;
 constexpr int kGruTileN = 192;
-constexpr int kGruStages = 3;
-constexpr int kGruStageBytes = kTileM * kTileK * 2 + kGruTileN * kTileK * 2;  // 40960
+constexpr int kGruStages = 6;
+constexpr int kGruABytes = kTileM * kTileK * 2;                               // 16384: own 128 rows of h
+constexpr int kGruStageBytes = kGruABytes + (kGruTileN / 2) * kTileK * 2;     // + half of the W tile = 28672
 constexpr int kGruBoxBytes = 128 * 128;                                       // one [128 rows x 128 B] box
 constexpr int kGruGiBytes = 3 * kGruBoxBytes;                                 // gi r, z, n of one tile
-constexpr int kGruSmemBytes = kGruStages * kGruStageBytes + 2 * kGruGiBytes + 256 + 1024;
+constexpr int kGruSmemBytes = kGruStages * kGruStageBytes + kGruGiBytes + 256 + 1024;
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
@@ -58,31 +63,36 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(kGruThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGruThreads, 1)
 gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1) 16-bit, box (64, 128, 1)
-                const __grid_constant__ CUtensorMap tmW,      // 2-D (H, 3H) 16-bit, box (64, 192)
+                const __grid_constant__ CUtensorMap tmW,      // 2-D (H, 3H) 16-bit, box (64, 96): half a tile
                 const __grid_constant__ CUtensorMap tmGi,     // 3-D (3H, B, Tc) fp16, box (64, 128, 1)
                 const __grid_constant__ CUtensorMap tmHrelu,  // 3-D (H, B, Tc) 16-bit, box (64, 128, 1)
                 const float* __restrict__ bhh, float* __restrict__ h32, int B, int H, int t) {
     using Op = Op16<FMT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* gi_smem = smem + kGruStages * kGruStageBytes;  // [2][3] boxes
-    uint64_t* bars = reinterpret_cast<uint64_t*>(gi_smem + 2 * kGruGiBytes);
-    uint64_t* full_bar = bars;                        // [3]  operand stage landed
-    uint64_t* empty_bar = bars + kGruStages;          // [3]  operand stage consumed
-    uint64_t* acc_full = bars + 2 * kGruStages;       // [2]  accumulator complete
-    uint64_t* acc_empty = bars + 2 * kGruStages + 2;  // [2]  accumulator drained
-    uint64_t* gi_full = bars + 2 * kGruStages + 4;    // [2]  gi boxes landed
-    uint64_t* res_ready = bars + 2 * kGruStages + 6;  // [2]  results written over the gi boxes
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGruStages + 8);
+    uint8_t* gi_smem = smem + kGruStages * kGruStageBytes;  // 3 boxes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gi_smem + kGruGiBytes);
+    uint64_t* full_bar = bars;                        // [S]  operand stage landed (leader CTA's copy is used)
+    uint64_t* empty_bar = bars + kGruStages;          // [S]  operand stage consumed (multicast commit, per CTA)
+    uint64_t* acc_full = bars + 2 * kGruStages;       // [2]  accumulator complete (multicast commit, per CTA)
+    uint64_t* acc_empty = bars + 2 * kGruStages + 2;  // [2]  accumulator drained (leader: 8 warps x 2 CTAs)
+    uint64_t* gi_full = bars + 2 * kGruStages + 4;    // [1]  gi boxes landed
+    uint64_t* res_ready = bars + 2 * kGruStages + 5;  // [1]  results written over the gi boxes
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGruStages + 6);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
     const int n_tiles = (3 * H) / kGruTileN;
-    const int m_tiles = (B + kTileM - 1) / kTileM;
+    const int m_tiles = (B + 2 * kTileM - 1) / (2 * kTileM);
     const int total_tiles = n_tiles * m_tiles;
     const int k_blocks = H / kTileK;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int row_base = static_cast<int>(rank) * kTileM;  // this CTA's 128 rows inside the 256-row pair tile
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmHseq);
@@ -95,18 +105,18 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
         }
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(&acc_full[b], 1);
-            ptx::mbar_init(&acc_empty[b], kGruEpiWarps);
-            ptx::mbar_init(&gi_full[b], 1);
-            ptx::mbar_init(&res_ready[b], kGruEpiWarps);
+            ptx::mbar_init(&acc_empty[b], 2 * kGruEpiWarps);
         }
+        ptx::mbar_init(gi_full, 1);
+        ptx::mbar_init(res_ready, kGruEpiWarps);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, 512);
-        ptx::tmem_relinquish();
+        ptx::tmem_alloc2(tmem_slot, 512);
+        ptx::tmem_relinquish2();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -115,15 +125,15 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * kTileM;
-                const int n0 = (tile % n_tiles) * kGruTileN;
+            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+                const int m0 = (tile / n_tiles) * (2 * kTileM) + row_base;
+                const int n0 = (tile % n_tiles) * kGruTileN + static_cast<int>(rank) * (kGruTileN / 2);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * kGruStageBytes;
-                    ptx::mbar_expect_tx(&full_bar[stage], kGruStageBytes);
-                    ptx::tma_load_3d(&tmHseq, sa, &full_bar[stage], kb * kTileK, m0, t, ptx::kEvictNormal);
-                    ptx::tma_load_2d(&tmW, sa + kTileM * kTileK * 2, &full_bar[stage], kb * kTileK, n0, ptx::kEvictLast);
+                    if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * kGruStageBytes);
+                    ptx::tma_load_3d_2sm(&tmHseq, sa, &full_bar[stage], kb * kTileK, m0, t, ptx::kEvictNormal);
+                    ptx::tma_load_2d_2sm(&tmW, sa + kGruABytes, &full_bar[stage], kb * kTileK, n0, ptx::kEvictLast);
                     if (++stage == kGruStages) {
                         stage = 0;
                         phase ^= 1;
@@ -133,11 +143,11 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc(FMT, kTileM, kGruTileN);
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc(FMT, 2 * kTileM, kGruTileN);
             int stage = 0, it = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
                 const int buf = it & 1;
                 ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
                 ptx::tc_fence_after();
@@ -147,52 +157,45 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + stage * kGruStageBytes);
                     const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
-                    const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + kTileM * kTileK * 2);
+                    const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + kGruABytes);
 #pragma unroll
                     for (int k = 0; k < kTileK / 16; ++k)
-                        ptx::mma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    ptx::mma_commit(&empty_bar[stage]);
+                        ptx::mma_f16_ss_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::mma_commit_2sm(&empty_bar[stage], 3);
                     if (++stage == kGruStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                ptx::mma_commit(&acc_full[buf]);
+                ptx::mma_commit_2sm(&acc_full[buf], 3);
             }
         }
     } else if (warp == 10) {
-        // ------------------------------- gi loader (two tiles ahead) + result storer (TMA both ways)
+        // ------------------------------- gi loader + result storer (TMA both ways, one buffer)
         if (lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int p = it & 1;
-                uint8_t* box = gi_smem + p * kGruGiBytes;
-                if (it >= 2) {
-                    // results of tile it-2 sit in this buffer: store them, then the buffer is free
-                    const int ptile = tile - 2 * gridDim.x;
-                    const int pm0 = (ptile / n_tiles) * kTileM, pnt = ptile % n_tiles;
-                    ptx::mbar_wait(&res_ready[p], ((it - 2) >> 1) & 1);
-                    ptx::tma_store_3d(&tmHseq, box, pnt * 64, pm0, t + 1);
-                    ptx::tma_store_3d(&tmHrelu, box + kGruBoxBytes, pnt * 64, pm0, t);
+            int pm0 = 0, pnt = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+                if (it >= 1) {
+                    // results of the previous tile sit in the buffer: store them, then it is free
+                    ptx::mbar_wait(res_ready, (it - 1) & 1);
+                    ptx::tma_store_3d(&tmHseq, gi_smem, pnt * 64, pm0, t + 1);
+                    ptx::tma_store_3d(&tmHrelu, gi_smem + kGruBoxBytes, pnt * 64, pm0, t);
                     ptx::tma_store_commit();
                     ptx::tma_store_wait_read();
                 }
-                const int m0 = (tile / n_tiles) * kTileM, nt = tile % n_tiles;
-                ptx::mbar_expect_tx(&gi_full[p], kGruGiBytes);
+                const int m0 = (tile / n_tiles) * (2 * kTileM) + row_base, nt = tile % n_tiles;
+                ptx::mbar_expect_tx(gi_full, kGruGiBytes);
 #pragma unroll
                 for (int g = 0; g < 3; ++g)
-                    ptx::tma_load_3d(&tmGi, box + g * kGruBoxBytes, &gi_full[p], nt * kGruTileN + g * 64, m0, t, ptx::kEvictFirst);
+                    ptx::tma_load_3d(&tmGi, gi_smem + g * kGruBoxBytes, gi_full, nt * kGruTileN + g * 64, m0, t, ptx::kEvictFirst);
+                pm0 = m0;
+                pnt = nt;
             }
-            // drain: the last (up to) two tiles
-            const int n_mine = it;
-            for (int j = (n_mine >= 2 ? n_mine - 2 : 0); j < n_mine; ++j) {
-                const int p = j & 1;
-                const int ptile = blockIdx.x + j * gridDim.x;
-                const int pm0 = (ptile / n_tiles) * kTileM, pnt = ptile % n_tiles;
-                uint8_t* box = gi_smem + p * kGruGiBytes;
-                ptx::mbar_wait(&res_ready[p], (j >> 1) & 1);
-                ptx::tma_store_3d(&tmHseq, box, pnt * 64, pm0, t + 1);
-                ptx::tma_store_3d(&tmHrelu, box + kGruBoxBytes, pnt * 64, pm0, t);
+            if (it >= 1) {
+                ptx::mbar_wait(res_ready, (it - 1) & 1);
+                ptx::tma_store_3d(&tmHseq, gi_smem, pnt * 64, pm0, t + 1);
+                ptx::tma_store_3d(&tmHrelu, gi_smem + kGruBoxBytes, pnt * 64, pm0, t);
                 ptx::tma_store_commit();
             }
             ptx::tma_store_wait_all();
@@ -209,38 +212,38 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
         // fp32 state of the first tile -> registers
         float4 hnext[8];
         {
-            const int tile = blockIdx.x;
+            const int tile = cluster_id;
             if (tile < total_tiles) {
-                const int row = (tile / n_tiles) * kTileM + r;
+                const int row = (tile / n_tiles) * (2 * kTileM) + row_base + r;
                 const float4* src = reinterpret_cast<const float4*>(h32 + static_cast<int64_t>(row) * H + (tile % n_tiles) * 64 + half * 32);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) hnext[i] = row < B ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
             const int buf = it & 1;
             const uint32_t par = (it >> 1) & 1;
-            const int m0 = (tile / n_tiles) * kTileM;
+            const int m0 = (tile / n_tiles) * (2 * kTileM) + row_base;
             const int nt = tile % n_tiles;
             const int row = m0 + r;
             float4 hcur[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) hcur[i] = hnext[i];
             {   // prefetch the next tile's state while this one is computed
-                const int ntile = tile + gridDim.x;
+                const int ntile = tile + num_clusters;
                 if (ntile < total_tiles) {
-                    const int nrow = (ntile / n_tiles) * kTileM + r;
+                    const int nrow = (ntile / n_tiles) * (2 * kTileM) + row_base + r;
                     const float4* src = reinterpret_cast<const float4*>(h32 + static_cast<int64_t>(nrow) * H + (ntile % n_tiles) * 64 + half * 32);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) hnext[i] = nrow < B ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
-            ptx::mbar_wait(&gi_full[buf], par);
+            ptx::mbar_wait(gi_full, it & 1);
             ptx::mbar_wait(&acc_full[buf], par);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + buf * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-            const uint32_t s_box = s_gi + buf * kGruGiBytes + row_off;
+            const uint32_t s_box = s_gi + row_off;
             const float* bh = bhh + nt * kGruTileN;
             float4* hdst = reinterpret_cast<float4*>(h32 + static_cast<int64_t>(row) * H + nt * 64 + half * 32);
 #pragma unroll
@@ -305,17 +308,17 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
             ptx::fence_proxy_async_smem();  // make the st.shared results visible to the TMA store
             __syncwarp();
             if (lane == 0) {
-                ptx::mbar_arrive(&acc_empty[buf]);
-                ptx::mbar_arrive(&res_ready[buf]);
+                ptx::mbar_arrive_leader(&acc_empty[buf]);
+                ptx::mbar_arrive(res_ready);
             }
         }
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    ptx::cluster_sync();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, 512);
+        ptx::tmem_dealloc2(tmem_base, 512);
     }
 }
 
