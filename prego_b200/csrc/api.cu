@@ -253,10 +253,10 @@ int check_model(const prego_model* m, bool need_weights) {
     return PREGO_OK;
 }
 
-template <int NB>
-int launch_latency(const GruLatencyArgs& a, int H, cudaStream_t stream) {
-    auto kfn = gru_latency_kernel<NB>;
-    const size_t smem = (3 * kLatUnitsPerCta * H + 2 * NB * H) * sizeof(float);
+template <int NB, bool REGW>
+int launch_latency_impl(const GruLatencyArgs& a, int H, cudaStream_t stream) {
+    auto kfn = gru_latency_kernel<NB, REGW>;
+    const size_t smem = ((REGW ? 0 : 3 * kLatUnitsPerCta * H) + 2 * NB * H) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -266,6 +266,11 @@ int launch_latency(const GruLatencyArgs& a, int H, cudaStream_t stream) {
     void* params[] = {&args};
     CUDA_TRY(cudaLaunchCooperativeKernel((void*)kfn, dim3(H / kLatUnitsPerCta), dim3(kLatThreads), params, smem, stream));
     return PREGO_OK;
+}
+
+template <int NB>
+int launch_latency(const GruLatencyArgs& a, int H, cudaStream_t stream) {
+    return H == 1024 ? launch_latency_impl<NB, true>(a, H, stream) : launch_latency_impl<NB, false>(a, H, stream);
 }
 
 // Few-stream recurrence on the persistent SIMT kernel (passes of <= 4 streams).

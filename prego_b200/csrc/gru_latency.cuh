@@ -44,19 +44,30 @@ struct GruLatencyArgs {
     int64_t row_sb, row_st;
 };
 
-template <int NB>
+// REGW = true (H == 1024): the warp's three weight rows live in REGISTERS (96 per lane) -- the per-step
+// smem traffic drops from 96 KB of weights to the 4 KB/stream of h; REGW = false keeps them in smem (any H).
+template <int NB, bool REGW>
 __global__ void __launch_bounds__(kLatThreads, 1)
 gru_latency_kernel(GruLatencyArgs a) {
     extern __shared__ float smem_f[];
-    const int H = a.H;
-    float* wsm = smem_f;                              // [3][8][H]
-    float* hbuf = smem_f + 3 * kLatUnitsPerCta * H;   // [2][NB][H]
+    const int H = REGW ? 1024 : a.H;
+    float* wsm = smem_f;                                              // [3][8][H]   (REGW: unused, size 0)
+    float* hbuf = smem_f + (REGW ? 0 : 3 * kLatUnitsPerCta * H);      // [2][NB][H]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int u = blockIdx.x * kLatUnitsPerCta + warp;      // hidden unit of this warp
     const int pcol = (u / 64) * 192 + (u % 64);             // packed column of gate r; z: +64, n: +128
 
-    // Prologue: this CTA's 24 weight rows -> shared memory.
-    for (int idx = tid; idx < 3 * kLatUnitsPerCta * (H / 4); idx += kLatThreads) {
+    // Prologue: this CTA's 24 weight rows -> registers (REGW) or shared memory.
+    float wreg[3][32];
+    if constexpr (REGW) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            const float* wrow = a.whh + static_cast<int64_t>((u / 64) * 192 + g * 64 + (u % 64)) * H;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) wreg[g][i] = __ldg(wrow + lane + 32 * i);
+        }
+    }
+    for (int idx = tid; !REGW && idx < 3 * kLatUnitsPerCta * (H / 4); idx += kLatThreads) {
         const int row = idx / (H / 4), c4 = idx % (H / 4);
         const int g = row / kLatUnitsPerCta, w = row % kLatUnitsPerCta;
         const int uu = blockIdx.x * kLatUnitsPerCta + w;
@@ -123,15 +134,28 @@ gru_latency_kernel(GruLatencyArgs a) {
         const float* w0 = wsm + (0 * kLatUnitsPerCta + warp) * H;
         const float* w1 = wsm + (1 * kLatUnitsPerCta + warp) * H;
         const float* w2 = wsm + (2 * kLatUnitsPerCta + warp) * H;
-#pragma unroll 8
-        for (int k = lane; k < H; k += 32) {
-            const float wr = w0[k], wz = w1[k], wn = w2[k];
+        if constexpr (REGW) {
 #pragma unroll
-            for (int s = 0; s < NB; ++s) {
-                const float hv = hb[s * H + k];
-                acc[0][s] = fmaf(wr, hv, acc[0][s]);
-                acc[1][s] = fmaf(wz, hv, acc[1][s]);
-                acc[2][s] = fmaf(wn, hv, acc[2][s]);
+            for (int i = 0; i < 32; ++i) {
+#pragma unroll
+                for (int s = 0; s < NB; ++s) {
+                    const float hv = hb[s * H + lane + 32 * i];
+                    acc[0][s] = fmaf(wreg[0][i], hv, acc[0][s]);
+                    acc[1][s] = fmaf(wreg[1][i], hv, acc[1][s]);
+                    acc[2][s] = fmaf(wreg[2][i], hv, acc[2][s]);
+                }
+            }
+        } else {
+#pragma unroll 8
+            for (int k = lane; k < H; k += 32) {
+                const float wr = w0[k], wz = w1[k], wn = w2[k];
+#pragma unroll
+                for (int s = 0; s < NB; ++s) {
+                    const float hv = hb[s * H + k];
+                    acc[0][s] = fmaf(wr, hv, acc[0][s]);
+                    acc[1][s] = fmaf(wz, hv, acc[1][s]);
+                    acc[2][s] = fmaf(wn, hv, acc[2][s]);
+                }
             }
         }
 #pragma unroll

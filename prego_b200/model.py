@@ -107,18 +107,23 @@ class MROAD(nn.Module):
         self._handle, self._handle_device = h, device
         return lib
 
+    def _param_tensors(self):
+        l1, ln, fc, g = self.layer1[0], self.layer1[1], self.f_classification[0], self.gru
+        return (l1.weight, l1.bias, ln.weight, ln.bias, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0,
+                fc.weight, fc.bias)  # order of _STATE_KEYS / prego_weights_t
+
     def _sync_weights(self, lib, device):
-        sd = {k: v for k, v in self.state_dict().items()}
-        tensors = []
-        for k in _STATE_KEYS:
-            t = sd[k]
-            if t.device != device or t.dtype != torch.float32:
-                raise RuntimeError(f"parameter {k} must be fp32 on {device} (got {t.dtype} on {t.device}); call model.to(device)")
-            tensors.append(t.contiguous())
+        """Re-pack the ten tensors into the library handle when any of them changed (in-place update,
+        load_state_dict, .to()).  Cheap when nothing changed: ten (data_ptr, version) pairs."""
+        tensors = self._param_tensors()
         key = tuple((t.data_ptr(), t._version) for t in tensors)
         if key == self._packed_key:
             return
-        w = _lib.Weights(*[t.data_ptr() for t in tensors])
+        for k, t in zip(_STATE_KEYS, tensors):
+            if t.device != device or t.dtype != torch.float32:
+                raise RuntimeError(f"parameter {k} must be fp32 on {device} (got {t.dtype} on {t.device}); call model.to(device)")
+        keep = [t.detach().contiguous() for t in tensors]
+        w = _lib.Weights(*[t.data_ptr() for t in keep])
         stream = torch.cuda.current_stream(device).cuda_stream
         _lib.check(lib.prego_model_load_weights(self._handle, C.byref(w), stream), "prego_model_load_weights")
         self._packed_key = key
@@ -135,7 +140,7 @@ class MROAD(nn.Module):
     # ------------------------------------------------------------------------ inference
     @torch.no_grad()
     def infer(self, rgb_input, flow_input, h_state=None, want_probs=True, want_logits=False, want_labels=True,
-              precision=None, chunk_T=None):
+              precision=None, chunk_T=None, out=None):
         """Run the CUDA path.  rgb/flow: fp32 CUDA tensors [B, T, D].  ``h_state`` ([B, H] fp32 CUDA)
         is updated in place when given (streaming / time-chunked online inference)."""
         ref = rgb_input if self.use_rgb else flow_input
@@ -163,9 +168,12 @@ class MROAD(nn.Module):
             need = lib.prego_workspace_bytes(self._handle, B, chunk_T, prec)
             ws_ptr = self._get_workspace(need, device)
             K = self.out_dim
-            probs = torch.empty(B, T, K, dtype=torch.float32, device=device) if want_probs else None
-            logits = torch.empty(B, T, K, dtype=torch.float32, device=device) if want_logits else None
-            labels = torch.empty(B, T, dtype=torch.int32, device=device) if want_labels else None
+            if out is not None:  # caller-owned output buffers (streaming loops: no allocation per call)
+                probs, logits, labels = out.get("probs"), out.get("logits"), out.get("labels")
+            else:
+                probs = torch.empty(B, T, K, dtype=torch.float32, device=device) if want_probs else None
+                logits = torch.empty(B, T, K, dtype=torch.float32, device=device) if want_logits else None
+                labels = torch.empty(B, T, dtype=torch.int32, device=device) if want_labels else None
             if h_state is not None:
                 if h_state.device != device or h_state.dtype != torch.float32 or tuple(h_state.shape) != (B, self.hidden_dim) \
                         or not h_state.is_contiguous():
