@@ -92,6 +92,44 @@ size_t prego_workspace_bytes(const prego_model_t* model, int64_t B, int64_t chun
 /* Replaces MROAD.forward (rnn.py:51-71) plus the label extraction of Evaluate.eval (trainer/eval.py:53). */
 int prego_forward(prego_model_t* model, const prego_forward_args_t* args, void* stream);
 
+/* ---- Training step (reference: rnn.py:51-71 in train mode, trainer/train.py:20-24) -------------------------
+ * prego_train_forward computes the raw logits [B, T, K] (train-mode out['logits'], rnn.py:67) with dropout active
+ * (rnn.py:43; own counter-based mask from `seed`) and keeps the activations in the workspace;
+ * prego_train_backward takes dL/dlogits and writes the gradients of the ten state_dict tensors (overwriting
+ * `grads`, torch layouts): full BPTT through all T steps.  What loss.backward() does for the reference module.
+ * Exact fp32.  The criterion (criterions/loss.py:15-34), the optimizer step and the gradient all-reduce stay
+ * with the caller (torch / torch.distributed NCCL). */
+typedef struct prego_grads {
+    float* layer1_0_weight;
+    float* layer1_0_bias;
+    float* layer1_1_weight;
+    float* layer1_1_bias;
+    float* gru_weight_ih_l0;
+    float* gru_weight_hh_l0;
+    float* gru_bias_ih_l0;
+    float* gru_bias_hh_l0;
+    float* f_classification_0_weight;
+    float* f_classification_0_bias;
+} prego_grads_t;
+
+typedef struct prego_train_args {
+    const float* rgb;        /* [B, T, d_rgb]  */
+    const float* flow;       /* [B, T, d_flow] */
+    int64_t B;
+    int64_t T;
+    float* logits;           /* forward:  [B, T, K] out */
+    const float* dlogits;    /* backward: [B, T, K] in  */
+    const prego_grads_t* grads; /* backward: ten gradient buffers, overwritten */
+    void* workspace;         /* >= prego_train_workspace_bytes(model, B, T); the same buffer for forward and backward */
+    size_t workspace_bytes;
+    float dropout_p;         /* cfg['dropout']; 0 disables */
+    uint64_t seed;           /* dropout mask stream */
+} prego_train_args_t;
+
+size_t prego_train_workspace_bytes(const prego_model_t* model, int64_t B, int64_t T);
+int prego_train_forward(prego_model_t* model, const prego_train_args_t* args, void* stream);
+int prego_train_backward(prego_model_t* model, const prego_train_args_t* args, void* stream);
+
 /* Phase timing of prego_forward, measured with CUDA events on the launching stream (what bench.py's
  * roofline uses).  prego_profile_begin arms it; prego_profile_end waits for the last recorded event and
  * returns the summed device time (ms) and kernel-launch count of each phase since begin. */

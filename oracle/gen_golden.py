@@ -89,6 +89,33 @@ def main():
                                "zero_flow": zero_flow, "rgb_sha256": sha(rgb), "flow_sha256": sha(flow)}
         print(name, probs.shape, "labels", np.bincount(probs.argmax(-1).ravel())[:6])
 
+    # ---- training step: reference module + reference OadLoss, autograd gradients (dropout 0 for parity)
+    from criterions import build_criterion  # the reference's criterions/loss_builder.py
+    from oracle.miniroad_torch_cpu import TorchRefMROAD, oad_loss
+    cfg = dict(synthetic.EPIC_TENT_O, dropout=0.0, loss="NONUNIFORM")
+    torch.manual_seed(20)
+    ref = build_model(cfg, "cpu").train()
+    crit = build_criterion(cfg, "cpu")
+    sids, T = [60, 61, 62], 10
+    rgb, flow = synthetic.feature_batch(sids, T, "cpu", False)
+    target = torch.stack([synthetic.targets(s, T, 12) for s in sids])
+    loss = crit(ref(rgb, flow), target)
+    loss.backward()
+    port = TorchRefMROAD(4096, 2048, 1024, 12, 0.0).train()
+    port.load_state_dict(ref.state_dict())
+    ploss = oad_loss(port(rgb, flow)["logits"], target)
+    ploss.backward()
+    assert abs(float(ploss) - float(loss)) < 1e-6
+    grads = {}
+    for (k, p_ref), (_, p_port) in zip(ref.named_parameters(), port.named_parameters()):
+        assert torch.allclose(p_ref.grad, p_port.grad, rtol=1e-5, atol=1e-8), k
+        g = p_ref.grad.reshape(-1)
+        grads[k + ".head"] = g[:64].numpy().copy()
+        grads[k + ".stats"] = np.array([g.sum().item(), g.abs().sum().item(), g.norm().item(), g.abs().max().item()])
+    np.savez_compressed(os.path.join(GOLD, "train_epic_b3_t10.npz"), loss=np.array(float(loss)), **grads)
+    meta["train_case"] = {"cfg": "EPIC_TENT_O", "dropout": 0.0, "stream_ids": sids, "T": T, "loss": float(loss)}
+    print("train case loss", float(loss))
+
     # aggregate golden pair (the reference's only known-answer vectors)
     src_in = os.path.join(REF, "output_miniRoad", "output_miniROAD.json")
     src_out = os.path.join(REF, "data", "output", "aggregated_data.json")

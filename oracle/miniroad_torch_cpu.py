@@ -50,3 +50,31 @@ class CpuMiniROAD:
     def labels(self, rgb, flow):
         """trainer/eval.py:46-53: .cpu().numpy() then np.argmax(axis=-1)."""
         return np.argmax(self.forward(rgb, flow).numpy(), axis=-1)
+
+
+class TorchRefMROAD(torch.nn.Module):
+    """Train-capable restatement of the reference module on stock torch.nn layers (rnn.py:18-71): the same
+    sub-modules, names and creation order, so ``state_dict`` keys and seeded init coincide.  Used as the
+    gradient oracle for the CUDA training step (autograd through ATen = what ``loss.backward()`` does in
+    trainer/train.py:23).  Checked against the live reference in oracle/gen_golden.py."""
+
+    def __init__(self, input_dim, embedding_dim, hidden_dim, num_classes, dropout):
+        super().__init__()
+        self.gru = torch.nn.GRU(embedding_dim, hidden_dim, 1, batch_first=True)
+        self.layer1 = torch.nn.Sequential(torch.nn.Linear(input_dim, embedding_dim), torch.nn.LayerNorm(embedding_dim),
+                                          torch.nn.ReLU(), torch.nn.Dropout(p=dropout))
+        self.f_classification = torch.nn.Sequential(torch.nn.Linear(hidden_dim, num_classes))
+        self.hidden_dim = hidden_dim
+
+    def forward(self, rgb, flow):
+        x = self.layer1(torch.cat((rgb, flow), 2))
+        h0 = torch.zeros(1, x.shape[0], self.hidden_dim, device=x.device)
+        ht, _ = self.gru(x, h0)
+        logits = self.f_classification(F.relu(ht))
+        return {"logits": logits if self.training else F.softmax(logits, dim=-1)}
+
+
+def oad_loss(logits, target):
+    """criterions/loss.py:15-34 (NONUNIFORM): last-frame CE with L2-normalised targets, batch mean."""
+    lg, tg = logits[:, -1, :], target[:, -1, :]
+    return torch.sum(-F.normalize(tg) * F.log_softmax(lg, dim=-1), dim=1).mean()

@@ -38,6 +38,17 @@ class ForwardArgs(C.Structure):
                 ("precision", C.c_int32), ("chunk_T", C.c_int32)]
 
 
+class Grads(C.Structure):
+    _fields_ = Weights._fields_
+
+
+class TrainArgs(C.Structure):
+    _fields_ = [("rgb", C.c_void_p), ("flow", C.c_void_p), ("B", C.c_int64), ("T", C.c_int64),
+                ("logits", C.c_void_p), ("dlogits", C.c_void_p), ("grads", C.POINTER(Grads)),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("dropout_p", C.c_float),
+                ("seed", C.c_uint64)]
+
+
 # name -> (restype, argtypes); every symbol include/prego_b200.h declares
 SIGNATURES = {
     "prego_abi_version": (C.c_int, []),
@@ -47,6 +58,9 @@ SIGNATURES = {
     "prego_model_load_weights": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_void_p]),
     "prego_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
     "prego_forward": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.c_void_p]),
+    "prego_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64]),
+    "prego_train_forward": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
+    "prego_train_backward": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
     "prego_profile_begin": (C.c_int, [C.c_void_p]),
     "prego_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "prego_window_mode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,

@@ -17,6 +17,7 @@
 #include "gru_latency.cuh"
 #include "gru_step.cuh"
 #include "simt_kernels.cuh"
+#include "train_kernels.cuh"
 
 using namespace prego;
 
@@ -684,3 +685,5 @@ int prego_gemm_f32_nt(const float* A, const float* W, const float* bias, float* 
 }
 
 }  // extern "C"
+
+#include "train_api.inc"

@@ -81,6 +81,7 @@ class MROAD(nn.Module):
         self._handle_device = None
         self._packed_key = None
         self._workspace = None
+        self._train_ws = None
         self.last_labels = None  # int32 [B, T] labels of the last forward (fused argmax)
 
     # ------------------------------------------------------------------ C-ABI plumbing
@@ -204,13 +205,11 @@ class MROAD(nn.Module):
         return {p: {"ms": ms[i], "launches": int(cnt[i])} for i, p in enumerate(_lib.PHASES)}
 
     def forward(self, rgb_input, flow_input):
-        """rnn.py:51-71.  Eval: ``out['logits']`` = softmax probabilities [B, T, K]."""
+        """rnn.py:51-71.  Eval: ``out['logits']`` = softmax probabilities [B, T, K]; train: raw logits."""
         if self.training:
-            # train mode returns raw logits with dropout active and needs autograd (rnn.py:66-67,
-            # trainer/train.py:20-24); the backward kernels are SURVEY 8 row a17 / config 5.
-            raise NotImplementedError(
-                "prego_b200.MROAD: the training step (BPTT backward + NCCL all-reduce) is not built yet; "
-                "call model.eval() for the online-inference path")
+            # train mode: raw logits, dropout active, autograd-tracked (rnn.py:66-67, trainer/train.py:20-24)
+            from .training import train_forward
+            return {"logits": train_forward(self, rgb_input, flow_input)}
         out = self.infer(rgb_input, flow_input, want_probs=True, want_labels=True)
         self.last_labels = out["labels"]
         return {"logits": out["probs"]}

@@ -87,7 +87,7 @@ def test_cpu_tensors_and_train_mode_rejected():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(x, x)
     m.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(x, x)
 
 

@@ -1,0 +1,87 @@
+"""Training step on the CUDA path (BASELINE configs[4]): gradients of all ten tensors
+against the reference-made golden gradients and against autograd through stock torch layers."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD
+from oracle.miniroad_torch_cpu import TorchRefMROAD, oad_loss
+from prego_b200 import OadLoss, synthetic, train_one_step
+
+pytestmark = pytest.mark.gpu
+GRAD_REL = 2e-4  # exact-fp32 kernels vs ATen autograd: relative to max|grad| of the tensor
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _grads_cuda(cfg, rgb, flow, target, dev):
+    model = synthetic.seeded_model(cfg, seed=20, device=dev).train()
+    out = model(rgb.to(dev), flow.to(dev))
+    assert out["logits"].requires_grad and tuple(out["logits"].shape) == (rgb.shape[0], rgb.shape[1], cfg["num_classes"])
+    loss = OadLoss(cfg)(out, target.to(dev))
+    loss.backward()
+    torch.cuda.synchronize()
+    return model, float(loss), {k: p.grad.detach().cpu() for k, p in model.named_parameters()}, out["logits"].detach().cpu()
+
+
+def test_gradients_match_reference_golden(dev, golden_meta):
+    gold = np.load(os.path.join(GOLD, "train_epic_b3_t10.npz"))
+    c = golden_meta["train_case"]
+    cfg = dict(synthetic.EPIC_TENT_O, dropout=0.0)
+    rgb, flow = synthetic.feature_batch(c["stream_ids"], c["T"], "cpu", False)
+    target = torch.stack([synthetic.targets(s, c["T"], 12) for s in c["stream_ids"]])
+    _, loss, grads, _ = _grads_cuda(cfg, rgb, flow, target, dev)
+    assert abs(loss - float(gold["loss"])) <= 1e-5
+    for k, g in grads.items():
+        g = g.reshape(-1)
+        scale = float(gold[k + ".stats"][3])
+        assert np.abs(g[:64].numpy() - gold[k + ".head"]).max() <= GRAD_REL * scale, k
+        assert abs(g.abs().sum().item() - gold[k + ".stats"][1]) <= 1e-3 * gold[k + ".stats"][1], k
+        assert abs(g.norm().item() - gold[k + ".stats"][2]) <= 1e-3 * gold[k + ".stats"][2], k
+
+
+@pytest.mark.parametrize("B,T,K", [(5, 17, 86), (16, 128, 86)])
+def test_gradients_match_torch_autograd(dev, B, T, K):
+    cfg = dict(synthetic.ASSEMBLY101_O, dropout=0.0, num_classes=K)
+    rgb, flow = synthetic.feature_batch(list(range(100, 100 + B)), T, "cpu", False)
+    # a loss that touches EVERY frame (the reference loss only touches the last one)
+    wts = torch.randn(B, T, K, generator=torch.Generator().manual_seed(1))
+    model = synthetic.seeded_model(cfg, seed=20, device=dev).train()
+    logits = model(rgb.to(dev), flow.to(dev))["logits"]
+    (logits * wts.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    port = TorchRefMROAD(4096, 2048, 1024, K, 0.0).train()
+    port.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    ref_logits = port(rgb, flow)["logits"]
+    (ref_logits * wts).sum().backward()
+    assert (logits.detach().cpu() - ref_logits.detach()).abs().max().item() <= 1e-4 * ref_logits.abs().max().item()
+    for (k, p), (_, q) in zip(model.named_parameters(), port.named_parameters()):
+        err = (p.grad.cpu() - q.grad).abs().max().item()
+        assert err <= GRAD_REL * q.grad.abs().max().item(), f"{k}: {err} vs max {q.grad.abs().max().item()}"
+
+
+def test_dropout_mask_and_training_loop(dev):
+    cfg = dict(synthetic.EPIC_TENT_O, dropout=0.2)
+    B, T, K = 8, 32, 12
+    rgb, flow = synthetic.feature_batch(list(range(B)), T, dev, True)  # zero flow, as the reference loader feeds it
+    target = torch.stack([synthetic.targets(s, T, K) for s in range(B)]).to(dev)
+    model = synthetic.seeded_model(cfg, seed=20, device=dev).train()
+    torch.manual_seed(1)
+    a = model(rgb, flow)["logits"].detach()
+    torch.manual_seed(1)
+    b = model(rgb, flow)["logits"].detach()
+    c = model(rgb, flow)["logits"].detach()
+    assert torch.equal(a, b) and not torch.equal(a, c)      # mask stream follows torch's RNG state
+    model.eval()
+    p = model(rgb, flow)["logits"]
+    assert (p.sum(-1) - 1).abs().max().item() < 1e-5          # eval path unaffected
+    crit = OadLoss(cfg)
+    opt = torch.optim.AdamW([{"params": model.parameters(), "initial_lr": 1e-3}], lr=1e-3, weight_decay=0.05)
+    losses = [float(train_one_step(model, crit, opt, rgb, flow, target)) for _ in range(12)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
