@@ -68,7 +68,7 @@ class TorchRefMROAD(torch.nn.Module):
 
     def forward(self, rgb, flow):
         x = self.layer1(torch.cat((rgb, flow), 2))
-        h0 = torch.zeros(1, x.shape[0], self.hidden_dim, device=x.device)
+        h0 = torch.zeros(1, x.shape[0], self.hidden_dim, device=x.device, dtype=x.dtype)
         ht, _ = self.gru(x, h0)
         logits = self.f_classification(F.relu(ht))
         return {"logits": logits if self.training else F.softmax(logits, dim=-1)}

