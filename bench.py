@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-latency", action="store_true", help="skip the single-stream latency leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     return ap.parse_args()
 
 
@@ -215,6 +216,43 @@ def latency_leg(dev, precision):
     return out
 
 
+# ----------------------------------------------------------------------------- training-step leg
+def training_leg(dev, world):
+    """BASELINE configs[4]: MiniROAD training step (forward + BPTT backward + AdamW), per-GPU batch 16 (the
+    reference's) and 256 windows of 128 frames, zero flow as the reference loader feeds it, dropout 0.2,
+    gradients all-reduced over NCCL when world > 1.  Exact-fp32 CUDA-core kernels (first version)."""
+    import torch.distributed as dist
+    from prego_b200 import OadLoss, synthetic, train_one_step
+    cfg = dict(synthetic.ASSEMBLY101_O)
+    model = synthetic.seeded_model(cfg, seed=20, device=dev)
+    crit = OadLoss(cfg)
+    opt = torch.optim.AdamW([{"params": model.parameters(), "initial_lr": 1e-4}], lr=1e-4, weight_decay=0.05)
+    out = {}
+    for B in (16, 256):
+        T = 128
+        rgb, flow = synthetic.device_features(B, T, dev, seed=7, zero_flow=True)
+        target = torch.nn.functional.one_hot(torch.randint(0, 86, (B, T), device=dev), 86).float()
+        for _ in range(2):
+            train_one_step(model, crit, opt, rgb, flow, target)
+        torch.cuda.synchronize()
+        n = 5 if B == 16 else 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        for _ in range(n):
+            loss = train_one_step(model, crit, opt, rgb, flow, target)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out[f"B{B}_T{T}"] = {"ms_per_step": float(ms), "frames_per_s": world * B * T / float(ms) * 1e3, "loss": float(loss)}
+        del rgb, flow, target
+    out["note"] = "fwd + BPTT + torch AdamW, dropout 0.2, flow = 0, fp32 CUDA-core GEMMs; grads all-reduced (NCCL) when n_gpus > 1"
+    return out
+
+
 # ----------------------------------------------------------------------------- main arm
 def run_ours(args, world, rank, local):
     import torch.distributed as dist
@@ -309,6 +347,12 @@ def run_ours(args, world, rank, local):
                "note": "pinned host fp32 features -> H2D -> prego_forward -> int32 labels D2H; PCIe-bound (16 KiB/frame); all ranks concurrently, max over ranks"}
         del hr, hf, drgb, dflow
 
+    train = None
+    if not args.no_train:
+        del rgb, flow
+        torch.cuda.empty_cache()
+        train = training_leg(dev, world)
+        rgb = flow = None
     if rank != 0:
         if world > 1:
             # keep ranks alive until rank 0 finished its extra legs
@@ -339,7 +383,6 @@ def run_ours(args, world, rank, local):
 
     lat = None
     if not args.no_latency and world == 1:
-        del rgb, flow
         torch.cuda.empty_cache()
         lat = latency_leg(dev, args.precision)
 
@@ -356,7 +399,7 @@ def run_ours(args, world, rank, local):
                        "l2_policy": "inputs larger than L2 (4 GiB of features per step vs 126 MB L2)",
                        "weights": "seed-20 default init (no checkpoint ships with the reference)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "single_stream": lat}
+            "single_stream": lat, "train_step": train}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
