@@ -167,7 +167,7 @@ def run_reference(args, world, rank):
             "config": {"workload": f"Assembly101-O-shaped, {args.streams} streams x {args.chunk}-frame chunks (K=86)", "sample": sample},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- single-stream latency leg
@@ -400,13 +400,35 @@ def run_ours(args, world, rank, local):
                        "weights": "seed-20 default init (no checkpoint ships with the reference)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "single_stream": lat, "train_step": train}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner) must not pollute the ONE JSON line on stdout: route fd 1 to
+    stderr for the duration of the run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    _quiet_stdout()
     args = parse()
     world, rank, local = dist_env(args.gpus)
     if args.impl == "reference":

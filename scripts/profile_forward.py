@@ -12,6 +12,6 @@ model = synthetic.seeded_model(dict(getattr(synthetic, cfgname)), seed=20, devic
 rgb, flow = synthetic.device_features(B, T, dev, seed=1)
 h = torch.zeros(B, 1024, device=dev)
 for _ in range(2):
-    model.infer(rgb, flow, h_state=h, want_probs=False, precision="bf16", chunk_T=T)
+    model.infer(rgb, flow, h_state=h, want_probs=False, precision="fp16", chunk_T=T)
 torch.cuda.synchronize()
 print("done")
