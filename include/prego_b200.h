@@ -92,6 +92,10 @@ size_t prego_workspace_bytes(const prego_model_t* model, int64_t B, int64_t chun
 /* Replaces MROAD.forward (rnn.py:51-71) plus the label extraction of Evaluate.eval (trainer/eval.py:53). */
 int prego_forward(prego_model_t* model, const prego_forward_args_t* args, void* stream);
 
+/* Device-side watchdog: the persistent recurrence kernels bound every inter-CTA spin; if a peer never shows up
+ * they set a flag instead of hanging the GPU.  Reads (and clears) it; synchronises the device.  0 = healthy. */
+int prego_device_error(prego_model_t* model, int32_t* out);
+
 /* ---- Training step (reference: rnn.py:51-71 in train mode, trainer/train.py:20-24) -------------------------
  * prego_train_forward computes the raw logits [B, T, K] (train-mode out['logits'], rnn.py:67) with dropout active
  * (rnn.py:43; own counter-based mask from `seed`) and keeps the activations in the workspace;

@@ -175,6 +175,7 @@ struct Plan {
     int64_t hrelu;         // 16-bit or fp32 [Mc, H]
     int64_t gh;            // fp32 [B, 3H]                          (fp32 batched recurrence)
     int64_t logits;        // fp32 [Mc, K]                          (fp32 head)
+    int64_t sync;          // uint32 [Tc, ceil(B/256)] dependency counters  (batched 16-bit recurrence)
     int64_t total;
 };
 
@@ -198,6 +199,7 @@ Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec) {
     p.hrelu = take(Mc * H * (h16 ? 2 : 4));
     p.gh = (!h16 && batched) ? take(B * 3 * H * 4) : 0;
     p.logits = h16 ? 0 : take(Mc * K * 4);
+    p.sync = (h16 && batched) ? take(Tc * ((B + 255) / 256) * 4) : 0;
     p.total = off;
     return p;
 }
@@ -237,6 +239,15 @@ int launch_gemm_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N
     kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, a_c1, epi);
     LAUNCH_CHECK(name);
     return PREGO_OK;
+}
+
+bool use_persistent_gru() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PREGO_GRU_PERSISTENT");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 bool use_2cta() {
@@ -356,18 +367,50 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
         RC_TRY(make_tmap_w(&tmW, dt, m->whh_16p[FMT], H, 3 * H, kGruTileN / 2));
         RC_TRY(make_tmap_tm(&tmGi, kF16, gi, 3 * H, B, tc, 2));
         RC_TRY(make_tmap_tm(&tmHrelu, dt, hrelu, H, B, tc, 2));
-        auto kfn = gru_step_kernel<FMT>;
+        auto kfn = gru_seq_kernel<FMT>;
         static bool attr_set = false;
         if (!attr_set) {
             CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmemBytes));
             attr_set = true;
         }
-        const int tiles = (3 * H / kGruTileN) * (int)((B + 2 * kTileM - 1) / (2 * kTileM));  // CTA-pair tiles
-        const int grid = 2 * tiles < m->sm_count ? 2 * tiles : (m->sm_count & ~1);
-        for (int t = 0; t < tc; ++t)
-            kfn<<<grid, kGruThreads, kGruSmemBytes, s>>>(tmHseq, tmW, tmGi, tmHrelu, m->bhh_p, h_cur, (int)B, H, t);
-        LAUNCH_CHECK("gru_step_kernel");
-        prof_mark(m, s, PREGO_PHASE_RECURRENCE, tc + 1);
+        const int m_tiles = (int)((B + 2 * kTileM - 1) / (2 * kTileM));
+        const int per_step = (3 * H / kGruTileN) * m_tiles;  // CTA-pair tiles per time step
+        const int max_grid = m->sm_count & ~1;
+        int launches = 0;
+        if (use_persistent_gru()) {
+            // one launch for the whole chunk: dataflow dependencies between steps (done counters)
+            uint32_t* done = reinterpret_cast<uint32_t*>(ws + p.sync);
+            CUDA_TRY(cudaMemsetAsync(done, 0, (size_t)tc * m_tiles * 4, s));
+            const int64_t items = (int64_t)per_step * tc;
+            const int grid = 2 * items < max_grid ? (int)(2 * items) : max_grid;
+            GruSeqArgs ga{m->bhh_p, h_cur, done, m->err_flag, (int)B, H, 0, tc};
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(kGruThreads);
+            cfg.dynamicSmemBytes = kGruSmemBytes;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeCooperative;  // all CTA pairs co-resident (the dependency spins rely on it)
+            attr[0].val.cooperative = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cudaError_t le = cudaLaunchKernelEx(&cfg, kfn, tmHseq, tmW, tmGi, tmHrelu, ga);
+            if (le != cudaSuccess) {
+                (void)cudaGetLastError();
+                cfg.numAttrs = 0;  // cooperative attribute rejected with clusters: plain launch, grid <= resident CTAs
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, tmHseq, tmW, tmGi, tmHrelu, ga));
+            }
+            launches = 2;
+        } else {
+            const int grid = 2 * per_step < max_grid ? 2 * per_step : max_grid;
+            for (int t = 0; t < tc; ++t) {
+                GruSeqArgs ga{m->bhh_p, h_cur, nullptr, m->err_flag, (int)B, H, t, t + 1};
+                kfn<<<grid, kGruThreads, kGruSmemBytes, s>>>(tmHseq, tmW, tmGi, tmHrelu, ga);
+            }
+            launches = tc + 1;
+        }
+        LAUNCH_CHECK("gru_seq_kernel");
+        prof_mark(m, s, PREGO_PHASE_RECURRENCE, launches);
     } else {
         RC_TRY(run_latency_recurrence(m, reinterpret_cast<const float*>(gi), h_cur, h_alt, hrelu, B, tc, FMT, 1, B, s));
         prof_mark(m, s, PREGO_PHASE_RECURRENCE, (int)((B + 3) / 4));
@@ -601,6 +644,16 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
     }
     if (a->h_state != nullptr)
         CUDA_TRY(cudaMemcpyAsync(a->h_state, h_cur, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, s));
+    return PREGO_OK;
+}
+
+int prego_device_error(prego_model_t* m, int32_t* out) {
+    RC_TRY(check_model(m, false));
+    if (out == nullptr) return fail(PREGO_ERR_INVALID, "out is NULL");
+    int v = 0;
+    CUDA_TRY(cudaMemcpy(&v, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));  // synchronises with prior work
+    *out = v;
+    if (v != 0) CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
     return PREGO_OK;
 }
 

@@ -1,34 +1,36 @@
-// One GRU time step for all streams (rnn.py:61), batched regime (B > 16):
+// GRU recurrence for all streams (rnn.py:61), batched regime (B > 16).  Per time step t:
 //
-//   gh = h_{t-1} W_hh'^T          tcgen05 GEMM, 128 streams x (64 hidden units x 3 gates) per tile
+//   gh = h_{t-1} W_hh'^T          tcgen05 GEMM, 256 streams x (64 hidden units x 3 gates) per CTA-pair tile
 //   r = sigma(gi_r + gh_r + b_hr),  z = sigma(gi_z + gh_z + b_hz)
 //   n = tanh(gi_n + r * (gh_n + b_hn)),  h_t = (h_{t-1} - n) * z + n       (ATen's order)
 //
-// fused in one persistent kernel.  The epilogue never waits on DRAM:
-//   * the gate pre-activations gi[t] of a tile (3 fp16 boxes of [128 x 64]) are bulk-loaded by TMA into a
-//     DOUBLE-BUFFERED swizzled shared-memory area by a dedicated warp, two tiles ahead of their use;
-//   * the fp32 master state of the NEXT tile is prefetched into registers while the current tile is
-//     being computed;
-//   * the 16-bit operand copy of h_t (history slot t+1, the next step's MMA operand) and relu(h_t) (the
-//     classifier's operand) are written over the consumed gi boxes and leave through TMA stores issued by
-//     the same dedicated warp; the fp32 state is stored straight from registers.
-// The GEMM runs on CTA PAIRS (cta_group::2): one 256-stream x 192-column tile per pair, each CTA stages its
-// own 128 rows of h_{t-1} and half of the W_hh' tile (28 KB per k-block instead of 40 KB), which buys a
-// 6-deep operand pipeline -- the step is bound by bytes in flight / TMA latency, not by the tensor pipe.
-// History: v1 (per-thread global loads in the epilogue) 292 us/step, 74 % long-scoreboard stalls; v2
-// (single-buffered TMA operands) 43 us/step with the epilogue waiting on its operand load for 24 % of the
-// samples; v3 (double-buffered gi, 3 x 40 KB stages) 41 us/step; this is v4 (CTA pairs, 6 x 28 KB stages,
-// single gi buffer refilled behind the next tile's main loop).  See profiles/r01_ncu_full_summary.txt.
+// ONE persistent launch covers a whole range of time steps [t_begin, t_end): the work items (t, m, n) --
+// step, 256-stream block, 64-unit block -- are numbered step-major and dealt round-robin to the CTA pairs, and
+// the only synchronisation between steps is a DATAFLOW dependency: item (t, m, .) may read h_{t-1} of stream
+// block m once the 16 items (t-1, m, *) have published it.  Each CTA bumps done[t][m] (release) after its
+// results are globally visible; consumers spin on it with acquire loads.  There is no grid-wide barrier, no
+// per-step launch / prologue / tail, and pairs that finish step t early simply start on step t+1.
+// (One launch per step cost 14.8 us of fixed overhead per step on top of ~6 us of work per wave:
+// scripts/sweep_recurrence.py, profiles/r01_recurrence_sweep.txt.)  With sync == nullptr the kernel runs a
+// single step without any inter-CTA protocol (used when the pairs cannot all be co-resident).
+//
+// The epilogue never waits on DRAM: gi[t] of a tile (3 fp16 boxes of [128 x 64]) is bulk-loaded by TMA into
+// swizzled shared memory behind the previous tile's stores; the 16-bit operand copy of h_t (history slot t+1,
+// the next step's MMA operand) and relu(h_t) (the classifier's operand) are written over the consumed gi boxes
+// and leave through TMA stores; the fp32 master state moves through registers.
+// The GEMM runs on CTA PAIRS (cta_group::2): each CTA stages its own 128 rows of h_{t-1} and half of the W_hh'
+// tile (28 KB per k-block), 6-deep pipeline.
 //
 // Layouts (time-major inside a chunk so one step touches contiguous rows):
 //   hseq  [Tc+1, B, H]  16-bit operand history, slot t = h_{t-1}
 //   gi    [Tc,   B, 3H] fp16, gate-interleaved columns (tile n: [r(64) | z(64) | n(64)])
 //   hrelu [Tc,   B, H]  16-bit relu(h_t)
 //   h32   [B, H]        fp32 master state
+//   done  [Tc, m_tiles] uint32 dependency counters (zeroed by the host before the launch)
 //
 // Warp roles (352 threads): warp 0 = operand TMA producer, warp 1 = TMEM alloc + MMA issuer,
 // warps 2..9 = epilogue (TMEM lane quadrant = warp % 4; warps 2-5 take hidden units 0-31 of the tile,
-// warps 6-9 units 32-63), warp 10 = gi loader + result storer.
+// warps 6-9 units 32-63), warp 10 = gi loader + result storer + publisher.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -62,13 +64,38 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Dependency wait: spin (acquire) until done[idx] >= target, then order later async-proxy (TMA) reads after it.
+// Bounded: a missing peer sets the error flag instead of hanging the GPU.
+__device__ __forceinline__ void dep_wait(const uint32_t* ctr, uint32_t target, int* err_flag) {
+    uint32_t v;
+    long long spins = 0;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= target) break;
+        if (++spins > (1ll << 26)) {
+            *err_flag = 2;
+            break;
+        }
+    } while (true);
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+struct GruSeqArgs {
+    const float* bhh;   // [3H] packed order
+    float* h32;         // [B, H] fp32 master state (in/out)
+    uint32_t* done;     // [Tc][m_tiles] dependency counters, or nullptr (single step, no protocol)
+    int* err_flag;
+    int B, H;
+    int t_begin, t_end;
+};
+
 template <int FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGruThreads, 1)
-gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1) 16-bit, box (64, 128, 1)
-                const __grid_constant__ CUtensorMap tmW,      // 2-D (H, 3H) 16-bit, box (64, 96): half a tile
-                const __grid_constant__ CUtensorMap tmGi,     // 3-D (3H, B, Tc) fp16, box (64, 128, 1)
-                const __grid_constant__ CUtensorMap tmHrelu,  // 3-D (H, B, Tc) 16-bit, box (64, 128, 1)
-                const float* __restrict__ bhh, float* __restrict__ h32, int B, int H, int t) {
+gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1) 16-bit, box (64, 128, 1)
+               const __grid_constant__ CUtensorMap tmW,      // 2-D (H, 3H) 16-bit, box (64, 96): half a tile
+               const __grid_constant__ CUtensorMap tmGi,     // 3-D (3H, B, Tc) fp16, box (64, 128, 1)
+               const __grid_constant__ CUtensorMap tmHrelu,  // 3-D (H, B, Tc) 16-bit, box (64, 128, 1)
+               const GruSeqArgs a) {
     using Op = Op16<FMT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -86,13 +113,17 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
     const int lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const bool leader = rank == 0;
+    const int B = a.B, H = a.H;
     const int n_tiles = (3 * H) / kGruTileN;
     const int m_tiles = (B + 2 * kTileM - 1) / (2 * kTileM);
-    const int total_tiles = n_tiles * m_tiles;
+    const int per_step = n_tiles * m_tiles;
     const int k_blocks = H / kTileK;
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
     const int row_base = static_cast<int>(rank) * kTileM;  // this CTA's 128 rows inside the 256-row pair tile
+    const int item_begin = a.t_begin * per_step + cluster_id;
+    const int item_end = a.t_end * per_step;
+    const uint32_t dep_target = 2u * static_cast<uint32_t>(n_tiles);  // both CTAs of all n-tiles of a stream block
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmHseq);
@@ -125,9 +156,12 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-                const int m0 = (tile / n_tiles) * (2 * kTileM) + row_base;
-                const int n0 = (tile % n_tiles) * kGruTileN + static_cast<int>(rank) * (kGruTileN / 2);
+            for (int item = item_begin; item < item_end; item += num_clusters) {
+                const int t = item / per_step, rem = item % per_step;
+                const int mt = rem / n_tiles;
+                const int m0 = mt * (2 * kTileM) + row_base;
+                const int n0 = (rem % n_tiles) * kGruTileN + static_cast<int>(rank) * (kGruTileN / 2);
+                if (a.done != nullptr && t > a.t_begin) dep_wait(a.done + (t - 1) * m_tiles + mt, dep_target, a.err_flag);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * kGruStageBytes;
@@ -147,7 +181,7 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
             constexpr uint32_t idesc = ptx::make_idesc(FMT, 2 * kTileM, kGruTileN);
             int stage = 0, it = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+            for (int item = item_begin; item < item_end; item += num_clusters, ++it) {
                 const int buf = it & 1;
                 ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
                 ptx::tc_fence_after();
@@ -171,34 +205,48 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
             }
         }
     } else if (warp == 10) {
-        // ------------------------------- gi loader + result storer (TMA both ways, one buffer)
+        // ------------------- gi loader + result storer + publisher (TMA both ways, one buffer)
         if (lane == 0) {
             int it = 0;
-            int pm0 = 0, pnt = 0;
-            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+            int pm0 = 0, pnt = 0, pt = 0, pmt = 0;
+            for (int item = item_begin; item < item_end; item += num_clusters, ++it) {
+                const int t = item / per_step, rem = item % per_step;
+                const int mt = rem / n_tiles, nt = rem % n_tiles;
+                const int m0 = mt * (2 * kTileM) + row_base;
                 if (it >= 1) {
-                    // results of the previous tile sit in the buffer: store them, then it is free
+                    // results of the previous item sit in the buffer: store them, then it is free
                     ptx::mbar_wait(res_ready, (it - 1) & 1);
-                    ptx::tma_store_3d(&tmHseq, gi_smem, pnt * 64, pm0, t + 1);
-                    ptx::tma_store_3d(&tmHrelu, gi_smem + kGruBoxBytes, pnt * 64, pm0, t);
+                    ptx::tma_store_3d(&tmHseq, gi_smem, pnt * 64, pm0, pt + 1);
+                    ptx::tma_store_3d(&tmHrelu, gi_smem + kGruBoxBytes, pnt * 64, pm0, pt);
                     ptx::tma_store_commit();
                     ptx::tma_store_wait_read();
                 }
-                const int m0 = (tile / n_tiles) * (2 * kTileM) + row_base, nt = tile % n_tiles;
+                // gi[t] itself has no dependency (GEMM2 finished before the launch): load it right away
                 ptx::mbar_expect_tx(gi_full, kGruGiBytes);
 #pragma unroll
                 for (int g = 0; g < 3; ++g)
                     ptx::tma_load_3d(&tmGi, gi_smem + g * kGruBoxBytes, gi_full, nt * kGruTileN + g * 64, m0, t, ptx::kEvictFirst);
-                pm0 = m0;
-                pnt = nt;
+                if (it >= 1 && a.done != nullptr) {
+                    // publish the previous item: its TMA stores and the epilogue's fp32 stores are complete
+                    ptx::tma_store_wait_all();
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.done + pt * m_tiles + pmt) : "memory");
+                }
+                pm0 = m0; pnt = nt; pt = t; pmt = mt;
             }
             if (it >= 1) {
                 ptx::mbar_wait(res_ready, (it - 1) & 1);
-                ptx::tma_store_3d(&tmHseq, gi_smem, pnt * 64, pm0, t + 1);
-                ptx::tma_store_3d(&tmHrelu, gi_smem + kGruBoxBytes, pnt * 64, pm0, t);
+                ptx::tma_store_3d(&tmHseq, gi_smem, pnt * 64, pm0, pt + 1);
+                ptx::tma_store_3d(&tmHrelu, gi_smem + kGruBoxBytes, pnt * 64, pm0, pt);
                 ptx::tma_store_commit();
+                ptx::tma_store_wait_all();
+                if (a.done != nullptr) {
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.done + pt * m_tiles + pmt) : "memory");
+                }
             }
-            ptx::tma_store_wait_all();
         }
     } else {
         // -------------------------------------------------------------------------- epilogue
@@ -207,45 +255,43 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
         const int r = quad * 32 + lane;    // row of the tile = TMEM lane
         const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
         const uint32_t sw = static_cast<uint32_t>(r & 7);
-        const uint32_t s_gi = ptx::smem_u32(gi_smem);
-
-        // fp32 state of the first tile -> registers
-        float4 hnext[8];
-        {
-            const int tile = cluster_id;
-            if (tile < total_tiles) {
-                const int row = (tile / n_tiles) * (2 * kTileM) + row_base + r;
-                const float4* src = reinterpret_cast<const float4*>(h32 + static_cast<int64_t>(row) * H + (tile % n_tiles) * 64 + half * 32);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) hnext[i] = row < B ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
+        const uint32_t s_box = ptx::smem_u32(gi_smem) + row_off;
         int it = 0;
-        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+        for (int item = item_begin; item < item_end; item += num_clusters, ++it) {
             const int buf = it & 1;
-            const uint32_t par = (it >> 1) & 1;
-            const int m0 = (tile / n_tiles) * (2 * kTileM) + row_base;
-            const int nt = tile % n_tiles;
+            const int rem = item % per_step;
+            const int m0 = (rem / n_tiles) * (2 * kTileM) + row_base;
+            const int nt = rem % n_tiles;
             const int row = m0 + r;
+            // fp32 state of step t-1 for this tile.  It may be loaded as soon as the item's dependency is known to be
+            // satisfied: always (per-step launches), or when a non-blocking look at the counter says so -- the usual
+            // case, the dependency is a whole step old -- so the load hides behind the accumulator wait.  Otherwise
+            // it is loaded after acc_full: the operand producer waited for the dependency before loading h_{t-1},
+            // and the accumulator cannot complete before those loads.  L1 is bypassed (another SM wrote the data).
+            float4* hptr = reinterpret_cast<float4*>(a.h32 + static_cast<int64_t>(row) * H + nt * 64 + half * 32);
             float4 hcur[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) hcur[i] = hnext[i];
-            {   // prefetch the next tile's state while this one is computed
-                const int ntile = tile + num_clusters;
-                if (ntile < total_tiles) {
-                    const int nrow = (ntile / n_tiles) * (2 * kTileM) + row_base + r;
-                    const float4* src = reinterpret_cast<const float4*>(h32 + static_cast<int64_t>(nrow) * H + (ntile % n_tiles) * 64 + half * 32);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) hnext[i] = nrow < B ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            ptx::mbar_wait(gi_full, it & 1);
+            bool early = true;
+            if (a.done != nullptr) {
+                const int t = item / per_step;
+                if (t > a.t_begin) {
+                    uint32_t v = 0;
+                    if (lane == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.done + (t - 1) * m_tiles + rem / n_tiles) : "memory");
+                    early = __shfl_sync(0xffffffffu, v, 0) >= dep_target;
                 }
             }
-            ptx::mbar_wait(gi_full, it & 1);
-            ptx::mbar_wait(&acc_full[buf], par);
+            if (early) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hcur[i] = row < B ? __ldcg(hptr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
+            if (!early) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hcur[i] = row < B ? __ldcg(hptr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             const uint32_t taddr = tmem_base + buf * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-            const uint32_t s_box = s_gi + row_off;
-            const float* bh = bhh + nt * kGruTileN;
-            float4* hdst = reinterpret_cast<float4*>(h32 + static_cast<int64_t>(row) * H + nt * 64 + half * 32);
+            const float* bh = a.bhh + nt * kGruTileN;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {  // 8 hidden units per iteration
                 const int c = half * 4 + i;
@@ -291,8 +337,8 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
                     }
                 }
                 if (row < B) {  // fp32 master state straight from registers
-                    hdst[2 * i] = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    hdst[2 * i + 1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                    hptr[2 * i] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                    hptr[2 * i + 1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
                 }
                 uint4 os, orl;
                 os.x = Op::pack2(hn[0], hn[1]); os.y = Op::pack2(hn[2], hn[3]);
@@ -306,6 +352,7 @@ gru_step_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1
             }
             ptx::tc_fence_before();
             ptx::fence_proxy_async_smem();  // make the st.shared results visible to the TMA store
+            if (a.done != nullptr) __threadfence();  // fp32 state stores visible before the item is published
             __syncwarp();
             if (lane == 0) {
                 ptx::mbar_arrive_leader(&acc_empty[buf]);

@@ -190,6 +190,14 @@ class MROAD(nn.Module):
             _lib.check(lib.prego_forward(self._handle, C.byref(args), stream), "prego_forward")
         return {"probs": probs, "logits": logits, "labels": labels}
 
+    def device_error(self) -> int:
+        """Watchdog flag of the persistent recurrence kernels (0 = healthy); synchronises the device."""
+        if self._handle is None:
+            return 0
+        v = C.c_int32(0)
+        _lib.check(_lib.load().prego_device_error(self._handle, C.byref(v)), "prego_device_error")
+        return int(v.value)
+
     def profile_begin(self):
         """Arm per-phase CUDA-event timing inside the library (used by bench.py's roofline)."""
         if self._handle is None:

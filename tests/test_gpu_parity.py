@@ -237,6 +237,7 @@ def test_big_batch_tensor_recurrence_vs_oracle(dev):
         torch.cuda.synchronize()
         rel, agree = _check_against_reference(out, gold, REL[prec])
         assert np.abs(h.cpu().numpy() - ref_h).max() <= 2 * REL[prec]
+        assert model.device_error() == 0
         print(f"[{prec} B=256] rel {rel:.2e} agree {agree:.4f}")
     h32 = torch.zeros(256, 1024, device=dev)
     out32 = model.infer(rgb, flow, h_state=h32, want_logits=True, precision="fp32")
@@ -359,3 +360,4 @@ def test_full_size_batch_invariance(dev):
     assert (full["probs"].sum(-1) - 1).abs().max().item() < 1e-5
     assert (full["probs"][perm] - sub["probs"]).abs().max().item() <= 1e-6
     assert torch.equal(full["labels"][perm], sub["labels"])
+    assert model.device_error() == 0  # no dependency spin of the persistent recurrence timed out
