@@ -28,9 +28,11 @@
 //   h32   [B, H]        fp32 master state
 //   done  [Tc, m_tiles] uint32 dependency counters (zeroed by the host before the launch)
 //
-// Warp roles (352 threads): warp 0 = operand TMA producer, warp 1 = TMEM alloc + MMA issuer,
-// warps 2..9 = epilogue (TMEM lane quadrant = warp % 4; warps 2-5 take hidden units 0-31 of the tile,
-// warps 6-9 units 32-63), warp 10 = gi loader + result storer + publisher.
+// Warp roles (608 threads): warp 0 = operand TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2..17 = epilogue (TMEM lane quadrant = warp % 4, hidden-unit group of 16 = (warp - 2) / 4; the
+// epilogue is latency-bound -- MUFU chains, TMEM loads -- so it is spread over 16 warps), warp 18 = gi
+// loader + result storer + publisher.  Results are staged in their own two boxes so the gi boxes can be
+// refilled as soon as the epilogue has read them (the TMA stores drain in the background).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -42,15 +44,17 @@
 
 namespace prego {
 
-constexpr int kGruThreads = 352;
-constexpr int kGruEpiWarps = 8;
+constexpr int kGruEpiWarps = 16;
+constexpr int kGruThreads = (kGruEpiWarps + 3) * 32;  // 608
+constexpr int kGruIoWarp = kGruEpiWarps + 2;          // 18
 constexpr int kGruTileN = 192;
-constexpr int kGruStages = 6;
+constexpr int kGruStages = 5;
 constexpr int kGruABytes = kTileM * kTileK * 2;                               // 16384: own 128 rows of h
 constexpr int kGruStageBytes = kGruABytes + (kGruTileN / 2) * kTileK * 2;     // + half of the W tile = 28672
 constexpr int kGruBoxBytes = 128 * 128;                                       // one [128 rows x 128 B] box
 constexpr int kGruGiBytes = 3 * kGruBoxBytes;                                 // gi r, z, n of one tile
-constexpr int kGruSmemBytes = kGruStages * kGruStageBytes + kGruGiBytes + 256 + 1024;
+constexpr int kGruOutBytes = 2 * kGruBoxBytes;                                // operand copy of h_t, relu(h_t)
+constexpr int kGruSmemBytes = kGruStages * kGruStageBytes + kGruGiBytes + kGruOutBytes + 256 + 1024;
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
@@ -100,14 +104,16 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* gi_smem = smem + kGruStages * kGruStageBytes;  // 3 boxes
-    uint64_t* bars = reinterpret_cast<uint64_t*>(gi_smem + kGruGiBytes);
+    uint8_t* out_smem = gi_smem + kGruGiBytes;              // 2 boxes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_smem + kGruOutBytes);
     uint64_t* full_bar = bars;                        // [S]  operand stage landed (leader CTA's copy is used)
     uint64_t* empty_bar = bars + kGruStages;          // [S]  operand stage consumed (multicast commit, per CTA)
     uint64_t* acc_full = bars + 2 * kGruStages;       // [2]  accumulator complete (multicast commit, per CTA)
     uint64_t* acc_empty = bars + 2 * kGruStages + 2;  // [2]  accumulator drained (leader: 8 warps x 2 CTAs)
     uint64_t* gi_full = bars + 2 * kGruStages + 4;    // [1]  gi boxes landed
-    uint64_t* res_ready = bars + 2 * kGruStages + 5;  // [1]  results written over the gi boxes
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGruStages + 6);
+    uint64_t* epi_done = bars + 2 * kGruStages + 5;   // [1]  gi boxes consumed + results staged (all epilogue warps)
+    uint64_t* out_free = bars + 2 * kGruStages + 6;   // [1]  staged results have been read by the TMA stores
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGruStages + 7);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -139,7 +145,8 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
             ptx::mbar_init(&acc_empty[b], 2 * kGruEpiWarps);
         }
         ptx::mbar_init(gi_full, 1);
-        ptx::mbar_init(res_ready, kGruEpiWarps);
+        ptx::mbar_init(epi_done, kGruEpiWarps);
+        ptx::mbar_init(out_free, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -204,58 +211,54 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
                 ptx::mma_commit_2sm(&acc_full[buf], 3);
             }
         }
-    } else if (warp == 10) {
-        // ------------------- gi loader + result storer + publisher (TMA both ways, one buffer)
+    } else if (warp == kGruIoWarp) {
+        // ------------------- gi loader + result storer + publisher (TMA both ways)
         if (lane == 0) {
             int it = 0;
             int pm0 = 0, pnt = 0, pt = 0, pmt = 0;
+            auto store_and_publish = [&](int i_prev) {
+                // results of item i_prev are staged (epi_done already observed): store, free the staging, publish
+                ptx::tma_store_3d(&tmHseq, out_smem, pnt * 64, pm0, pt + 1);
+                ptx::tma_store_3d(&tmHrelu, out_smem + kGruBoxBytes, pnt * 64, pm0, pt);
+                ptx::tma_store_commit();
+                ptx::tma_store_wait_read();
+                ptx::mbar_arrive(out_free);
+                if (a.done != nullptr) {
+                    ptx::tma_store_wait_all();
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();  // also carries the epilogue warps' fp32 state stores (observed through epi_done)
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.done + pt * m_tiles + pmt) : "memory");
+                }
+                (void)i_prev;
+            };
             for (int item = item_begin; item < item_end; item += num_clusters, ++it) {
                 const int t = item / per_step, rem = item % per_step;
                 const int mt = rem / n_tiles, nt = rem % n_tiles;
                 const int m0 = mt * (2 * kTileM) + row_base;
-                if (it >= 1) {
-                    // results of the previous item sit in the buffer: store them, then it is free
-                    ptx::mbar_wait(res_ready, (it - 1) & 1);
-                    ptx::tma_store_3d(&tmHseq, gi_smem, pnt * 64, pm0, pt + 1);
-                    ptx::tma_store_3d(&tmHrelu, gi_smem + kGruBoxBytes, pnt * 64, pm0, pt);
-                    ptx::tma_store_commit();
-                    ptx::tma_store_wait_read();
-                }
-                // gi[t] itself has no dependency (GEMM2 finished before the launch): load it right away
+                if (it >= 1) ptx::mbar_wait(epi_done, (it - 1) & 1);  // gi boxes free, previous results staged
+                // gi[t] itself has no dependency (GEMM2 finished before the launch): refill right away
                 ptx::mbar_expect_tx(gi_full, kGruGiBytes);
 #pragma unroll
                 for (int g = 0; g < 3; ++g)
                     ptx::tma_load_3d(&tmGi, gi_smem + g * kGruBoxBytes, gi_full, nt * kGruTileN + g * 64, m0, t, ptx::kEvictFirst);
-                if (it >= 1 && a.done != nullptr) {
-                    // publish the previous item: its TMA stores and the epilogue's fp32 stores are complete
-                    ptx::tma_store_wait_all();
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    __threadfence();
-                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.done + pt * m_tiles + pmt) : "memory");
-                }
+                if (it >= 1) store_and_publish(it - 1);
                 pm0 = m0; pnt = nt; pt = t; pmt = mt;
             }
             if (it >= 1) {
-                ptx::mbar_wait(res_ready, (it - 1) & 1);
-                ptx::tma_store_3d(&tmHseq, gi_smem, pnt * 64, pm0, pt + 1);
-                ptx::tma_store_3d(&tmHrelu, gi_smem + kGruBoxBytes, pnt * 64, pm0, pt);
-                ptx::tma_store_commit();
-                ptx::tma_store_wait_all();
-                if (a.done != nullptr) {
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    __threadfence();
-                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.done + pt * m_tiles + pmt) : "memory");
-                }
+                ptx::mbar_wait(epi_done, (it - 1) & 1);
+                store_and_publish(it - 1);
             }
+            ptx::tma_store_wait_all();
         }
     } else {
         // -------------------------------------------------------------------------- epilogue
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;  // which 32 hidden units of the tile
+        const int ugrp = (warp - 2) >> 2;  // which 16 hidden units of the tile
         const int r = quad * 32 + lane;    // row of the tile = TMEM lane
         const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
         const uint32_t sw = static_cast<uint32_t>(r & 7);
         const uint32_t s_box = ptx::smem_u32(gi_smem) + row_off;
+        const uint32_t s_out = ptx::smem_u32(out_smem) + row_off;
         int it = 0;
         for (int item = item_begin; item < item_end; item += num_clusters, ++it) {
             const int buf = it & 1;
@@ -268,8 +271,8 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
             // case, the dependency is a whole step old -- so the load hides behind the accumulator wait.  Otherwise
             // it is loaded after acc_full: the operand producer waited for the dependency before loading h_{t-1},
             // and the accumulator cannot complete before those loads.  L1 is bypassed (another SM wrote the data).
-            float4* hptr = reinterpret_cast<float4*>(a.h32 + static_cast<int64_t>(row) * H + nt * 64 + half * 32);
-            float4 hcur[8];
+            float4* hptr = reinterpret_cast<float4*>(a.h32 + static_cast<int64_t>(row) * H + nt * 64 + ugrp * 16);
+            float4 hcur[4];
             ptx::mbar_wait(gi_full, it & 1);
             bool early = true;
             if (a.done != nullptr) {
@@ -282,19 +285,20 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
             }
             if (early) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) hcur[i] = row < B ? __ldcg(hptr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 4; ++i) hcur[i] = row < B ? __ldcg(hptr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
             if (!early) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) hcur[i] = row < B ? __ldcg(hptr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 4; ++i) hcur[i] = row < B ? __ldcg(hptr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            ptx::mbar_wait(out_free, (it & 1) ^ 1);  // the previous item's staged results have left
             const uint32_t taddr = tmem_base + buf * 256 + (static_cast<uint32_t>(quad * 32) << 16);
             const float* bh = a.bhh + nt * kGruTileN;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {  // 8 hidden units per iteration
-                const int c = half * 4 + i;
+            for (int i = 0; i < 2; ++i) {  // 8 hidden units per iteration
+                const int c = ugrp * 2 + i;
                 uint32_t vr[8], vz[8], vn[8];
                 ptx::tmem_ld8(taddr + c * 8, vr);
                 ptx::tmem_ld8(taddr + 64 + c * 8, vz);
@@ -347,16 +351,16 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
                 for (int u = 0; u < 8; ++u) hn[u] = fmaxf(hn[u], 0.0f);
                 orl.x = Op::pack2(hn[0], hn[1]); orl.y = Op::pack2(hn[2], hn[3]);
                 orl.z = Op::pack2(hn[4], hn[5]); orl.w = Op::pack2(hn[6], hn[7]);
-                sts128(a_gi, os);                  // operand copy of h_t (over the consumed gi_r chunk)
-                sts128(a_gi + kGruBoxBytes, orl);  // relu(h_t)           (over the consumed gi_z chunk)
+                const uint32_t a_out = s_out + ((static_cast<uint32_t>(c) ^ sw) << 4);
+                sts128(a_out, os);                  // operand copy of h_t
+                sts128(a_out + kGruBoxBytes, orl);  // relu(h_t)
             }
             ptx::tc_fence_before();
             ptx::fence_proxy_async_smem();  // make the st.shared results visible to the TMA store
-            if (a.done != nullptr) __threadfence();  // fp32 state stores visible before the item is published
             __syncwarp();
             if (lane == 0) {
                 ptx::mbar_arrive_leader(&acc_empty[buf]);
-                ptx::mbar_arrive(res_ready);
+                ptx::mbar_arrive(epi_done);  // release: the publisher's gpu-scope fence is cumulative over these stores
             }
         }
     }
