@@ -241,6 +241,15 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
 #pragma unroll
                 for (int g = 0; g < 3; ++g)
                     ptx::tma_load_3d(&tmGi, gi_smem + g * kGruBoxBytes, gi_full, nt * kGruTileN + g * 64, m0, t, ptx::kEvictFirst);
+                {   // gi streams from HBM (GEMM2's 1.6 GB output): warm L2 for this pair's NEXT item now
+                    const int nitem = item + num_clusters;
+                    if (nitem < item_end) {
+                        const int t2 = nitem / per_step, rem2 = nitem % per_step;
+                        const int m2 = (rem2 / n_tiles) * (2 * kTileM) + row_base, nt2 = rem2 % n_tiles;
+#pragma unroll
+                        for (int g = 0; g < 3; ++g) ptx::tma_prefetch_3d(&tmGi, nt2 * kGruTileN + g * 64, m2, t2);
+                    }
+                }
                 if (it >= 1) store_and_publish(it - 1);
                 pm0 = m0; pnt = nt; pt = t; pmt = mt;
             }

@@ -97,6 +97,14 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, void* smem_dst, ui
         : "memory");
 }
 
+// L2 prefetch of a tensor tile (no shared memory, no barrier): warms L2 for a TMA load issued later.
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 // ----------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
