@@ -135,6 +135,7 @@ struct prego_model {
     // fp32 (exact path + SIMT recurrence)
     float *w1_f32 = nullptr, *b1 = nullptr, *ln_g = nullptr, *ln_b = nullptr;
     float *wih_f32p = nullptr, *whh_f32p = nullptr, *bih_p = nullptr, *bhh_p = nullptr;
+    float* bgi_p = nullptr;  // b_ih' + (r, z parts of b_hh'): bias of the input-gate GEMM on the batched 16-bit path
     float *wc_f32 = nullptr, *bc = nullptr;
     // 16-bit operands of the tcgen05 path, [0] = fp16, [1] = bf16
     void *w1_16[2] = {nullptr, nullptr}, *wih_16p[2] = {nullptr, nullptr}, *whh_16p[2] = {nullptr, nullptr},
@@ -346,13 +347,13 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     if (use_2cta()) {
         RC_TRY(make_tmap_w(&tmB, dt, m->wih_16p[FMT], E, 3 * H, 128));
         if (batched)
-            RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<256, 0>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2 (2cta)")));
+            RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<256, 0>{gi, m->bgi_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2 (2cta)")));
         else
             RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<256, -1>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2 (2cta)")));
     } else {
         RC_TRY(make_tmap_w(&tmB, dt, m->wih_16p[FMT], E, 3 * H, 192));
         if (batched)
-            RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, 0>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2")));
+            RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, 0>{gi, m->bgi_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2")));
         else
             RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, -1>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2")));
     }
@@ -542,7 +543,7 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
     const int64_t H = d.hidden_dim, E = d.embed_dim, K = d.num_classes;
 #define ALLOC(ptr, bytes) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes)))
     ALLOC(m->w1_f32, E * din * 4); ALLOC(m->b1, E * 4); ALLOC(m->ln_g, E * 4); ALLOC(m->ln_b, E * 4);
-    ALLOC(m->wih_f32p, 3 * H * E * 4); ALLOC(m->whh_f32p, 3 * H * H * 4); ALLOC(m->bih_p, 3 * H * 4); ALLOC(m->bhh_p, 3 * H * 4);
+    ALLOC(m->wih_f32p, 3 * H * E * 4); ALLOC(m->whh_f32p, 3 * H * H * 4); ALLOC(m->bih_p, 3 * H * 4); ALLOC(m->bhh_p, 3 * H * 4); ALLOC(m->bgi_p, 3 * H * 4);
     ALLOC(m->wc_f32, K * H * 4); ALLOC(m->bc, K * 4);
     for (int f = 0; f < 2; ++f) {
         ALLOC(m->w1_16[f], E * din * 2); ALLOC(m->wih_16p[f], 3 * H * E * 2); ALLOC(m->whh_16p[f], 3 * H * H * 2);
@@ -559,7 +560,7 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
 int prego_model_destroy(prego_model_t* m) {
     if (m == nullptr) return PREGO_OK;
     cudaSetDevice(m->device);
-    void* ptrs[] = {m->w1_f32, m->b1, m->ln_g, m->ln_b, m->wih_f32p, m->whh_f32p, m->bih_p, m->bhh_p, m->wc_f32, m->bc,
+    void* ptrs[] = {m->w1_f32, m->b1, m->ln_g, m->ln_b, m->wih_f32p, m->whh_f32p, m->bih_p, m->bhh_p, m->bgi_p, m->wc_f32, m->bc,
                     m->w1_16[0], m->w1_16[1], m->wih_16p[0], m->wih_16p[1], m->whh_16p[0], m->whh_16p[1], m->wc_16p[0],
                     m->wc_16p[1], m->xchg, m->err_flag};
     for (void* p : ptrs)
@@ -593,6 +594,7 @@ int prego_model_load_weights(prego_model_t* m, const prego_weights_t* w, void* s
     pack_rows_f32<<<g((int64_t)3 * H * H), T, 0, s>>>(w->gru_weight_hh_l0, m->whh_f32p, 3 * H, H, H, 1);
     pack_rows_f32<<<g(3 * H), T, 0, s>>>(w->gru_bias_ih_l0, m->bih_p, 3 * H, 1, H, 1);
     pack_rows_f32<<<g(3 * H), T, 0, s>>>(w->gru_bias_hh_l0, m->bhh_p, 3 * H, 1, H, 1);
+    presum_gate_bias<<<g(3 * H), T, 0, s>>>(m->bih_p, m->bhh_p, m->bgi_p, 3 * H);
     LAUNCH_CHECK("fp32 weight packing");
     RC_TRY(pack16<0>(m, w, s));
     RC_TRY(pack16<1>(m, w, s));

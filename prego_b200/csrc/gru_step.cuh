@@ -23,7 +23,8 @@
 //
 // Layouts (time-major inside a chunk so one step touches contiguous rows):
 //   hseq  [Tc+1, B, H]  16-bit operand history, slot t = h_{t-1}
-//   gi    [Tc,   B, 3H] fp16, gate-interleaved columns (tile n: [r(64) | z(64) | n(64)])
+//   gi    [Tc,   B, 3H] fp16, gate-interleaved columns (tile n: [r(64) | z(64) | n(64)]); includes b_ih and the
+//                       r / z parts of b_hh (pre-summed; b_hn must stay inside r * (W_hn h + b_hn))
 //   hrelu [Tc,   B, H]  16-bit relu(h_t)
 //   h32   [B, H]        fp32 master state
 //   done  [Tc, m_tiles] uint32 dependency counters (zeroed by the host before the launch)
@@ -111,9 +112,10 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
     uint64_t* acc_full = bars + 2 * kGruStages;       // [2]  accumulator complete (multicast commit, per CTA)
     uint64_t* acc_empty = bars + 2 * kGruStages + 2;  // [2]  accumulator drained (leader: 8 warps x 2 CTAs)
     uint64_t* gi_full = bars + 2 * kGruStages + 4;    // [1]  gi boxes landed
-    uint64_t* epi_done = bars + 2 * kGruStages + 5;   // [1]  gi boxes consumed + results staged (all epilogue warps)
+    uint64_t* epi_done = bars + 2 * kGruStages + 5;   // [1]  results staged (all epilogue warps)
     uint64_t* out_free = bars + 2 * kGruStages + 6;   // [1]  staged results have been read by the TMA stores
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGruStages + 7);
+    uint64_t* gi_free = bars + 2 * kGruStages + 7;    // [1]  gi boxes copied to registers (all epilogue warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGruStages + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -147,6 +149,7 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
         ptx::mbar_init(gi_full, 1);
         ptx::mbar_init(epi_done, kGruEpiWarps);
         ptx::mbar_init(out_free, 1);
+        ptx::mbar_init(gi_free, kGruEpiWarps);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -235,7 +238,7 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
                 const int t = item / per_step, rem = item % per_step;
                 const int mt = rem / n_tiles, nt = rem % n_tiles;
                 const int m0 = mt * (2 * kTileM) + row_base;
-                if (it >= 1) ptx::mbar_wait(epi_done, (it - 1) & 1);  // gi boxes free, previous results staged
+                if (it >= 1) ptx::mbar_wait(gi_free, (it - 1) & 1);  // the epilogue holds the previous gi in registers
                 // gi[t] itself has no dependency (GEMM2 finished before the launch): refill right away
                 ptx::mbar_expect_tx(gi_full, kGruGiBytes);
 #pragma unroll
@@ -250,7 +253,10 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
                         for (int g = 0; g < 3; ++g) ptx::tma_prefetch_3d(&tmGi, nt2 * kGruTileN + g * 64, m2, t2);
                     }
                 }
-                if (it >= 1) store_and_publish(it - 1);
+                if (it >= 1) {
+                    ptx::mbar_wait(epi_done, (it - 1) & 1);
+                    store_and_publish(it - 1);
+                }
                 pm0 = m0; pnt = nt; pt = t; pmt = mt;
             }
             if (it >= 1) {
@@ -305,6 +311,18 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
             ptx::mbar_wait(out_free, (it & 1) ^ 1);  // the previous item's staged results have left
             const uint32_t taddr = tmem_base + buf * 256 + (static_cast<uint32_t>(quad * 32) << 16);
             const float* bh = a.bhh + nt * kGruTileN;
+            // gi of this thread's 16 units -> registers, then hand the boxes back so the next item's gi streams in
+            // behind this item's gate math
+            uint4 gq[2][3];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const uint32_t a_gi = s_box + ((static_cast<uint32_t>(ugrp * 2 + i) ^ sw) << 4);
+                gq[i][0] = lds128(a_gi);
+                gq[i][1] = lds128(a_gi + kGruBoxBytes);
+                gq[i][2] = lds128(a_gi + 2 * kGruBoxBytes);
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(gi_free);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {  // 8 hidden units per iteration
                 const int c = ugrp * 2 + i;
@@ -312,18 +330,11 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
                 ptx::tmem_ld8(taddr + c * 8, vr);
                 ptx::tmem_ld8(taddr + 64 + c * 8, vz);
                 ptx::tmem_ld8(taddr + 128 + c * 8, vn);
-                const uint32_t a_gi = s_box + ((static_cast<uint32_t>(c) ^ sw) << 4);
-                const uint4 qr = lds128(a_gi);
-                const uint4 qz = lds128(a_gi + kGruBoxBytes);
-                const uint4 qn = lds128(a_gi + 2 * kGruBoxBytes);
-                float br[8], bz[8], bn[8];
+                const uint4 qr = gq[i][0], qz = gq[i][1], qn = gq[i][2];
+                float bn[8];  // b_hr / b_hz are pre-summed into gi by the input-gate GEMM; b_hn stays inside r * (.)
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(bh + c * 8) + q);
-                    const float4 y = __ldg(reinterpret_cast<const float4*>(bh + 64 + c * 8) + q);
                     const float4 w = __ldg(reinterpret_cast<const float4*>(bh + 128 + c * 8) + q);
-                    br[4 * q] = x.x; br[4 * q + 1] = x.y; br[4 * q + 2] = x.z; br[4 * q + 3] = x.w;
-                    bz[4 * q] = y.x; bz[4 * q + 1] = y.y; bz[4 * q + 2] = y.z; bz[4 * q + 3] = y.w;
                     bn[4 * q] = w.x; bn[4 * q + 1] = w.y; bn[4 * q + 2] = w.z; bn[4 * q + 3] = w.w;
                 }
                 const uint32_t gr[4] = {qr.x, qr.y, qr.z, qr.w}, gz[4] = {qz.x, qz.y, qz.z, qz.w},
@@ -343,8 +354,8 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int u = 2 * j + e;
-                        const float rr = fast_sigmoid(gir[e] + (__uint_as_float(vr[u]) + br[u]));
-                        const float zz = fast_sigmoid(giz[e] + (__uint_as_float(vz[u]) + bz[u]));
+                        const float rr = fast_sigmoid(gir[e] + __uint_as_float(vr[u]));
+                        const float zz = fast_sigmoid(giz[e] + __uint_as_float(vz[u]));
                         const float nn = fast_tanh(gin[e] + rr * (__uint_as_float(vn[u]) + bn[u]));
                         hn[u] = (hp[u] - nn) * zz + nn;
                     }

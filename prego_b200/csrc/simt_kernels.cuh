@@ -339,6 +339,12 @@ __global__ void pack_rows_f32(const float* __restrict__ src, float* __restrict__
     }
 }
 
+// bgi[p] = bih[p] + (gate(p) is r or z ? bhh[p] : 0), packed order: columns [r64 | z64 | n64] per 192.
+__global__ void presum_gate_bias(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ bgi, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bgi[i] = bih[i] + ((i % 192) < 128 ? bhh[i] : 0.f);
+}
+
 // dst rows beyond src_rows are zero (class padding of the head weight).
 template <int FMT>
 __global__ void pack_rows_16(const float* __restrict__ src, typename Op16<FMT>::T* __restrict__ dst, int rows,
