@@ -177,6 +177,7 @@ struct Plan {
     int64_t gh;            // fp32 [B, 3H]                          (fp32 batched recurrence)
     int64_t logits;        // fp32 [Mc, K]                          (fp32 head)
     int64_t sync;          // uint32 [Tc, ceil(B/256)] dependency counters  (batched 16-bit recurrence)
+    int64_t h32t;          // fp32 state in the recurrence's tiled order, rows padded to 128 (batched 16-bit recurrence)
     int64_t total;
 };
 
@@ -201,6 +202,7 @@ Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec) {
     p.gh = (!h16 && batched) ? take(B * 3 * H * 4) : 0;
     p.logits = h16 ? 0 : take(Mc * K * 4);
     p.sync = (h16 && batched) ? take(Tc * ((B + 255) / 256) * 4) : 0;
+    p.h32t = (h16 && batched) ? take((B + 127) / 128 * 128 * H * 4) : 0;
     p.total = off;
     return p;
 }
@@ -362,7 +364,9 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     // 5. recurrence
     if (batched) {
         f32_to_16<FMT><<<grid_for(B * H, 256, m->sm_count), 256, 0, s>>>(h_cur, hseq, B * H);  // history slot 0 = carried state
-        LAUNCH_CHECK("f32_to_16 (hseq slot 0)");
+        float* h32t = reinterpret_cast<float*>(ws + p.h32t);
+        h32_retile<<<grid_for((B + 127) / 128 * 128 * (H / 4), 256, m->sm_count), 256, 0, s>>>(h_cur, h32t, (int)B, H, 1);
+        LAUNCH_CHECK("f32_to_16 (hseq slot 0) / h32_retile");
         CUtensorMap tmHseq, tmW, tmGi, tmHrelu;
         RC_TRY(make_tmap_tm(&tmHseq, dt, hseq, H, B, tc + 1, 2));
         RC_TRY(make_tmap_w(&tmW, dt, m->whh_16p[FMT], H, 3 * H, kGruTileN / 2));
@@ -384,7 +388,7 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
             CUDA_TRY(cudaMemsetAsync(done, 0, (size_t)tc * m_tiles * 4, s));
             const int64_t items = (int64_t)per_step * tc;
             const int grid = 2 * items < max_grid ? (int)(2 * items) : max_grid;
-            GruSeqArgs ga{m->bhh_p, h_cur, done, m->err_flag, (int)B, H, 0, tc};
+            GruSeqArgs ga{m->bhh_p, h32t, done, m->err_flag, (int)B, H, 0, tc};
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(grid);
             cfg.blockDim = dim3(kGruThreads);
@@ -405,12 +409,14 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
         } else {
             const int grid = 2 * per_step < max_grid ? 2 * per_step : max_grid;
             for (int t = 0; t < tc; ++t) {
-                GruSeqArgs ga{m->bhh_p, h_cur, nullptr, m->err_flag, (int)B, H, t, t + 1};
+                GruSeqArgs ga{m->bhh_p, h32t, nullptr, m->err_flag, (int)B, H, t, t + 1};
                 kfn<<<grid, kGruThreads, kGruSmemBytes, s>>>(tmHseq, tmW, tmGi, tmHrelu, ga);
             }
             launches = tc + 1;
         }
+        h32_retile<<<grid_for((B + 127) / 128 * 128 * (H / 4), 256, m->sm_count), 256, 0, s>>>(h_cur, h32t, (int)B, H, 0);
         LAUNCH_CHECK("gru_seq_kernel");
+        launches += 2;
         prof_mark(m, s, PREGO_PHASE_RECURRENCE, launches);
     } else {
         RC_TRY(run_latency_recurrence(m, reinterpret_cast<const float*>(gi), h_cur, h_alt, hrelu, B, tc, FMT, 1, B, s));

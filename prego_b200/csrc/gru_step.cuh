@@ -26,7 +26,10 @@
 //   gi    [Tc,   B, 3H] fp16, gate-interleaved columns (tile n: [r(64) | z(64) | n(64)]); includes b_ih and the
 //                       r / z parts of b_hh (pre-summed; b_hn must stay inside r * (W_hn h + b_hn))
 //   hrelu [Tc,   B, H]  16-bit relu(h_t)
-//   h32   [B, H]        fp32 master state
+//   h32t  fp32 master state in the epilogue's own TILED order [B/128][H/64][16][128][4] (row block, unit block,
+//         4-unit chunk, row, unit): a warp's 32 rows x 16 B are 512 contiguous bytes, so the per-thread state
+//         loads / stores are perfectly coalesced (plain [B, H] rows cost 32 sectors per instruction and made the
+//         epilogue LSU-bound).  Converted from / to [B, H] once per chunk (simt_kernels.cuh).
 //   done  [Tc, m_tiles] uint32 dependency counters (zeroed by the host before the launch)
 //
 // Warp roles (608 threads): warp 0 = operand TMA producer, warp 1 = TMEM alloc + MMA issuer,
@@ -87,7 +90,7 @@ __device__ __forceinline__ void dep_wait(const uint32_t* ctr, uint32_t target, i
 
 struct GruSeqArgs {
     const float* bhh;   // [3H] packed order
-    float* h32;         // [B, H] fp32 master state (in/out)
+    float* h32t;        // fp32 master state, tiled order (in/out), rows padded to a multiple of 128
     uint32_t* done;     // [Tc][m_tiles] dependency counters, or nullptr (single step, no protocol)
     int* err_flag;
     int B, H;
@@ -286,7 +289,8 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
             // case, the dependency is a whole step old -- so the load hides behind the accumulator wait.  Otherwise
             // it is loaded after acc_full: the operand producer waited for the dependency before loading h_{t-1},
             // and the accumulator cannot complete before those loads.  L1 is bypassed (another SM wrote the data).
-            float4* hptr = reinterpret_cast<float4*>(a.h32 + static_cast<int64_t>(row) * H + nt * 64 + ugrp * 16);
+            float4* hptr = reinterpret_cast<float4*>(a.h32t) +
+                           ((static_cast<int64_t>(row >> 7) * (H / 64) + nt) * 16 + ugrp * 4) * 128 + (row & 127);
             float4 hcur[4];
             ptx::mbar_wait(gi_full, it & 1);
             bool early = true;
@@ -300,13 +304,13 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
             }
             if (early) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) hcur[i] = row < B ? __ldcg(hptr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 4; ++i) hcur[i] = __ldcg(hptr + i * 128);
             }
             ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
             if (!early) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) hcur[i] = row < B ? __ldcg(hptr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 4; ++i) hcur[i] = __ldcg(hptr + i * 128);
             }
             ptx::mbar_wait(out_free, (it & 1) ^ 1);  // the previous item's staged results have left
             const uint32_t taddr = tmem_base + buf * 256 + (static_cast<uint32_t>(quad * 32) << 16);
@@ -360,10 +364,9 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
                         hn[u] = (hp[u] - nn) * zz + nn;
                     }
                 }
-                if (row < B) {  // fp32 master state straight from registers
-                    hptr[2 * i] = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    hptr[2 * i + 1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
-                }
+                // fp32 master state straight from registers (padding rows are allocated, no mask needed)
+                hptr[(2 * i) * 128] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                hptr[(2 * i + 1) * 128] = make_float4(hn[4], hn[5], hn[6], hn[7]);
                 uint4 os, orl;
                 os.x = Op::pack2(hn[0], hn[1]); os.y = Op::pack2(hn[2], hn[3]);
                 os.z = Op::pack2(hn[4], hn[5]); os.w = Op::pack2(hn[6], hn[7]);

@@ -339,6 +339,27 @@ __global__ void pack_rows_f32(const float* __restrict__ src, float* __restrict__
     }
 }
 
+// fp32 GRU state between the caller's [B, H] rows and the batched recurrence's tiled order
+// [ceil(B/128)][H/64][16][128][4] (see gru_step.cuh).  to_tiled = 1: plain -> tiled (padding rows zeroed).
+__global__ void h32_retile(float* __restrict__ plain, float* __restrict__ tiled, int B, int H, int to_tiled) {
+    const int64_t rows_pad = (static_cast<int64_t>(B) + 127) / 128 * 128;
+    const int64_t total = rows_pad * (H / 4);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        // i enumerates float4 slots of the TILED buffer
+        const int r = static_cast<int>(i % 128);
+        int64_t q = i / 128;
+        const int c16 = static_cast<int>(q % 16); q /= 16;
+        const int nt = static_cast<int>(q % (H / 64));
+        const int64_t mb = q / (H / 64);
+        const int64_t row = mb * 128 + r;
+        float4* tp = reinterpret_cast<float4*>(tiled) + i;
+        float4* pp = reinterpret_cast<float4*>(plain + row * H + nt * 64 + c16 * 4);
+        if (to_tiled) *tp = row < B ? *pp : make_float4(0.f, 0.f, 0.f, 0.f);
+        else if (row < B) *pp = *tp;
+    }
+}
+
 // bgi[p] = bih[p] + (gate(p) is r or z ? bhh[p] : 0), packed order: columns [r64 | z64 | n64] per 192.
 __global__ void presum_gate_bias(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ bgi, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
