@@ -16,6 +16,7 @@
 #include "gemm_tc.cuh"
 #include "gru_latency.cuh"
 #include "gru_step.cuh"
+#include "online_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "train_kernels.cuh"
 
@@ -177,6 +178,7 @@ struct Plan {
     int64_t gh;            // fp32 [B, 3H]                          (fp32 batched recurrence)
     int64_t logits;        // fp32 [Mc, K]                          (fp32 head)
     int64_t sync;          // uint32 [Tc, ceil(B/256)] dependency counters  (batched 16-bit recurrence)
+    int64_t online;        // fp32 scratch of the per-frame online path: 8 x (E + 3H + H)
     int64_t h32t;          // fp32 state in the recurrence's tiled order, rows padded to 128 (batched 16-bit recurrence)
     int64_t total;
 };
@@ -201,6 +203,7 @@ Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec) {
     p.hrelu = take(Mc * H * (h16 ? 2 : 4));
     p.gh = (!h16 && batched) ? take(B * 3 * H * 4) : 0;
     p.logits = h16 ? 0 : take(Mc * K * 4);
+    p.online = h16 ? take(kOnlineMaxRows * (E + 3 * H + H) * 4) : 0;
     p.sync = (h16 && batched) ? take(Tc * ((B + 255) / 256) * 4) : 0;
     p.h32t = (h16 && batched) ? take((B + 127) / 128 * 128 * H * 4) : 0;
     p.total = off;
@@ -434,6 +437,49 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     return PREGO_OK;
 }
 
+// Strict per-frame online step (T == 1, B <= 8) on the GEMV kernels of online_kernels.cuh.
+template <int FMT, int R>
+int online_step_r(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt,
+                  cudaStream_t s) {
+    using OpT = typename Op16<FMT>::T;
+    const prego_dims_t& d = m->d;
+    const int rows = (int)a->B, H = d.hidden_dim, E = d.embed_dim, K = d.num_classes, Din = m->din;
+    float* y = reinterpret_cast<float*>(ws + p.online);
+    float* gi = y + kOnlineMaxRows * E;
+    float* hrelu = gi + kOnlineMaxRows * 3 * H;
+    static bool attr_set = false;
+    const int smem1 = R * Din * 2;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(online_proj1<FMT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+        attr_set = true;
+    }
+    const int wpb = kOnlineThreads / 32;
+    online_proj1<FMT, R><<<(E + wpb - 1) / wpb, kOnlineThreads, smem1, s>>>(a->rgb, a->flow, reinterpret_cast<const OpT*>(m->w1_16[FMT]), m->b1, y,
+                                                                            rows, d.d_rgb, d.d_flow, E, a->T, 0);
+    prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
+    online_proj2<FMT, R><<<(3 * H + wpb - 1) / wpb, kOnlineThreads, R * E * 2, s>>>(y, m->ln_g, m->ln_b, reinterpret_cast<const OpT*>(m->wih_16p[FMT]),
+                                                                                     m->bih_p, gi, rows, E, 3 * H, 1e-5f);
+    prof_mark(m, s, PREGO_PHASE_GEMM2, 1);
+    online_gru<FMT, R><<<(H + wpb - 1) / wpb, kOnlineThreads, R * H * 2, s>>>(gi, reinterpret_cast<const OpT*>(m->whh_16p[FMT]), m->bhh_p, h_cur, h_alt,
+                                                                               hrelu, rows, H);
+    prof_mark(m, s, PREGO_PHASE_RECURRENCE, 1);
+    online_head<<<rows, kOnlineThreads, 0, s>>>(hrelu, m->wc_f32, m->bc, a->probs, a->logits, a->labels, H, K, a->T, 0);
+    LAUNCH_CHECK("online step");
+    prof_mark(m, s, PREGO_PHASE_HEAD, 1);
+    float* tmp = h_cur; h_cur = h_alt; h_alt = tmp;
+    return PREGO_OK;
+}
+
+template <int FMT>
+int online_step(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt,
+                cudaStream_t s) {
+    const int B = (int)a->B;
+    if (B == 1) return online_step_r<FMT, 1>(m, a, p, ws, h_cur, h_alt, s);
+    if (B == 2) return online_step_r<FMT, 2>(m, a, p, ws, h_cur, h_alt, s);
+    if (B <= 4) return online_step_r<FMT, 4>(m, a, p, ws, h_cur, h_alt, s);
+    return online_step_r<FMT, 8>(m, a, p, ws, h_cur, h_alt, s);
+}
+
 // One time chunk of the exact-fp32 CUDA-core path (stream-major rows throughout).
 int chunk_f32(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt,
               int64_t t0, int tc, cudaStream_t s) {
@@ -643,9 +689,15 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
     else
         CUDA_TRY(cudaMemsetAsync(h_cur, 0, (size_t)B * H * 4, s));
 
+    const bool online = h16 && T == 1 && B <= kOnlineMaxRows && d.d_rgb % 2 == 0 && m->din % 8 == 0;
     for (int64_t t0 = 0; t0 < T; t0 += Tc) {
         const int tc = static_cast<int>(T - t0 < Tc ? T - t0 : Tc);
         prof_mark(m, s, -1, 0);
+        if (online) {
+            if (a->precision == PREGO_PREC_F16) RC_TRY(online_step<0>(m, a, p, ws, h_cur, h_alt, s));
+            else RC_TRY(online_step<1>(m, a, p, ws, h_cur, h_alt, s));
+            continue;
+        }
         if (a->precision == PREGO_PREC_F16) RC_TRY(chunk_16<0>(m, a, p, ws, h_cur, h_alt, t0, tc, s));
         else if (a->precision == PREGO_PREC_BF16) RC_TRY(chunk_16<1>(m, a, p, ws, h_cur, h_alt, t0, tc, s));
         else RC_TRY(chunk_f32(m, a, p, ws, h_cur, h_alt, t0, tc, s));

@@ -222,6 +222,34 @@ def test_single_frame_steps(dev, golden_meta):
     assert np.array_equal(got[margin > 1e-4], ref[margin > 1e-4])
 
 
+@pytest.mark.parametrize("name,prec", [("epic_b1_t96_rgbonly", "fp16"), ("asm_b2_t160", "fp16"), ("asm_b2_t160", "bf16"),
+                                       ("asm_b40_t24", "fp16")])
+def test_online_per_frame_path(dev, golden_meta, name, prec):
+    """One frame per call through the GEMV kernels (T == 1, B <= 8: online_kernels.cuh) with carried state
+    reproduces the reference's whole-sequence logits."""
+    gold = load_model_case(name)
+    cfg, rgb, flow = case_inputs(golden_meta, name, dev)
+    rows = min(rgb.shape[0], 5)   # 5 streams of the 40-stream case exercise the row masking (R = 8)
+    rgb, flow = rgb[:rows].contiguous(), flow[:rows].contiguous()
+    model = seeded_weights_checked(golden_meta, name, dev)
+    h = torch.zeros(rows, 1024, device=dev)
+    n = min(rgb.shape[1], 24)
+    lg, lb = [], []
+    for t in range(n):
+        o = model.infer(rgb[:, t:t + 1].contiguous(), flow[:, t:t + 1].contiguous(), h_state=h, want_logits=True, precision=prec)
+        lg.append(o["logits"]); lb.append(o["labels"])
+        assert (o["probs"].sum(-1) - 1).abs().max().item() < 1e-5
+    torch.cuda.synchronize()
+    logits = torch.cat(lg, 1).cpu().numpy()
+    ref = gold["logits"][:rows, :n]
+    d = np.abs(logits - ref).max()
+    assert d <= REL[prec] * np.abs(gold["logits"]).max(), d
+    labels = torch.cat(lb, 1).cpu().numpy()
+    margin = miniroad_np.top2_margin(ref)
+    clear = margin >= 4 * d
+    assert np.array_equal(labels[clear], ref.argmax(-1)[clear])
+
+
 def test_big_batch_tensor_recurrence_vs_oracle(dev):
     """B = 256 streams (two 128-row tiles, all 16 gate tiles) x 6 steps against the numpy oracle."""
     from prego_b200 import synthetic
