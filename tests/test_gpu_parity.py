@@ -315,6 +315,31 @@ def test_evaluate_writes_reference_json(dev, golden_meta, tmp_path, monkeypatch)
     assert data["video_a"]["gt"] == target[0].argmax(-1).tolist()
 
 
+def test_batched_ragged_evaluation_equals_per_video(dev, tmp_path):
+    """Length-bucketed, end-padded batches (pipeline.py) give every video the labels of its own B = 1 run, and the
+    collapsed step sequences are those of the oracle on these labels."""
+    from prego_b200 import recognize_and_aggregate, synthetic
+    cfg = dict(synthetic.EPIC_TENT_O, precision="fp32")
+    model = synthetic.seeded_model(cfg, seed=20, device=dev)
+    lens = [37, 410, 200, 1, 333, 64, 199, 401, 250, 90, 128, 77, 512, 300, 31, 222, 45, 280, 160, 5]
+    videos, gts = [], {}
+    for i, T in enumerate(lens):
+        rgb, flow = synthetic.features(200 + i, T, "cpu", zero_flow=True)
+        videos.append((f"v{i}", rgb, flow))
+        gts[f"v{i}"] = synthetic.targets(200 + i, T, 12).argmax(-1).tolist()
+    frame_json, aggregated = recognize_and_aggregate(model, videos, gts, dev, batch_streams=20, precision="fp32", out_dir=str(tmp_path))
+    assert list(frame_json) == [v[0] for v in videos]
+    for vid, rgb, flow in videos:
+        single = model.infer(rgb.unsqueeze(0).to(dev), flow.unsqueeze(0).to(dev), want_logits=True, precision="fp32")
+        ref_labels = single["labels"][0].cpu().numpy()
+        margin = miniroad_np.top2_margin(single["logits"][0].cpu().numpy())
+        got = np.array(frame_json[vid]["pred"])
+        assert got.shape == ref_labels.shape
+        assert np.array_equal(got[margin > 1e-4], ref_labels[margin > 1e-4])
+        assert aggregated[vid] == aggregate_np.aggregate_video(frame_json[vid]["pred"], gts[vid])
+    assert json.load(open(tmp_path / "aggregated_data.json")) == aggregated
+
+
 # ------------------------------------------------------------------ aggregation (bit-exact)
 def test_aggregate_golden_pair_byte_exact(dev, tmp_path, golden_meta):
     import hashlib
