@@ -145,6 +145,9 @@ struct prego_model {
     uint2* xchg = nullptr;
     int* err_flag = nullptr;
     uint32_t tag_base = 0;
+    // side stream: stages the features of the next time chunk (HBM-bound) under the current chunk's GEMMs
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     // optional phase profiling (CUDA events on the launching stream)
     bool prof = false;
     int prof_n = 0;
@@ -171,6 +174,7 @@ inline void prof_mark(prego_model* m, cudaStream_t s, int phase, int launches) {
 struct Plan {
     int64_t h32_a, h32_b;  // [B, H] fp32 state ping-pong
     int64_t xb;            // 16-bit [Mc, Din]                      (16-bit modes)
+    int64_t xb2;           // second staging buffer: features of chunk c+1 are staged while chunk c computes (0 = none)
     int64_t ye;            // fp16 y -> 16-bit e in place, or fp32  [Mc, E]
     int64_t gi;            // [Mc, 3H] fp16 (batched 16-bit recurrence) or fp32
     int64_t hseq;          // 16-bit [Tc+1, B, H]                   (batched 16-bit recurrence)
@@ -183,7 +187,7 @@ struct Plan {
     int64_t total;
 };
 
-Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec) {
+Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec, bool double_xb = true) {
     Plan p{};
     const int64_t Mc = B * Tc, H = d.hidden_dim, E = d.embed_dim, Din = d.d_rgb + d.d_flow, K = d.num_classes;
     int64_t off = 0;
@@ -197,6 +201,7 @@ Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec) {
     const bool h16 = prec != PREGO_PREC_FP32;
     const bool batched = B > kLatencyMaxB;
     p.xb = h16 ? take(Mc * Din * 2) : 0;
+    p.xb2 = (h16 && double_xb && B > kLatencyMaxB) ? take(Mc * Din * 2) : 0;
     p.ye = take(Mc * E * (h16 ? 2 : 4));
     p.gi = take(Mc * 3 * H * ((h16 && batched) ? 2 : 4));
     p.hseq = (h16 && batched) ? take(B * (Tc + 1) * H * 2) : 0;
@@ -251,6 +256,15 @@ bool use_persistent_gru() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("PREGO_GRU_PERSISTENT");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+bool use_overlap() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PREGO_STAGE_OVERLAP");
         v = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
     return v == 1;
@@ -312,8 +326,21 @@ int run_latency_recurrence(prego_model* m, const float* gi, float*& h_cur, float
 
 // One time chunk of the 16-bit tensor-core path.
 template <int FMT>
+int stage_chunk(prego_model* m, const prego_forward_args_t* a, void* xb, int64_t t0, int tc, int blocks_per_sm, cudaStream_t s) {
+    using OpT = typename Op16<FMT>::T;
+    const int64_t Mc = a->B * tc;
+    int grid = grid_for(Mc * (m->din / 8), 256, m->sm_count);
+    if (blocks_per_sm > 0 && grid > m->sm_count * blocks_per_sm) grid = m->sm_count * blocks_per_sm;
+    stage_features_16<FMT><<<grid, 256, 0, s>>>(a->rgb, a->flow, reinterpret_cast<OpT*>(xb), Mc, m->d.d_rgb, m->d.d_flow, (int)a->B, (int)a->T, (int)t0);
+    LAUNCH_CHECK("stage_features_16");
+    return PREGO_OK;
+}
+
+// ci = chunk index; with overlap the features of chunk ci were staged into xb[ci & 1] ahead of time on the side
+// stream, and this call stages chunk ci + 1 (starting at t_next, tc_next frames) behind its own GEMM1.
+template <int FMT>
 int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt,
-             int64_t t0, int tc, cudaStream_t s) {
+             int64_t t0, int tc, cudaStream_t s, int ci = 0, bool overlap = false, int64_t t_next = 0, int tc_next = 0) {
     using OpT = typename Op16<FMT>::T;
     const DType dt = FMT == 0 ? kF16 : kBF16;
     const prego_dims_t& d = m->d;
@@ -321,7 +348,7 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     const int Mi = static_cast<int>(Mc);
     const int H = d.hidden_dim, E = d.embed_dim, K = d.num_classes, Din = m->din;
     const bool batched = B > kLatencyMaxB;
-    OpT* xb = reinterpret_cast<OpT*>(ws + p.xb);
+    OpT* xb = reinterpret_cast<OpT*>(ws + ((overlap && (ci & 1)) ? p.xb2 : p.xb));
     void* ye = ws + p.ye;
     void* gi = ws + p.gi;
     OpT* hseq = reinterpret_cast<OpT*>(ws + p.hseq);
@@ -329,8 +356,11 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     CUtensorMap tmA, tmB;
 
     // 1. stage features: concat + operand rounding (replaces torch.cat, rnn.py:53)
-    stage_features_16<FMT><<<grid_for(Mc * (Din / 8), 256, m->sm_count), 256, 0, s>>>(a->rgb, a->flow, xb, Mc, d.d_rgb, d.d_flow, (int)B, (int)T, (int)t0);
-    LAUNCH_CHECK("stage_features_16");
+    if (!overlap) {
+        RC_TRY(stage_chunk<FMT>(m, a, xb, t0, tc, 0, s));
+    } else {
+        CUDA_TRY(cudaStreamWaitEvent(s, m->ev_ready[ci & 1], 0));  // staged on the side stream (or by the prologue)
+    }
     prof_mark(m, s, PREGO_PHASE_STAGE, 1);
     // 2. y = x W1^T + b1  (fp16 out; rows stay time-major, m = t*B + b)
     RC_TRY(make_tmap_a(&tmA, dt, xb, Din, Mc));
@@ -340,6 +370,16 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     } else {
         RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 256));
         RC_TRY((launch_gemm_tc<256, 4, FMT>(tmA, tmB, Mi, E, Din, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1")));
+    }
+    if (overlap) {
+        CUDA_TRY(cudaEventRecord(m->ev_free[ci & 1], s));  // GEMM1 has consumed this staging buffer
+        if (tc_next > 0) {
+            // next chunk's features -> the other buffer, on the side stream, issued AFTER GEMM1 so the GEMM's CTAs are
+            // placed first; a capped grid leaves room for them to co-reside (HBM-bound next to tensor-bound work)
+            CUDA_TRY(cudaStreamWaitEvent(m->side, m->ev_free[(ci + 1) & 1], 0));
+            RC_TRY(stage_chunk<FMT>(m, a, ws + (((ci + 1) & 1) ? p.xb2 : p.xb), t_next, tc_next, 4, m->side));
+            CUDA_TRY(cudaEventRecord(m->ev_ready[(ci + 1) & 1], m->side));
+        }
     }
     prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
     // 3. e = relu(LN(y))  (in place, operand format)
@@ -605,6 +645,12 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
 #undef ALLOC
     CUDA_TRY(cudaMemset(m->xchg, 0, 2 * 4 * H * sizeof(uint2)));
     CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
+    CUDA_TRY(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&m->ev_begin, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&m->ev_ready[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming));
+    }
     *out = m;
     return PREGO_OK;
 }
@@ -619,6 +665,9 @@ int prego_model_destroy(prego_model_t* m) {
         if (p != nullptr) cudaFree(p);
     for (cudaEvent_t e : m->prof_ev)
         if (e != nullptr) cudaEventDestroy(e);
+    for (cudaEvent_t e : {m->ev_begin, m->ev_ready[0], m->ev_ready[1], m->ev_free[0], m->ev_free[1]})
+        if (e != nullptr) cudaEventDestroy(e);
+    if (m->side != nullptr) cudaStreamDestroy(m->side);
     delete m;
     return PREGO_OK;
 }
@@ -672,7 +721,10 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
     if (h16 && m->kpad == 0) return fail(PREGO_ERR_INVALID, "16-bit paths support num_classes <= 128 (got %d); use PREGO_PREC_FP32", d.num_classes);
     const int64_t Tc = (a->chunk_T > 0 && a->chunk_T < T) ? a->chunk_T : T;
     if (B * Tc >= (int64_t(1) << 31) / 4) return fail(PREGO_ERR_INVALID, "B * chunk_T = %lld is too large for one pass; lower chunk_T", (long long)(B * Tc));
-    const Plan p = make_plan(d, B, Tc, a->precision);
+    // double-buffered feature staging only when there is a next chunk to stage and the caller's workspace has room
+    Plan p = make_plan(d, B, Tc, a->precision, true);
+    const bool overlap = h16 && T > Tc && B > kLatencyMaxB && p.xb2 != 0 && a->workspace_bytes >= (size_t)p.total && use_overlap();
+    if (!overlap) p = make_plan(d, B, Tc, a->precision, false);
     if (a->workspace == nullptr || a->workspace_bytes < (size_t)p.total)
         return fail(PREGO_ERR_WORKSPACE, "workspace too small: need %lld bytes, got %zu", (long long)p.total, a->workspace_bytes);
     if ((reinterpret_cast<uintptr_t>(a->workspace) & 1023) != 0) return fail(PREGO_ERR_INVALID, "workspace must be 1024-byte aligned");
@@ -690,16 +742,27 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
         CUDA_TRY(cudaMemsetAsync(h_cur, 0, (size_t)B * H * 4, s));
 
     const bool online = h16 && T == 1 && B <= kOnlineMaxRows && d.d_rgb % 2 == 0 && m->din % 8 == 0;
-    for (int64_t t0 = 0; t0 < T; t0 += Tc) {
+    if (overlap) {
+        // prologue: chunk 0 is staged on the main stream; both staging buffers start out free
+        const int tc0 = static_cast<int>(T < Tc ? T : Tc);
+        if (a->precision == PREGO_PREC_F16) RC_TRY(stage_chunk<0>(m, a, ws + p.xb, 0, tc0, 0, s));
+        else RC_TRY(stage_chunk<1>(m, a, ws + p.xb, 0, tc0, 0, s));
+        CUDA_TRY(cudaEventRecord(m->ev_ready[0], s));
+        CUDA_TRY(cudaEventRecord(m->ev_free[1], s));  // also orders the side stream after everything before this call
+    }
+    int ci = 0;
+    for (int64_t t0 = 0; t0 < T; t0 += Tc, ++ci) {
         const int tc = static_cast<int>(T - t0 < Tc ? T - t0 : Tc);
+        const int64_t t_next = t0 + Tc;
+        const int tc_next = t_next < T ? static_cast<int>(T - t_next < Tc ? T - t_next : Tc) : 0;
         prof_mark(m, s, -1, 0);
         if (online) {
             if (a->precision == PREGO_PREC_F16) RC_TRY(online_step<0>(m, a, p, ws, h_cur, h_alt, s));
             else RC_TRY(online_step<1>(m, a, p, ws, h_cur, h_alt, s));
             continue;
         }
-        if (a->precision == PREGO_PREC_F16) RC_TRY(chunk_16<0>(m, a, p, ws, h_cur, h_alt, t0, tc, s));
-        else if (a->precision == PREGO_PREC_BF16) RC_TRY(chunk_16<1>(m, a, p, ws, h_cur, h_alt, t0, tc, s));
+        if (a->precision == PREGO_PREC_F16) RC_TRY(chunk_16<0>(m, a, p, ws, h_cur, h_alt, t0, tc, s, ci, overlap, t_next, tc_next));
+        else if (a->precision == PREGO_PREC_BF16) RC_TRY(chunk_16<1>(m, a, p, ws, h_cur, h_alt, t0, tc, s, ci, overlap, t_next, tc_next));
         else RC_TRY(chunk_f32(m, a, p, ws, h_cur, h_alt, t0, tc, s));
     }
     if (a->h_state != nullptr)
