@@ -736,12 +736,15 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
     float* h_cur = reinterpret_cast<float*>(ws + p.h32_a);
     float* h_alt = reinterpret_cast<float*>(ws + p.h32_b);
 
-    if (a->h_state != nullptr)
-        CUDA_TRY(cudaMemcpyAsync(h_cur, a->h_state, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, s));
-    else
-        CUDA_TRY(cudaMemsetAsync(h_cur, 0, (size_t)B * H * 4, s));
-
     const bool online = h16 && T == 1 && B <= kOnlineMaxRows && d.d_rgb % 2 == 0 && m->din % 8 == 0;
+    if (online && a->h_state != nullptr) {
+        h_cur = a->h_state;  // per-frame path: read the caller's state in place (one copy back instead of two)
+    } else if (a->h_state != nullptr) {
+        CUDA_TRY(cudaMemcpyAsync(h_cur, a->h_state, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, s));
+    } else {
+        CUDA_TRY(cudaMemsetAsync(h_cur, 0, (size_t)B * H * 4, s));
+    }
+
     if (overlap) {
         // prologue: chunk 0 is staged on the main stream; both staging buffers start out free
         const int tc0 = static_cast<int>(T < Tc ? T : Tc);

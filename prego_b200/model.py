@@ -190,6 +190,11 @@ class MROAD(nn.Module):
             _lib.check(lib.prego_forward(self._handle, C.byref(args), stream), "prego_forward")
         return {"probs": probs, "logits": logits, "labels": labels}
 
+    def online_session(self, num_streams: int, device=None, precision=None, want_probs=False):
+        """Strict per-frame online inference: ``session.step(rgb_frame, flow_frame) -> labels`` with the GRU state
+        carried inside the session and all per-call host work hoisted out (BASELINE configs[1])."""
+        return OnlineSession(self, num_streams, device, precision, want_probs)
+
     def device_error(self) -> int:
         """Watchdog flag of the persistent recurrence kernels (0 = healthy); synchronises the device."""
         if self._handle is None:
@@ -221,3 +226,45 @@ class MROAD(nn.Module):
         out = self.infer(rgb_input, flow_input, want_probs=True, want_labels=True)
         self.last_labels = out["labels"]
         return {"logits": out["probs"]}
+
+
+class OnlineSession:
+    """One frame per call for ``B`` concurrent streams (B <= 8 takes the GEMV kernels of online_kernels.cuh).
+    Buffers, workspace and the argument struct are built once; ``step`` only patches two pointers."""
+
+    def __init__(self, model: MROAD, num_streams: int, device=None, precision=None, want_probs=False):
+        lib = _lib.load()
+        if device is None:
+            device = next(model.parameters()).device
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("prego_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self.model, self.device, self.B = model, device, int(num_streams)
+        self.prec = _lib.PRECISIONS[precision or model.precision]
+        with torch.cuda.device(device):
+            model._ensure_handle(device)
+            model._sync_weights(lib, device)
+            self.h = torch.zeros(self.B, model.hidden_dim, dtype=torch.float32, device=device)
+            self.labels = torch.empty(self.B, 1, dtype=torch.int32, device=device)
+            self.probs = torch.empty(self.B, 1, model.out_dim, dtype=torch.float32, device=device) if want_probs else None
+            need = lib.prego_workspace_bytes(model._handle, self.B, 1, self.prec)
+            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
+            ws_ptr = self._ws.data_ptr() + (-self._ws.data_ptr()) % 1024
+            self._args = _lib.ForwardArgs(None, None, self.B, 1, self.h.data_ptr(),
+                                          self.probs.data_ptr() if want_probs else None, None, self.labels.data_ptr(),
+                                          ws_ptr, need, self.prec, 1)
+        self._lib, self._handle, self._ref = lib, model._handle, C.byref(self._args)
+
+    def reset(self):
+        self.h.zero_()
+
+    def step(self, rgb_frame, flow_frame):
+        """rgb_frame / flow_frame: contiguous fp32 CUDA tensors with B * D elements ([B, D] or [B, 1, D]).
+        Returns the int32 label tensor [B, 1] (device; overwritten by the next step)."""
+        a = self._args
+        a.rgb = rgb_frame.data_ptr() if rgb_frame is not None else None
+        a.flow = flow_frame.data_ptr() if flow_frame is not None else None
+        rc = self._lib.prego_forward(self._handle, self._ref, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _lib.check(rc, "prego_forward")
+        return self.labels

@@ -250,6 +250,26 @@ def test_online_per_frame_path(dev, golden_meta, name, prec):
     assert np.array_equal(labels[clear], ref.argmax(-1)[clear])
 
 
+def test_online_session_matches_infer(dev, golden_meta):
+    name = "epic_b1_t300"
+    gold = load_model_case(name)
+    cfg, rgb, flow = case_inputs(golden_meta, name, dev)
+    model = seeded_weights_checked(golden_meta, name, dev)
+    sess = model.online_session(1, dev, "fp16", want_probs=True)
+    got = []
+    for t in range(40):
+        got.append(sess.step(rgb[0, t].contiguous(), flow[0, t].contiguous()).clone())
+        assert abs(float(sess.probs.sum()) - 1) < 1e-5
+    torch.cuda.synchronize()
+    labels = torch.cat(got, 1).cpu().numpy()[0]
+    margin = miniroad_np.top2_margin(gold["logits"])[0, :40]
+    ref = gold["probs"].argmax(-1)[0, :40]
+    assert np.array_equal(labels[margin > 4e-3], ref[margin > 4e-3])
+    assert np.abs(sess.h.cpu().numpy()).max() > 0
+    sess.reset()
+    assert float(sess.h.abs().sum()) == 0.0
+
+
 def test_big_batch_tensor_recurrence_vs_oracle(dev):
     """B = 256 streams (two 128-row tiles, all 16 gate tiles) x 6 steps against the numpy oracle."""
     from prego_b200 import synthetic
