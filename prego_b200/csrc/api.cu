@@ -487,11 +487,11 @@ int online_step_r(prego_model* m, const prego_forward_args_t* a, const Plan& p, 
     float* y = reinterpret_cast<float*>(ws + p.online);
     float* gi = y + kOnlineMaxRows * E;
     float* hrelu = gi + kOnlineMaxRows * 3 * H;
-    static bool attr_set = false;
+    static int attr_max = 48 * 1024;  // opt-in limit set so far for this instantiation (models may differ in Din)
     const int smem1 = R * Din * 2;
-    if (!attr_set) {
+    if (smem1 > attr_max) {
         CUDA_TRY(cudaFuncSetAttribute(online_proj1<FMT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-        attr_set = true;
+        attr_max = smem1;
     }
     const int wpb = kOnlineThreads / 32;
     online_proj1<FMT, R><<<(E + wpb - 1) / wpb, kOnlineThreads, smem1, s>>>(a->rgb, a->flow, reinterpret_cast<const OpT*>(m->w1_16[FMT]), m->b1, y,
