@@ -33,25 +33,37 @@ __device__ __forceinline__ void warp_row_dot(const typename Op16<FMT>::T* __rest
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.f;
     const uint4* w4 = reinterpret_cast<const uint4*>(wrow);
-    for (int i = lane; i < K / 8; i += 32) {
-        const uint4 w = __ldg(w4 + i);
-        const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
-        float wf[8];
+    const int nvec = K / 8;
+    // four 16-byte weight loads in flight per lane (the rows stream from L2: latency-bound without the batching)
+    for (int i0 = lane; i0 < nvec; i0 += 128) {
+        uint4 w[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 f = Op::unpack2(wu[j]);
-            wf[2 * j] = f.x;
-            wf[2 * j + 1] = f.y;
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            w[u] = i < nvec ? __ldg(w4 + i) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const uint4 x = *reinterpret_cast<const uint4*>(xs + static_cast<int64_t>(r) * K + i * 8);
-            const uint32_t xu[4] = {x.x, x.y, x.z, x.w};
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            if (i >= nvec) break;
+            const uint32_t wu[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+            float wf[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float2 f = Op::unpack2(xu[j]);
-                acc[r] = fmaf(wf[2 * j], f.x, acc[r]);
-                acc[r] = fmaf(wf[2 * j + 1], f.y, acc[r]);
+                const float2 f = Op::unpack2(wu[j]);
+                wf[2 * j] = f.x;
+                wf[2 * j + 1] = f.y;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint4 x = *reinterpret_cast<const uint4*>(xs + static_cast<int64_t>(r) * K + i * 8);
+                const uint32_t xu[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = Op::unpack2(xu[j]);
+                    acc[r] = fmaf(wf[2 * j], f.x, acc[r]);
+                    acc[r] = fmaf(wf[2 * j + 1], f.y, acc[r]);
+                }
             }
         }
     }
