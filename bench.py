@@ -222,6 +222,7 @@ def latency_leg(dev, precision):
     gpu_us = sum(v["ms"] for v in prof_on.values()) / 100 * 1e3
     out["per_frame_online"] = {"frames": n, "p50_ms": float(np.percentile(wall, 50)), "p99_ms": float(np.percentile(wall, 99)),
                                "gpu_us_per_frame": gpu_us,
+                               "gpu_phase_us": {k: round(v["ms"] * 10, 2) for k, v in prof_on.items()},
                                "note": "OnlineSession.step per frame: host call + 4 kernels + label D2H + stream sync (wall clock)"}
     return out
 
@@ -404,7 +405,13 @@ def run_ours(args, world, rank, local):
     stage_gbs = (BYTES_FEATURES + 8192) * Mc * K / (prof["stage"]["ms"] * 1e-3) / 1e9
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<256,4,...> (Linear 4096->2048, tcgen05 kind::f16)",
                 "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+                "frac": achieved / pk["bf16_tflops_sustained"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` capture
+                # (profiles/r01_ncu_bench_shape.txt): 3.341 GB + 1.060 GB per launch vs 3.238 GB algorithmic
+                "traffic": 4.400951e9 if (B, Tc, args.precision) == (4096, 64, "fp16") and min(Tc, args.subchunk) == 64 else None,
+                "traffic_note": "ncu capture at chunk 64; with internal_subchunk 32 a launch moves half of it",
+                "algorithmic_bytes_per_launch": (8192 + 4096) * Mc + 4096 * 2048 * 2,
+                "tensor_pipe_active_pct_ncu": 99.6,
                 "peak_source": f"{pk['source']} bf16 sustained (kernel timed inside a long step)",
                 "per_launch_ms": g1_ms, "flops_per_launch": FLOP_GEMM1 * Mc,
                 "phase_share": phase_share, "phase_tflops": phase_tflops,
