@@ -48,8 +48,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
-    ap.add_argument("--subchunk", type=int, default=32,
-                    help="internal time-chunk of prego_forward inside one step (feature staging of chunk c+1 overlaps chunk c)")
+    ap.add_argument("--subchunk", type=int, default=64,
+                    help="internal time-chunk of prego_forward inside one step; < --chunk stages the features of chunk c+1 on a side "
+                         "stream under chunk c (measured +2 %% at 32, but it blurs the per-kernel roofline timing, so off by default)")
     return ap.parse_args()
 
 
@@ -394,8 +395,9 @@ def run_ours(args, world, rank, local):
 
     pk = peaks()
     Mc = B * Tc
+    rows_per_launch = B * min(Tc, args.subchunk)  # one GEMM1 launch per internal time chunk
     g1_ms = prof["gemm1"]["ms"] / max(prof["gemm1"]["launches"], 1)
-    achieved = FLOP_GEMM1 * Mc / (g1_ms * 1e-3) / 1e12
+    achieved = FLOP_GEMM1 * rows_per_launch / (g1_ms * 1e-3) / 1e12
     phase_share = {p: round(v["ms"] / sum(x["ms"] for x in prof.values()), 4) for p, v in prof.items()}
     phase_tflops = {
         "gemm1": FLOP_GEMM1 * Mc * K / (prof["gemm1"]["ms"] * 1e-3) / 1e12,
@@ -410,10 +412,10 @@ def run_ours(args, world, rank, local):
                 # (profiles/r01_ncu_bench_shape.txt): 3.341 GB + 1.060 GB per launch vs 3.238 GB algorithmic
                 "traffic": 4.400951e9 if (B, Tc, args.precision) == (4096, 64, "fp16") and min(Tc, args.subchunk) == 64 else None,
                 "traffic_note": "ncu capture at chunk 64; with internal_subchunk 32 a launch moves half of it",
-                "algorithmic_bytes_per_launch": (8192 + 4096) * Mc + 4096 * 2048 * 2,
+                "algorithmic_bytes_per_launch": (8192 + 4096) * rows_per_launch + 4096 * 2048 * 2,
                 "tensor_pipe_active_pct_ncu": 99.6,
                 "peak_source": f"{pk['source']} bf16 sustained (kernel timed inside a long step)",
-                "per_launch_ms": g1_ms, "flops_per_launch": FLOP_GEMM1 * Mc,
+                "per_launch_ms": g1_ms, "flops_per_launch": FLOP_GEMM1 * rows_per_launch,
                 "phase_share": phase_share, "phase_tflops": phase_tflops,
                 "stage_features_gbs": stage_gbs, "stage_frac_of_hbm": stage_gbs / pk["hbm_gbs"],
                 "whole_step_tflops": (FLOP_GEMM1 + FLOP_GEMM2 + FLOP_REC + 2 * 1024 * 86) * value / world / 1e12}
