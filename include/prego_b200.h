@@ -92,6 +92,18 @@ size_t prego_workspace_bytes(const prego_model_t* model, int64_t B, int64_t chun
 /* Replaces MROAD.forward (rnn.py:51-71) plus the label extraction of Evaluate.eval (trainer/eval.py:53). */
 int prego_forward(prego_model_t* model, const prego_forward_args_t* args, void* stream);
 
+/* ---- Per-frame online sessions (BASELINE configs[1]: one frame per call, carried GRU state; rnn.py:51-71 called
+ * with T = 1) for 1..8 concurrent streams.  The session owns a CUDA graph of the per-frame kernels; a step costs
+ * one graph launch.  h_state [B, H] (in/out), probs [B, K] / logits [B, K] / labels [B] (each may be NULL) are
+ * caller-owned device buffers fixed for the lifetime of the session; rgb / flow point at the frame's B x d_rgb /
+ * B x d_flow fp32 features (device) and may change every step.  Weights are captured at open time: re-open after
+ * prego_model_load_weights. */
+typedef struct prego_online prego_online_t;
+int prego_online_open(prego_model_t* model, int32_t num_streams, int32_t precision, float* h_state, float* probs,
+                      float* logits, int32_t* labels, prego_online_t** out);
+int prego_online_step(prego_online_t* session, const float* rgb, const float* flow, void* stream);
+int prego_online_close(prego_online_t* session);
+
 /* Device-side watchdog: the persistent recurrence kernels bound every inter-CTA spin; if a peer never shows up
  * they set a flag instead of hanging the GPU.  Reads (and clears) it; synchronises the device.  0 = healthy. */
 int prego_device_error(prego_model_t* model, int32_t* out);

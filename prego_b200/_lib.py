@@ -58,6 +58,10 @@ SIGNATURES = {
     "prego_model_load_weights": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_void_p]),
     "prego_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
     "prego_forward": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.c_void_p]),
+    "prego_online_open": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_void_p)]),
+    "prego_online_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prego_online_close": (C.c_int, [C.c_void_p]),
     "prego_device_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "prego_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64]),
     "prego_train_forward": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),

@@ -866,3 +866,4 @@ int prego_gemm_f32_nt(const float* A, const float* W, const float* bias, float* 
 }  // extern "C"
 
 #include "train_api.inc"
+#include "online_api.inc"

@@ -229,8 +229,9 @@ class MROAD(nn.Module):
 
 
 class OnlineSession:
-    """One frame per call for ``B`` concurrent streams (B <= 8 takes the GEMV kernels of online_kernels.cuh).
-    Buffers, workspace and the argument struct are built once; ``step`` only patches two pointers."""
+    """One frame per call for ``B`` <= 8 concurrent streams (GEMV kernels of online_kernels.cuh, replayed as one
+    CUDA graph per frame through ``prego_online_*``).  Buffers are allocated once; ``step`` patches two pointers.
+    The packed weights are captured when the session is opened: open a new session after changing parameters."""
 
     def __init__(self, model: MROAD, num_streams: int, device=None, precision=None, want_probs=False):
         lib = _lib.load()
@@ -239,21 +240,32 @@ class OnlineSession:
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("prego_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        prec_name = precision or model.precision
+        if prec_name == "fp32":
+            raise RuntimeError("online sessions run in 'fp16' or 'bf16' (use MROAD.infer for the exact fp32 path)")
         self.model, self.device, self.B = model, device, int(num_streams)
-        self.prec = _lib.PRECISIONS[precision or model.precision]
+        self._lib, self._session = lib, C.c_void_p()
         with torch.cuda.device(device):
             model._ensure_handle(device)
             model._sync_weights(lib, device)
             self.h = torch.zeros(self.B, model.hidden_dim, dtype=torch.float32, device=device)
             self.labels = torch.empty(self.B, 1, dtype=torch.int32, device=device)
             self.probs = torch.empty(self.B, 1, model.out_dim, dtype=torch.float32, device=device) if want_probs else None
-            need = lib.prego_workspace_bytes(model._handle, self.B, 1, self.prec)
-            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
-            ws_ptr = self._ws.data_ptr() + (-self._ws.data_ptr()) % 1024
-            self._args = _lib.ForwardArgs(None, None, self.B, 1, self.h.data_ptr(),
-                                          self.probs.data_ptr() if want_probs else None, None, self.labels.data_ptr(),
-                                          ws_ptr, need, self.prec, 1)
-        self._lib, self._handle, self._ref = lib, model._handle, C.byref(self._args)
+            torch.cuda.current_stream(device).synchronize()  # weight packing done before the graph is built
+            _lib.check(lib.prego_online_open(model._handle, self.B, _lib.PRECISIONS[prec_name], self.h.data_ptr(),
+                                             self.probs.data_ptr() if want_probs else None, None, self.labels.data_ptr(),
+                                             C.byref(self._session)), "prego_online_open")
+
+    def close(self):
+        if self._session is not None and self._session.value:
+            self._lib.prego_online_close(self._session)
+            self._session = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def reset(self):
         self.h.zero_()
@@ -261,10 +273,9 @@ class OnlineSession:
     def step(self, rgb_frame, flow_frame):
         """rgb_frame / flow_frame: contiguous fp32 CUDA tensors with B * D elements ([B, D] or [B, 1, D]).
         Returns the int32 label tensor [B, 1] (device; overwritten by the next step)."""
-        a = self._args
-        a.rgb = rgb_frame.data_ptr() if rgb_frame is not None else None
-        a.flow = flow_frame.data_ptr() if flow_frame is not None else None
-        rc = self._lib.prego_forward(self._handle, self._ref, torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self._lib.prego_online_step(self._session, rgb_frame.data_ptr() if rgb_frame is not None else None,
+                                         flow_frame.data_ptr() if flow_frame is not None else None,
+                                         torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
-            _lib.check(rc, "prego_forward")
+            _lib.check(rc, "prego_online_step")
         return self.labels
