@@ -30,6 +30,7 @@ extern "C" {
 /* Compute precision of the projection / recurrence / head GEMMs. */
 #define PREGO_PREC_BF16 0       /* tcgen05 kind::f16, bf16 operands, fp32 accumulate (throughput path) */
 #define PREGO_PREC_FP32 1       /* exact fp32 FFMA path (1e-4 parity mode) */
+#define PREGO_PREC_TF32 3       /* training only: fp32 storage, tcgen05 kind::tf32 operands, fp32 accumulate */
 #define PREGO_PREC_F16 2        /* tcgen05 kind::f16, fp16 operands (10-bit mantissa = TF32 accuracy at the bf16 rate),
                                    fp32 accumulate; inputs saturate at +-65504 (default throughput path) */
 
@@ -180,6 +181,10 @@ int prego_rle(const int32_t* seq, const int64_t* seg_offsets, const int64_t* fin
  * PREGO_PREC_BF16) on the tcgen05 path; N % tile_n == 0, tile_n in {96, 128, 192, 256}, K % 64 == 0. */
 int prego_gemm16_nt(const void* A, const void* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
                     int32_t tile_n, int32_t precision, void* stream);
+/* Same contract with fp32 storage and TF32 tensor-core operands (CTA pairs); N % 256 == 0, K % 32 == 0;
+ * accumulate != 0 adds into C.  Used by the PREGO_PREC_TF32 training step. */
+int prego_gemm_tf32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
+                       int32_t accumulate, void* stream);
 /* Same contract in exact fp32 on CUDA cores (K % 16 == 0). */
 int prego_gemm_f32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
                       void* stream);

@@ -105,6 +105,18 @@ int make_tmap_w(CUtensorMap* tm, DType dt, const void* base, uint64_t k, uint64_
     const uint32_t box[2] = {kTileK, tile_n};
     return make_tmap(tm, dt, 2, base, dims, str, box);
 }
+// fp32 (tf32) operands of the CTA-pair GEMM: 32 elements = 128 bytes per swizzle row.
+int make_tmap_a32(CUtensorMap* tm, const void* base, uint64_t k, uint64_t rows, uint64_t ld_elems) {
+    const uint64_t dims[3] = {k, 1, rows}, str[2] = {ld_elems * 4, ld_elems * 4};
+    const uint32_t box[3] = {32, 1, kTileM};
+    return make_tmap(tm, kF32, 3, base, dims, str, box);
+}
+int make_tmap_w32(CUtensorMap* tm, const void* base, uint64_t k, uint64_t n, uint64_t ld_elems, uint32_t box_rows) {
+    const uint64_t dims[2] = {k, n}, str[1] = {ld_elems * 4};
+    const uint32_t box[2] = {32, box_rows};
+    return make_tmap(tm, kF32, 2, base, dims, str, box);
+}
+
 // time-major activation [slots, B, cols] (elem_bytes each), box (128 B worth of cols, 128 rows, 1).
 int make_tmap_tm(CUtensorMap* tm, DType dt, const void* base, uint64_t cols, uint64_t B, uint64_t slots, int elem_bytes) {
     const uint64_t dims[3] = {cols, B, slots}, str[2] = {cols * elem_bytes, B * cols * elem_bytes};
@@ -250,6 +262,17 @@ int launch_gemm_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N
     kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, a_c1, epi);
     LAUNCH_CHECK(name);
     return PREGO_OK;
+}
+
+// C[M, N] (fp32, ldc) (+)= A[M, K] (lda) * W[N, K]^T (ldw) + bias, TF32 operands on CTA pairs.  N % 256 == 0, K % 32 == 0.
+int gemm_tf32_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M,
+                 int N, int K, int accumulate, int sm_count, cudaStream_t s) {
+    if (N % 256 != 0 || K % 32 != 0 || lda % 4 != 0 || ldw % 4 != 0) return fail(PREGO_ERR_INVALID, "gemm_tf32_nt: need N %% 256 == 0, K %% 32 == 0 (got N=%d K=%d)", N, K);
+    CUtensorMap tmA, tmB;
+    RC_TRY(make_tmap_a32(&tmA, A, K, M, lda));
+    RC_TRY(make_tmap_w32(&tmB, W, K, N, ldw, 128));
+    EpiStore<256, -1> epi{C, bias, ldc, 0, 0, accumulate};
+    return launch_gemm_tc2<256, 6, 2>(tmA, tmB, M, N, K, 0, epi, sm_count, s, "gemm_tf32 (2cta)");
 }
 
 bool use_persistent_gru() {
@@ -850,6 +873,16 @@ int prego_gemm16_nt(const void* A, const void* W, const float* bias, float* C, i
     if (precision == PREGO_PREC_F16) return gemm16_test<0>(A, W, bias, C, M, N, K, tile_n, sms, s);
     if (precision == PREGO_PREC_BF16) return gemm16_test<1>(A, W, bias, C, M, N, K, tile_n, sms, s);
     return fail(PREGO_ERR_INVALID, "precision must be PREGO_PREC_F16 or PREGO_PREC_BF16");
+}
+
+int prego_gemm_tf32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
+                       int32_t accumulate, void* stream) {
+    if (A == nullptr || W == nullptr || C == nullptr) return fail(PREGO_ERR_INVALID, "NULL pointer argument");
+    if (M <= 0 || N <= 0 || K <= 0) return fail(PREGO_ERR_INVALID, "bad shape");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return gemm_tf32_nt(A, K, W, K, bias, C, N, (int)M, (int)N, (int)K, accumulate, sms, static_cast<cudaStream_t>(stream));
 }
 
 int prego_gemm_f32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,

@@ -234,7 +234,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int n_tiles = N / TILE_N;
     const int m_tiles = (M + 2 * kTileM - 1) / (2 * kTileM);
     const int total_tiles = n_tiles * m_tiles;
-    const int k_blocks = K / kTileK;
+    constexpr int kElemsK = FMT == 2 ? 32 : kTileK;  // elements per 128-byte swizzle row: 64 x 16-bit or 32 x tf32
+    const int k_blocks = K / kElemsK;
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
 
@@ -271,8 +272,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-                    ptx::tma_load_3d_2sm(&tmA, sa, &full_bar[stage], kb * kTileK, a_c1, m0, ptx::kEvictNormal);
-                    ptx::tma_load_2d_2sm(&tmB, sa + Cfg::kABytes, &full_bar[stage], kb * kTileK, n0, ptx::kEvictLast);
+                    ptx::tma_load_3d_2sm(&tmA, sa, &full_bar[stage], kb * kElemsK, a_c1, m0, ptx::kEvictNormal);
+                    ptx::tma_load_2d_2sm(&tmB, sa + Cfg::kABytes, &full_bar[stage], kb * kElemsK, n0, ptx::kEvictLast);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -297,8 +298,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
                     const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + Cfg::kABytes);
 #pragma unroll
-                    for (int k = 0; k < kTileK / 16; ++k)
-                        ptx::mma_f16_ss_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {  // 4 MMAs of 32 bytes of K each (K = 16 halves or 8 tf32)
+                        if constexpr (FMT == 2) ptx::mma_tf32_ss_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else ptx::mma_f16_ss_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     ptx::mma_commit_2sm(&empty_bar[stage], 3);  // frees this stage in both CTAs
                     if (++stage == STAGES) {
                         stage = 0;
@@ -344,9 +347,10 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf
 template <int TILE_N, int OUT_FMT>
 struct EpiStore {
     void* out;
-    const float* bias;  // [N]
+    const float* bias;  // [N] or nullptr
     int64_t ldc;
     int Tc, B;          // Tc == 0: no re-ordering
+    int accumulate = 0; // fp32 output only: out += acc (+ bias)
 
     __device__ __forceinline__ void operator()(uint32_t taddr, int row, int n0, bool valid) const {
         const int64_t orow = Tc > 0 ? static_cast<int64_t>(row % Tc) * B + row / Tc : row;
@@ -360,7 +364,7 @@ struct EpiStore {
             float f[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float4 bb = __ldg(b4 + j);
+                const float4 bb = bias != nullptr ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
                 f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
                 f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
@@ -369,7 +373,14 @@ struct EpiStore {
             if constexpr (OUT_FMT < 0) {
                 float4* d4 = reinterpret_cast<float4*>(static_cast<float*>(out) + orow * ldc + n0 + c * 32);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) d4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    if (accumulate) {
+                        const float4 p = d4[j];
+                        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+                    }
+                    d4[j] = o;
+                }
             } else {
                 using O = Op16<OUT_FMT>;
                 uint4* d4 = reinterpret_cast<uint4*>(static_cast<typename O::T*>(out) + orow * ldc + n0 + c * 32);

@@ -297,6 +297,19 @@ __device__ __forceinline__ void mma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, 
         : "memory");
 }
 
+__device__ __forceinline__ void mma_tf32_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // commit -> arrive on the mbarrier at this offset in every CTA of `mask`
 __device__ __forceinline__ void mma_commit_2sm(uint64_t* bar, uint16_t mask) {
     asm volatile(

@@ -13,7 +13,7 @@ run() {  # name, timeout, pytest -k expr
 }
 : > gpurun_out/ci_summary.txt
 run gemm_tc 300 "gemm16_tcgen05"
-run gemm_2cta 300 "gemm16_2cta"
+run gemm_2cta 300 "gemm16_2cta or gemm_tf32"
 run simt 300 "gemm_f32 or forward_fp32"
 run aggregate 300 "aggregate"
 run bf16 400 "forward_bf16 or forward_fp16 or pooled or online or chunking or carried or single_frame or big_batch or module_forward or evaluate or batched_ragged"
