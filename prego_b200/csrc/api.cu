@@ -16,6 +16,7 @@
 #include "gemm_tc.cuh"
 #include "gru_latency.cuh"
 #include "gru_step.cuh"
+#include "online_fused.cuh"
 #include "online_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "train_kernels.cuh"
@@ -153,6 +154,7 @@ struct prego_model {
     // 16-bit operands of the tcgen05 path, [0] = fp16, [1] = bf16
     void *w1_16[2] = {nullptr, nullptr}, *wih_16p[2] = {nullptr, nullptr}, *whh_16p[2] = {nullptr, nullptr},
          *wc_16p[2] = {nullptr, nullptr};
+    unsigned* online_sync = nullptr;  // barrier counters of the fused per-frame kernel (self re-arming)
     // latency-kernel exchange
     uint2* xchg = nullptr;
     int* err_flag = nullptr;
@@ -300,6 +302,31 @@ bool use_2cta() {
         v = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
     return v == 1;
+}
+
+bool use_online_fused() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PREGO_ONLINE_FUSED");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// The one-launch-per-frame kernel covers the shipped shapes (H 1024, E 2048, D 2048 | 4096) on a full-size part.
+bool online_fused_ok(const prego_model* m) {
+    return use_online_fused() && m->d.hidden_dim == 1024 && m->d.embed_dim == 2048 && (m->din == 2048 || m->din == 4096) &&
+           m->d.d_rgb % 4 == 0 && m->sm_count >= 128;
+}
+
+void* online_fused_fn(int fmt, int din) {
+    if (fmt == 0) return din == 4096 ? (void*)online_fused_kernel<0, 4, 1> : (void*)online_fused_kernel<0, 2, 1>;
+    return din == 4096 ? (void*)online_fused_kernel<1, 4, 1> : (void*)online_fused_kernel<1, 2, 1>;
+}
+
+int online_fused_prepare(void* fn, size_t smem) {
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return PREGO_OK;
 }
 
 int check_model(const prego_model* m, bool need_weights) {
@@ -533,10 +560,29 @@ int online_step_r(prego_model* m, const prego_forward_args_t* a, const Plan& p, 
     return PREGO_OK;
 }
 
+// One cooperative launch per frame (online_fused.cuh); the state is updated in place.
+int online_step_fused(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float* h, int fmt, cudaStream_t s) {
+    const prego_dims_t& d = m->d;
+    float* y = reinterpret_cast<float*>(ws + p.online);
+    float* lg = y + kOnlineMaxRows * d.embed_dim;
+    float* hrelu = lg + kOnlineMaxRows * 3 * d.hidden_dim;
+    OnlineFusedArgs fa{a->rgb, a->flow, m->w1_16[fmt], m->wih_16p[fmt], m->whh_16p[fmt], m->b1, m->ln_g, m->ln_b, m->bih_p, m->bhh_p,
+                       m->wc_f32, m->bc, y, hrelu, lg, h, a->probs, a->logits, a->labels, m->online_sync, m->err_flag,
+                       (int)a->B, d.d_rgb, d.d_flow, d.embed_dim, d.hidden_dim, d.num_classes, a->T, 0, 1e-5f};
+    void* fn = online_fused_fn(fmt, m->din);
+    const size_t smem = online_fused_smem((int)a->B, m->din, d.hidden_dim);
+    RC_TRY(online_fused_prepare(fn, online_fused_smem(kFusedMaxRows, m->din, d.hidden_dim)));
+    void* params[] = {&fa};
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(m->sm_count), dim3(kFusedThreads), params, smem, s));
+    prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
+    return PREGO_OK;
+}
+
 template <int FMT>
 int online_step(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt,
                 cudaStream_t s) {
     const int B = (int)a->B;
+    if (online_fused_ok(m)) return online_step_fused(m, a, p, ws, h_cur, FMT, s);
     if (B == 1) return online_step_r<FMT, 1>(m, a, p, ws, h_cur, h_alt, s);
     if (B == 2) return online_step_r<FMT, 2>(m, a, p, ws, h_cur, h_alt, s);
     if (B <= 4) return online_step_r<FMT, 4>(m, a, p, ws, h_cur, h_alt, s);
@@ -664,8 +710,9 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
         ALLOC(m->w1_16[f], E * din * 2); ALLOC(m->wih_16p[f], 3 * H * E * 2); ALLOC(m->whh_16p[f], 3 * H * H * 2);
         if (m->kpad) ALLOC(m->wc_16p[f], (int64_t)m->kpad * H * 2);
     }
-    ALLOC(m->xchg, 2 * 4 * H * sizeof(uint2)); ALLOC(m->err_flag, sizeof(int));
+    ALLOC(m->xchg, 2 * 4 * H * sizeof(uint2)); ALLOC(m->err_flag, sizeof(int)); ALLOC(m->online_sync, 4 * sizeof(unsigned));
 #undef ALLOC
+    CUDA_TRY(cudaMemset(m->online_sync, 0, 4 * sizeof(unsigned)));
     CUDA_TRY(cudaMemset(m->xchg, 0, 2 * 4 * H * sizeof(uint2)));
     CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
     CUDA_TRY(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
@@ -683,7 +730,7 @@ int prego_model_destroy(prego_model_t* m) {
     cudaSetDevice(m->device);
     void* ptrs[] = {m->w1_f32, m->b1, m->ln_g, m->ln_b, m->wih_f32p, m->whh_f32p, m->bih_p, m->bhh_p, m->bgi_p, m->wc_f32, m->bc,
                     m->w1_16[0], m->w1_16[1], m->wih_16p[0], m->wih_16p[1], m->whh_16p[0], m->whh_16p[1], m->wc_16p[0],
-                    m->wc_16p[1], m->xchg, m->err_flag};
+                    m->wc_16p[1], m->xchg, m->err_flag, m->online_sync};
     for (void* p : ptrs)
         if (p != nullptr) cudaFree(p);
     for (cudaEvent_t e : m->prof_ev)
@@ -791,7 +838,7 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
         else if (a->precision == PREGO_PREC_BF16) RC_TRY(chunk_16<1>(m, a, p, ws, h_cur, h_alt, t0, tc, s, ci, overlap, t_next, tc_next));
         else RC_TRY(chunk_f32(m, a, p, ws, h_cur, h_alt, t0, tc, s));
     }
-    if (a->h_state != nullptr)
+    if (a->h_state != nullptr && h_cur != a->h_state)
         CUDA_TRY(cudaMemcpyAsync(a->h_state, h_cur, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, s));
     return PREGO_OK;
 }
