@@ -104,6 +104,9 @@ int prego_online_open(prego_model_t* model, int32_t num_streams, int32_t precisi
                       float* logits, int32_t* labels, prego_online_t** out);
 int prego_online_step(prego_online_t* session, const float* rgb, const float* flow, void* stream);
 int prego_online_close(prego_online_t* session);
+/* Diagnostics: SM-clock stamps of the phase boundaries of the last frame, out[ctas][16] (host memory), for sessions
+ * opened with the environment variable PREGO_ONLINE_TRACE=1; *num_ctas = rows written (<= max_ctas). */
+int prego_online_trace(prego_online_t* session, int64_t* out, int32_t max_ctas, int32_t* num_ctas);
 
 /* Device-side watchdog: the persistent recurrence kernels bound every inter-CTA spin; if a peer never shows up
  * they set a flag instead of hanging the GPU.  Reads (and clears) it; synchronises the device.  0 = healthy. */

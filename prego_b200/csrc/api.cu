@@ -151,10 +151,11 @@ struct prego_model {
     float *wih_f32p = nullptr, *whh_f32p = nullptr, *bih_p = nullptr, *bhh_p = nullptr;
     float* bgi_p = nullptr;  // b_ih' + (r, z parts of b_hh'): bias of the input-gate GEMM on the batched 16-bit path
     float *wc_f32 = nullptr, *bc = nullptr;
+    float* wct_f32 = nullptr;         // classifier transposed [H, K] (per-frame kernel)
+    float* online_scratch = nullptr;  // y | LayerNorm partials | logit partials | counters of the per-frame kernel
     // 16-bit operands of the tcgen05 path, [0] = fp16, [1] = bf16
     void *w1_16[2] = {nullptr, nullptr}, *wih_16p[2] = {nullptr, nullptr}, *whh_16p[2] = {nullptr, nullptr},
          *wc_16p[2] = {nullptr, nullptr};
-    unsigned* online_sync = nullptr;  // barrier counters of the fused per-frame kernel (self re-arming)
     // latency-kernel exchange
     uint2* xchg = nullptr;
     int* err_flag = nullptr;
@@ -316,7 +317,7 @@ bool use_online_fused() {
 // The one-launch-per-frame kernel covers the shipped shapes (H 1024, E 2048, D 2048 | 4096) on a full-size part.
 bool online_fused_ok(const prego_model* m) {
     return use_online_fused() && m->d.hidden_dim == 1024 && m->d.embed_dim == 2048 && (m->din == 2048 || m->din == 4096) &&
-           m->d.d_rgb % 4 == 0 && m->sm_count >= 128;
+           m->d.d_rgb % 64 == 0 && m->sm_count >= 128 && m->sm_count <= kFusedPartStride;
 }
 
 void* online_fused_fn(int fmt, int din) {
@@ -560,15 +561,25 @@ int online_step_r(prego_model* m, const prego_forward_args_t* a, const Plan& p, 
     return PREGO_OK;
 }
 
+// Carves one online context's scratch (online_fused_scratch_floats) into the kernel's pointers.
+void online_fused_carve(float* scratch, int E, int K, OnlineFusedArgs* fa) {
+    fa->y = scratch;
+    fa->stats = reinterpret_cast<float2*>(scratch + (size_t)kFusedMaxRows * E);
+    fa->gpart = scratch + (size_t)kFusedMaxRows * (E + 2 * kFusedPartStride);
+    fa->sync = reinterpret_cast<unsigned*>(fa->gpart + (size_t)kFusedMaxRows * K * kFusedPartStride);
+}
+
 // One cooperative launch per frame (online_fused.cuh); the state is updated in place.
-int online_step_fused(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float* h, int fmt, cudaStream_t s) {
+int online_step_fused(prego_model* m, const prego_forward_args_t* a, float* h, int fmt, cudaStream_t s) {
     const prego_dims_t& d = m->d;
-    float* y = reinterpret_cast<float*>(ws + p.online);
-    float* lg = y + kOnlineMaxRows * d.embed_dim;
-    float* hrelu = lg + kOnlineMaxRows * 3 * d.hidden_dim;
-    OnlineFusedArgs fa{a->rgb, a->flow, m->w1_16[fmt], m->wih_16p[fmt], m->whh_16p[fmt], m->b1, m->ln_g, m->ln_b, m->bih_p, m->bhh_p,
-                       m->wc_f32, m->bc, y, hrelu, lg, h, a->probs, a->logits, a->labels, m->online_sync, m->err_flag,
-                       (int)a->B, d.d_rgb, d.d_flow, d.embed_dim, d.hidden_dim, d.num_classes, a->T, 0, 1e-5f};
+    OnlineFusedArgs fa{};
+    fa.rgb = a->rgb; fa.flow = a->flow;
+    fa.w1 = m->w1_16[fmt]; fa.wih = m->wih_16p[fmt]; fa.whh = m->whh_16p[fmt];
+    fa.b1 = m->b1; fa.ln_g = m->ln_g; fa.ln_b = m->ln_b; fa.bih = m->bih_p; fa.bhh = m->bhh_p; fa.wct = m->wct_f32; fa.bc = m->bc;
+    online_fused_carve(m->online_scratch, d.embed_dim, d.num_classes, &fa);
+    fa.h = h; fa.probs = a->probs; fa.logits = a->logits; fa.labels = a->labels; fa.err_flag = m->err_flag; fa.trace = nullptr;
+    fa.rows = (int)a->B; fa.Dr = d.d_rgb; fa.Df = d.d_flow; fa.E = d.embed_dim; fa.H = d.hidden_dim; fa.K = d.num_classes;
+    fa.T = a->T; fa.t0 = 0; fa.eps = 1e-5f;
     void* fn = online_fused_fn(fmt, m->din);
     const size_t smem = online_fused_smem((int)a->B, m->din, d.hidden_dim);
     RC_TRY(online_fused_prepare(fn, online_fused_smem(kFusedMaxRows, m->din, d.hidden_dim)));
@@ -582,7 +593,7 @@ template <int FMT>
 int online_step(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt,
                 cudaStream_t s) {
     const int B = (int)a->B;
-    if (online_fused_ok(m)) return online_step_fused(m, a, p, ws, h_cur, FMT, s);
+    if (online_fused_ok(m)) return online_step_fused(m, a, h_cur, FMT, s);
     if (B == 1) return online_step_r<FMT, 1>(m, a, p, ws, h_cur, h_alt, s);
     if (B == 2) return online_step_r<FMT, 2>(m, a, p, ws, h_cur, h_alt, s);
     if (B <= 4) return online_step_r<FMT, 4>(m, a, p, ws, h_cur, h_alt, s);
@@ -710,9 +721,10 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
         ALLOC(m->w1_16[f], E * din * 2); ALLOC(m->wih_16p[f], 3 * H * E * 2); ALLOC(m->whh_16p[f], 3 * H * H * 2);
         if (m->kpad) ALLOC(m->wc_16p[f], (int64_t)m->kpad * H * 2);
     }
-    ALLOC(m->xchg, 2 * 4 * H * sizeof(uint2)); ALLOC(m->err_flag, sizeof(int)); ALLOC(m->online_sync, 4 * sizeof(unsigned));
+    ALLOC(m->xchg, 2 * 4 * H * sizeof(uint2)); ALLOC(m->err_flag, sizeof(int)); ALLOC(m->wct_f32, K * H * 4);
+    ALLOC(m->online_scratch, online_fused_scratch_floats((int)E, (int)K) * 4);
 #undef ALLOC
-    CUDA_TRY(cudaMemset(m->online_sync, 0, 4 * sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(m->online_scratch, 0, online_fused_scratch_floats((int)E, (int)K) * 4));
     CUDA_TRY(cudaMemset(m->xchg, 0, 2 * 4 * H * sizeof(uint2)));
     CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
     CUDA_TRY(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
@@ -730,7 +742,7 @@ int prego_model_destroy(prego_model_t* m) {
     cudaSetDevice(m->device);
     void* ptrs[] = {m->w1_f32, m->b1, m->ln_g, m->ln_b, m->wih_f32p, m->whh_f32p, m->bih_p, m->bhh_p, m->bgi_p, m->wc_f32, m->bc,
                     m->w1_16[0], m->w1_16[1], m->wih_16p[0], m->wih_16p[1], m->whh_16p[0], m->whh_16p[1], m->wc_16p[0],
-                    m->wc_16p[1], m->xchg, m->err_flag, m->online_sync};
+                    m->wc_16p[1], m->xchg, m->err_flag, m->wct_f32, m->online_scratch};
     for (void* p : ptrs)
         if (p != nullptr) cudaFree(p);
     for (cudaEvent_t e : m->prof_ev)
@@ -766,6 +778,7 @@ int prego_model_load_weights(prego_model_t* m, const prego_weights_t* w, void* s
     pack_rows_f32<<<g(3 * H), T, 0, s>>>(w->gru_bias_ih_l0, m->bih_p, 3 * H, 1, H, 1);
     pack_rows_f32<<<g(3 * H), T, 0, s>>>(w->gru_bias_hh_l0, m->bhh_p, 3 * H, 1, H, 1);
     presum_gate_bias<<<g(3 * H), T, 0, s>>>(m->bih_p, m->bhh_p, m->bgi_p, 3 * H);
+    transpose_f32<<<g((int64_t)K * H), T, 0, s>>>(w->f_classification_0_weight, m->wct_f32, K, H);
     LAUNCH_CHECK("fp32 weight packing");
     RC_TRY(pack16<0>(m, w, s));
     RC_TRY(pack16<1>(m, w, s));

@@ -6,13 +6,15 @@
 // the legacy tensor-core path (mma.sync m16n8k16, fp32 accumulate): 16 weight rows x 8 streams per instruction, so
 // up to 8 streams cost the same as one and no warp-shuffle reductions are needed.
 //
-//   phase A : y[n]  = W1[n, :] . [rgb | flow] + b1[n]      (rows n of this CTA, K split over the 16 warps)
-//             gh[u] = W_hh'[u, :] . h                       (units u of this CTA, gates r | z | n; stays in smem)
-//   -- grid barrier 1 (y complete) --
-//   phase B : e = relu(LN(y)) (every CTA, 8 KB per stream), gi[u] = W_ih'[u, :] . e, gates, h' (in place), relu(h')
-//   -- barrier 2 (arrive: all CTAs; wait: only the CTAs that own a class row) --
-//   head    : logit[k] = Wc[k, :] . relu(h') + bc[k]; the last CTA to finish does softmax + first-max argmax and
-//             re-arms the three counters for the next frame.
+//   phase A : y[n]  = W1[n, :] . [rgb | flow] + b1[n]      (rows n of this CTA, K split over the 16 warps; each warp
+//             gh[u] = W_hh'[u, :] . h                        stages only ITS K slice of x / h: no CTA-wide sync first)
+//             + per-CTA LayerNorm partials (mean, M2 of its y rows) published with the barrier arrival
+//   -- grid barrier (y and the partials complete) --
+//   phase B : mean / rstd from the 148 partials (Chan's combination: as exact as two passes), e = relu(LN(y)),
+//             gi[u] = W_ih'[u, :] . e, gates, h' (in place); the classifier is split over K like everything else:
+//             every CTA publishes Wc[:, its units] . relu(h') for all classes
+//   tail    : the last CTA to arrive sums the per-CTA logit partials in a fixed order (deterministic), softmax,
+//             first-max argmax, and re-arms the counters for the next frame.
 //
 // The K permutation inside a 64-wide chunk is free (weights and activations are permuted alike): lane (g, t) loads
 // 32 contiguous bytes of weight row g (k = 16 t .. 16 t + 15 of the chunk) and feeds MMA j with its halves
@@ -30,6 +32,7 @@ namespace prego {
 constexpr int kFusedThreads = 512;
 constexpr int kFusedWarps = kFusedThreads / 32;
 constexpr int kFusedMaxRows = 8;
+constexpr int kFusedPartStride = 160;  // >= grid size (one logit partial per CTA, padded)
 constexpr uint32_t kFusedSpinMax = 1u << 22;  // bounded spins: a lost CTA raises the error flag instead of hanging the GPU
 
 struct OnlineFusedArgs {
@@ -39,16 +42,17 @@ struct OnlineFusedArgs {
     const void* wih;  // [3H, E] 16-bit, gate-interleaved rows (packed row = (u/64)*192 + gate*64 + u%64)
     const void* whh;  // [3H, H] 16-bit, same row order
     const float *b1, *ln_g, *ln_b, *bih, *bhh;  // bih / bhh in packed row order
-    const float *wc, *bc;                        // fp32 classifier
-    float* y;      // [8, E] scratch
-    float* hrelu;  // [8, H] scratch
-    float* lg;     // [8, K] scratch
-    float* h;      // [rows, H] carried state, updated in place
+    const float *wct, *bc;                       // fp32 classifier, transposed [H, K]
+    float* y;       // [8, E] scratch
+    float2* stats;  // [8, grid] scratch: (mean, M2) of each CTA's y rows
+    float* gpart;   // [8, K, kFusedPartStride] scratch: per-CTA logit partials
+    float* h;       // [rows, H] carried state, updated in place
     float* probs;
     float* logits;
     int32_t* labels;
-    unsigned* sync;  // [3] zero before the first launch; the kernel re-arms them
+    unsigned* sync;  // [2] zero before the first launch; the kernel re-arms them
     int* err_flag;
+    long long* trace;  // optional [grid][16] SM-clock stamps of the phase boundaries (diagnostics; NULL = off)
     int rows, Dr, Df, E, H, K;
     int64_t T, t0;  // output row of stream r is r * T + t0
     float eps;
@@ -104,8 +108,7 @@ __device__ __forceinline__ W32 lds_act(const uint8_t* row_base, int k, bool vali
 }
 
 __device__ __forceinline__ void fused_arrive(unsigned* ctr) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
 }
 __device__ __forceinline__ void fused_wait(unsigned* ctr, unsigned target, int* err_flag) {
     uint32_t spins = 0;
@@ -119,6 +122,20 @@ __device__ __forceinline__ void fused_wait(unsigned* ctr, unsigned target, int* 
         }
     }
 }
+
+// slot i = SM clock, slot 8 + i = %globaltimer (ns; comparable across SMs) for i = 0 (entry) and 7 / 8 (exit paths)
+#define FUSED_STAMP(i)                                                                              \
+    do {                                                                                            \
+        if (a.trace != nullptr && threadIdx.x == 0) {                                               \
+            a.trace[blockIdx.x * 16 + (i)] = clock64();                                             \
+            if ((i) == 0 || (i) >= 7) {                                                             \
+                unsigned long long gt_;                                                             \
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                             \
+                a.trace[blockIdx.x * 16 + ((i) == 0 ? 9 : 10)] = static_cast<long long>(gt_);       \
+                if ((i) == 0) a.trace[blockIdx.x * 16 + 8] = 0;                                     \
+            }                                                                                       \
+        }                                                                                           \
+    } while (0)
 
 // Packed row of hidden unit u, gate gt (0 r, 1 z, 2 n) in W_ih' / W_hh' / bih / bhh.
 __device__ __forceinline__ int packed_row(int u, int gt) { return (u >> 6) * 192 + gt * 64 + (u & 63); }
@@ -135,7 +152,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
     uint8_t* hs = xs + R * (XS > ES ? XS : ES);          // [R][HS]
     float* part = reinterpret_cast<float*>(hs + R * HS);  // [3][16 warps][128]
     float* ghs = part + 3 * kFusedWarps * 128;           // [3 gates][8 units][8 streams]
-    float* red = ghs + 192;                              // [32]
+    float* ysm = ghs + 192;                              // [8 streams][16 rows]   (phase A) / hrl [8 streams][8 units]
+    float* lnp = ysm + 128;                              // [8 streams][2]: mean, rstd
     __shared__ int is_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -145,6 +163,29 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
     const int nu = min(upc, max(H - u0, 0)), nr = min(rpc, max(E - n0, 0));
     const bool uval = g < nu;
     const int u = u0 + g;
+    FUSED_STAMP(0);
+
+    // ---- this warp's K slice of the activations is requested FIRST (the L2 -> SM path is served in order and the
+    //      weight requests below queue ~110 KB per SM): x = [rgb | flow] of frame t0 (k in [warp * C1 * 64, +C1 * 64)),
+    //      h = carried state (slice of CH * 64); first batch of four x loads + the h loads
+    constexpr int XV = C1 * 16, HV = CH * 16;  // float4 per stream in the slice
+    const int kx0 = warp * C1 * 64, kh0 = warp * CH * 64;
+    auto x_src = [&](int i) -> const float4* {
+        const int r = i / XV, c4 = kx0 + (i % XV) * 4;
+        return reinterpret_cast<const float4*>(c4 < a.Dr ? a.rgb + (static_cast<int64_t>(r) * a.T + a.t0) * a.Dr + c4
+                                                          : a.flow + (static_cast<int64_t>(r) * a.T + a.t0) * a.Df + (c4 - a.Dr));
+    };
+    float4 hv[(kFusedMaxRows * HV + 31) / 32], xv[4];
+#pragma unroll
+    for (int q = 0; q < (kFusedMaxRows * HV + 31) / 32; ++q) {
+        const int i = q * 32 + lane;
+        if (i < R * HV) hv[q] = __ldcg(reinterpret_cast<const float4*>(a.h + static_cast<int64_t>(i / HV) * H + kh0 + (i % HV) * 4));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = q * 32 + lane;
+        if (i < R * XV) xv[q] = __ldg(x_src(i));
+    }
 
     // ---- weight requests of phase A (nothing they depend on): W_hh' rows of (u, r|z|n), first half of the W1 chunks
     W32 wh[CH][3];
@@ -164,20 +205,37 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
         w1b[c] = ldw32(a.w1, r1b + k, v1b);
     }
 
-    // ---- activations -> 16-bit smem rows: x = [rgb | flow] of frame t0, h = carried state
-    for (int i = tid; i < R * (D / 4); i += kFusedThreads) {
-        const int r = i / (D / 4), c4 = (i % (D / 4)) * 4;
-        const float* src = c4 < a.Dr ? a.rgb + (static_cast<int64_t>(r) * a.T + a.t0) * a.Dr + c4
-                                     : a.flow + (static_cast<int64_t>(r) * a.T + a.t0) * a.Df + (c4 - a.Dr);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src));
-        *reinterpret_cast<uint2*>(xs + r * XS + c4 * 2) = make_uint2(Op::pack2(v.x, v.y), Op::pack2(v.z, v.w));
+    // ---- activations -> 16-bit smem rows (warp-private slices: __syncwarp only)
+    {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = q * 32 + lane;
+            if (i < R * XV)
+                *reinterpret_cast<uint2*>(xs + (i / XV) * XS + (kx0 + (i % XV) * 4) * 2) = make_uint2(Op::pack2(xv[q].x, xv[q].y), Op::pack2(xv[q].z, xv[q].w));
+        }
+        for (int i0 = 128; i0 < R * XV; i0 += 128) {  // more than two streams: further batches of four loads per lane
+            float4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q * 32 + lane;
+                if (i < R * XV) v[q] = __ldg(x_src(i));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q * 32 + lane;
+                if (i < R * XV)
+                    *reinterpret_cast<uint2*>(xs + (i / XV) * XS + (kx0 + (i % XV) * 4) * 2) = make_uint2(Op::pack2(v[q].x, v[q].y), Op::pack2(v[q].z, v[q].w));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < (kFusedMaxRows * HV + 31) / 32; ++q) {
+            const int i = q * 32 + lane;
+            if (i < R * HV)
+                *reinterpret_cast<uint2*>(hs + (i / HV) * HS + (kh0 + (i % HV) * 4) * 2) = make_uint2(Op::pack2(hv[q].x, hv[q].y), Op::pack2(hv[q].z, hv[q].w));
+        }
+        __syncwarp();
     }
-    for (int i = tid; i < R * (H / 4); i += kFusedThreads) {
-        const int r = i / (H / 4), c4 = (i % (H / 4)) * 4;
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(a.h + static_cast<int64_t>(r) * H + c4));
-        *reinterpret_cast<uint2*>(hs + r * HS + c4 * 2) = make_uint2(Op::pack2(v.x, v.y), Op::pack2(v.z, v.w));
-    }
-    __syncthreads();
+    FUSED_STAMP(1);
 
     // ---- phase A math
     const bool sval = g < R;  // this lane's B-fragment column (stream g) exists
@@ -189,7 +247,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
         mma_chunk<FMT>(crz, wh[c][0], wh[c][1], x);
         mma_chunk<FMT>(cn, wh[c][2], zero, x);
     }
-    // second half of the W1 chunks goes out while the first half is consumed
+    // second half of the W1 chunks goes out while the first half is consumed (registers are the landing zone; the
+    // L2 -> SM path is the limit anyway: ~47 GB/s per SM with all SMs streaming, measured)
     W32 w1c[C1 - C1A], w1d[C1 - C1A];
 #pragma unroll
     for (int c = C1A; c < C1; ++c) {
@@ -227,48 +286,99 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
         const int el = i >> 2, reg = i & 3;                       // accumulator register `reg` of lane `el`
         const int row = (el >> 2) + 8 * (reg >> 1), col = (el & 3) * 2 + (reg & 1);  // weight row, stream
         if (p == 0) {
-            if (row < nr && col < R) a.y[col * E + n0 + row] = s + __ldg(a.b1 + n0 + row);
+            float yv = 0.f;
+            if (row < nr && col < R) {
+                yv = s + __ldg(a.b1 + n0 + row);
+                a.y[col * E + n0 + row] = yv;
+            }
+            ysm[col * 16 + row] = yv;
         } else {
             const int gt = p == 1 ? (row >> 3) : 2;  // pair 1 = (r | z), pair 2 = (n | -)
             if (p == 1 || row < 8) ghs[(gt * 8 + (row & 7)) * 8 + col] = s;
         }
     }
     __syncthreads();
+    if (tid < R) {  // LayerNorm partials of this CTA's rows: (mean, sum of squared deviations)
+        float m = 0.f, q = 0.f;
+        if (nr > 0) {
+            for (int r = 0; r < nr; ++r) m += ysm[tid * 16 + r];
+            m /= static_cast<float>(nr);
+            for (int r = 0; r < nr; ++r) {
+                const float d = ysm[tid * 16 + r] - m;
+                q += d * d;
+            }
+        }
+        a.stats[tid * G + cta] = make_float2(m, q);
+    }
+    __syncthreads();
+    FUSED_STAMP(2);
     if (tid == 0) {
         fused_arrive(a.sync + 0);
         fused_wait(a.sync + 0, static_cast<unsigned>(G), a.err_flag);
     }
     __syncthreads();
+    FUSED_STAMP(3);
+
+    // gate biases and the fp32 master state of this thread's (unit, stream) item: requested now, used after phase B
+    float gb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, hp = 0.f;
+    if (tid < 64 && (tid >> 3) < nu && (tid & 7) < R) {
+        const int uu = u0 + (tid >> 3), pr = packed_row(uu, 0);
+#pragma unroll
+        for (int gt = 0; gt < 3; ++gt) {
+            gb[gt] = __ldg(a.bih + pr + gt * 64);
+            gb[3 + gt] = __ldg(a.bhh + pr + gt * 64);
+        }
+        hp = __ldcg(a.h + static_cast<int64_t>(tid & 7) * H + uu);  // only this CTA writes it (after this point)
+    }
 
     // ---- phase B: e = relu(LN(y)) for every stream (each CTA recomputes it), into the 16-bit rows es (alias of xs)
     uint8_t* es = xs;
-    for (int r = 0; r < R; ++r) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(a.y + r * E) + tid);
-        float s = (v.x + v.y) + (v.z + v.w);
+    if (warp < R) {  // warp r combines the per-CTA partials of stream r (Chan et al.: exact merge of (n, mean, M2))
+        float2 st[(kFusedPartStride + 31) / 32];
+        float wsum = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) red[warp] = s;
-        __syncthreads();
-        float tot = 0.f;
+        for (int q = 0; q < (kFusedPartStride + 31) / 32; ++q) {
+            const int c = q * 32 + lane;
+            st[q] = c < G ? __ldcg(a.stats + warp * G + c) : make_float2(0.f, 0.f);
+            const int nc = min(rpc, max(E - c * rpc, 0));
+            wsum += c < G ? st[q].x * static_cast<float>(nc) : 0.f;
+        }
 #pragma unroll
-        for (int w = 0; w < kFusedWarps; ++w) tot += red[w];
-        const float mu = tot / static_cast<float>(E);
-        const float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
-        float q = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        const float mu = wsum / static_cast<float>(E);
+        float m2 = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        if (lane == 0) red[16 + warp] = q;
-        __syncthreads();
-        float var = 0.f;
+        for (int q = 0; q < (kFusedPartStride + 31) / 32; ++q) {
+            const int c = q * 32 + lane;
+            const int nc = min(rpc, max(E - c * rpc, 0));
+            const float d = st[q].x - mu;
+            m2 += c < G ? st[q].y + static_cast<float>(nc) * d * d : 0.f;
+        }
 #pragma unroll
-        for (int w = 0; w < kFusedWarps; ++w) var += red[16 + w];
-        const float rstd = 1.0f / sqrtf(var / static_cast<float>(E) + a.eps);
+        for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+        if (lane == 0) {
+            lnp[warp * 2] = mu;
+            lnp[warp * 2 + 1] = 1.0f / sqrtf(m2 / static_cast<float>(E) + a.eps);
+        }
+    }
+    {
         const float4 gm = __ldg(reinterpret_cast<const float4*>(a.ln_g) + tid), bt = __ldg(reinterpret_cast<const float4*>(a.ln_b) + tid);
-        *reinterpret_cast<uint2*>(es + r * ES + tid * 8) =
-            make_uint2(Op::pack2(fmaxf(dx * rstd * gm.x + bt.x, 0.f), fmaxf(dy * rstd * gm.y + bt.y, 0.f)),
-                       Op::pack2(fmaxf(dz * rstd * gm.z + bt.z, 0.f), fmaxf(dw * rstd * gm.w + bt.w, 0.f)));
+        float4 v[kFusedMaxRows];
+#pragma unroll
+        for (int r = 0; r < kFusedMaxRows; ++r)
+            if (r < R) v[r] = __ldcg(reinterpret_cast<const float4*>(a.y + r * E) + tid);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kFusedMaxRows; ++r)
+            if (r < R) {
+                const float mu = lnp[r * 2], rstd = lnp[r * 2 + 1];
+                *reinterpret_cast<uint2*>(es + r * ES + tid * 8) =
+                    make_uint2(Op::pack2(fmaxf((v[r].x - mu) * rstd * gm.x + bt.x, 0.f), fmaxf((v[r].y - mu) * rstd * gm.y + bt.y, 0.f)),
+                               Op::pack2(fmaxf((v[r].z - mu) * rstd * gm.z + bt.z, 0.f), fmaxf((v[r].w - mu) * rstd * gm.w + bt.w, 0.f)));
+            }
     }
     __syncthreads();
+    FUSED_STAMP(4);
     float drz[4] = {0.f, 0.f, 0.f, 0.f}, dn[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < C2; ++c) {
@@ -276,10 +386,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
         mma_chunk<FMT>(drz, wi[c][0], wi[c][1], x);
         mma_chunk<FMT>(dn, wi[c][2], zero, x);
     }
-    // classifier row of this CTA (fp32, H floats) is requested before the second barrier
-    const int kc = cta;  // class rows kc, kc + G, ...
-    float2 wc0 = make_float2(0.f, 0.f);
-    if (kc < a.K && tid * 2 < H) wc0 = __ldg(reinterpret_cast<const float2*>(a.wc + static_cast<int64_t>(kc) * H) + tid);
+    // classifier columns of this CTA's units (fp32 Wc^T rows u0 .. u0 + nu - 1), first (class, stream) item of this thread
+    const int KR = a.K * R;
+    float wcv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wcv[j] = (tid < KR && j < nu) ? __ldg(a.wct + static_cast<int64_t>(u0 + j) * a.K + tid % a.K) : 0.f;
     *reinterpret_cast<float4*>(part + (0 * kFusedWarps + warp) * 128 + lane * 4) = make_float4(drz[0], drz[1], drz[2], drz[3]);
     *reinterpret_cast<float4*>(part + (1 * kFusedWarps + warp) * 128 + lane * 4) = make_float4(dn[0], dn[1], dn[2], dn[3]);
     __syncthreads();
@@ -295,80 +406,85 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
         if (p == 0 || row < 8) gis[(gt * 8 + (row & 7)) * 8 + col] = s;
     }
     __syncthreads();
+    float* hrl = ysm;  // [8 streams][8 units] relu(h') of this CTA's units
     if (tid < 64) {
         const int j = tid >> 3, n = tid & 7;  // unit j of this CTA, stream n
+        float hr = 0.f;
         if (j < nu && n < R) {
-            const int uu = u0 + j, pr = packed_row(uu, 0);
+            const int uu = u0 + j;
             // ATen's evaluation order: r, z from (gi + b_ih) + (gh + b_hh); n = tanh(gi_n + r * (gh_n + b_hn))
-            const float rr = sigmoid_f((gis[(0 * 8 + j) * 8 + n] + __ldg(a.bih + pr)) + (ghs[(0 * 8 + j) * 8 + n] + __ldg(a.bhh + pr)));
-            const float zz = sigmoid_f((gis[(1 * 8 + j) * 8 + n] + __ldg(a.bih + pr + 64)) + (ghs[(1 * 8 + j) * 8 + n] + __ldg(a.bhh + pr + 64)));
-            const float nn = tanhf((gis[(2 * 8 + j) * 8 + n] + __ldg(a.bih + pr + 128)) + rr * (ghs[(2 * 8 + j) * 8 + n] + __ldg(a.bhh + pr + 128)));
-            const float hp = __ldcg(a.h + static_cast<int64_t>(n) * H + uu);  // fp32 master state (only this CTA writes it)
+            const float rr = sigmoid_f((gis[(0 * 8 + j) * 8 + n] + gb[0]) + (ghs[(0 * 8 + j) * 8 + n] + gb[3]));
+            const float zz = sigmoid_f((gis[(1 * 8 + j) * 8 + n] + gb[1]) + (ghs[(1 * 8 + j) * 8 + n] + gb[4]));
+            const float nn = tanhf((gis[(2 * 8 + j) * 8 + n] + gb[2]) + rr * (ghs[(2 * 8 + j) * 8 + n] + gb[5]));
             const float hn = (hp - nn) * zz + nn;
             a.h[static_cast<int64_t>(n) * H + uu] = hn;
-            a.hrelu[n * H + uu] = fmaxf(hn, 0.f);
+            hr = fmaxf(hn, 0.f);
         }
+        hrl[n * 8 + j] = hr;
     }
     __syncthreads();
-    if (tid == 0) fused_arrive(a.sync + 1);
-    const int n_head = a.K < G ? a.K : G;
-    if (cta >= n_head) return;
-    if (tid == 0) fused_wait(a.sync + 1, static_cast<unsigned>(G), a.err_flag);
-    __syncthreads();
-
-    // ---- head: logit[k] for the class rows of this CTA
-    for (int k = kc; k < a.K; k += G) {
-        for (int r = 0; r < R; ++r) {
-            float s = 0.f;
-            for (int i = tid; i * 2 < H; i += kFusedThreads) {
-                const float2 w = (k == kc && i == tid) ? wc0 : __ldg(reinterpret_cast<const float2*>(a.wc + static_cast<int64_t>(k) * H) + i);
-                const float2 hv = __ldcg(reinterpret_cast<const float2*>(a.hrelu + r * H) + i);
-                s = fmaf(w.x, hv.x, s);
-                s = fmaf(w.y, hv.y, s);
-            }
+    FUSED_STAMP(5);
+    // ---- classifier, split over the hidden units like the other layers: this CTA's share of every logit
+    for (int i = tid; i < KR; i += kFusedThreads) {
+        const int k = i % a.K, n = i / a.K;
+        float s = 0.f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) red[warp] = s;
-            __syncthreads();
-            if (tid == 0) {
-                float tot = 0.f;
-#pragma unroll
-                for (int w = 0; w < kFusedWarps; ++w) tot += red[w];
-                a.lg[r * a.K + k] = tot + __ldg(a.bc + k);
-            }
-            __syncthreads();
+        for (int j = 0; j < 8; ++j) {
+            const float w = i == tid ? wcv[j] : (j < nu ? __ldg(a.wct + static_cast<int64_t>(u0 + j) * a.K + k) : 0.f);
+            s = fmaf(w, hrl[n * 8 + j], s);
         }
+        a.gpart[(static_cast<int64_t>(n) * a.K + k) * kFusedPartStride + cta] = s;
     }
+    const float bc0 = (tid >> 4) < KR ? __ldg(a.bc + (tid >> 4) % a.K) : 0.f;
+    __syncthreads();
+    FUSED_STAMP(6);
     if (tid == 0) {
         __threadfence();
-        const unsigned prev = atomicAdd(a.sync + 2, 1u);
-        is_last = prev + 1u == static_cast<unsigned>(n_head);
+        const unsigned prev = atomicAdd(a.sync + 1, 1u);
+        is_last = prev + 1u == static_cast<unsigned>(G);
     }
     __syncthreads();
+    FUSED_STAMP(7);
     if (!is_last) return;
-    __threadfence();
-    // ---- last CTA: softmax + first-max argmax per stream (one warp each), counters re-armed for the next frame
+    // ---- last CTA: logits = sum of the per-CTA partials in CTA order (16 lanes per logit, fixed shuffle tree),
+    //      softmax + first-max argmax per stream (one warp each); counters re-armed for the next frame
     if (tid == 0) {
         a.sync[0] = 0u;
         a.sync[1] = 0u;
-        a.sync[2] = 0u;
     }
+    float* lgs = reinterpret_cast<float*>(xs);  // [R][K] logits; the activation rows (>= 4 KB per stream) are free now
+    {
+        const int sub = tid & 15;
+        for (int o = tid >> 4; o < KR; o += kFusedThreads / 16) {
+            const float* gp = a.gpart + static_cast<int64_t>(o) * kFusedPartStride;
+            float v[kFusedPartStride / 16];
+#pragma unroll
+            for (int q = 0; q < kFusedPartStride / 16; ++q) v[q] = (q * 16 + sub) < G ? __ldcg(gp + q * 16 + sub) : 0.f;
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < kFusedPartStride / 16; ++q) s += v[q];
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (sub == 0) lgs[o] = s + (o == (tid >> 4) ? bc0 : __ldg(a.bc + o % a.K));
+        }
+    }
+    __syncthreads();
     if (warp < R) {
         const int r = warp, K = a.K;
-        const float* lg = a.lg + r * K;
+        const float* lg = lgs + r * K;
         const int64_t go = static_cast<int64_t>(r) * a.T + a.t0;
         float mx = -INFINITY;
-        for (int j = lane; j < K; j += 32) mx = fmaxf(mx, __ldcg(lg + j));
+        for (int j = lane; j < K; j += 32) mx = fmaxf(mx, lg[j]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         float sum = 0.f;
-        for (int j = lane; j < K; j += 32) sum += expf(__ldcg(lg + j) - mx);
+        for (int j = lane; j < K; j += 32) sum += expf(lg[j] - mx);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         float best = -1.f;
         int arg = 0x7fffffff;
         for (int j = lane; j < K; j += 32) {
-            const float l = __ldcg(lg + j);
+            const float l = lg[j];
             const float p = expf(l - mx) / sum;
             if (a.probs != nullptr) a.probs[go * K + j] = p;
             if (a.logits != nullptr) a.logits[go * K + j] = l;
@@ -388,11 +504,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
         }
         if (lane == 0 && a.labels != nullptr) a.labels[go] = arg;
     }
+    FUSED_STAMP(8);
 }
 
 inline size_t online_fused_smem(int rows, int D, int H) {
     const int XS = D * 2 + 16, ES = 2048 * 2 + 16, HS = H * 2 + 16;
-    return static_cast<size_t>(rows) * ((XS > ES ? XS : ES) + HS) + (3 * kFusedWarps * 128 + 192 + 32) * sizeof(float);
+    return static_cast<size_t>(rows) * ((XS > ES ? XS : ES) + HS) + (3 * kFusedWarps * 128 + 192 + 128 + 16) * sizeof(float);
+}
+
+// fp32 scratch of one online context: y [8, E] | stats [8, stride] float2 | gpart [8, K, stride] | 4 counters
+inline size_t online_fused_scratch_floats(int E, int K) {
+    return static_cast<size_t>(kFusedMaxRows) * (E + 2 * kFusedPartStride + static_cast<size_t>(K) * kFusedPartStride) + 4;
 }
 
 }  // namespace prego

@@ -360,6 +360,16 @@ __global__ void h32_retile(float* __restrict__ plain, float* __restrict__ tiled,
     }
 }
 
+// dst[c, r] = src[r, c]  (classifier weight [K, H] -> [H, K] for the split-K head of the per-frame kernel)
+__global__ void transpose_f32(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+    const int64_t total = static_cast<int64_t>(rows) * cols;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+        dst[static_cast<int64_t>(c) * rows + r] = src[i];
+    }
+}
+
 // bgi[p] = bih[p] + (gate(p) is r or z ? bhh[p] : 0), packed order: columns [r64 | z64 | n64] per 192.
 __global__ void presum_gate_bias(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ bgi, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

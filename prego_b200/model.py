@@ -190,10 +190,10 @@ class MROAD(nn.Module):
             _lib.check(lib.prego_forward(self._handle, C.byref(args), stream), "prego_forward")
         return {"probs": probs, "logits": logits, "labels": labels}
 
-    def online_session(self, num_streams: int, device=None, precision=None, want_probs=False):
+    def online_session(self, num_streams: int, device=None, precision=None, want_probs=False, host_labels=False):
         """Strict per-frame online inference: ``session.step(rgb_frame, flow_frame) -> labels`` with the GRU state
         carried inside the session and all per-call host work hoisted out (BASELINE configs[1])."""
-        return OnlineSession(self, num_streams, device, precision, want_probs)
+        return OnlineSession(self, num_streams, device, precision, want_probs, host_labels)
 
     def device_error(self) -> int:
         """Watchdog flag of the persistent recurrence kernels (0 = healthy); synchronises the device."""
@@ -233,7 +233,7 @@ class OnlineSession:
     CUDA graph per frame through ``prego_online_*``).  Buffers are allocated once; ``step`` patches two pointers.
     The packed weights are captured when the session is opened: open a new session after changing parameters."""
 
-    def __init__(self, model: MROAD, num_streams: int, device=None, precision=None, want_probs=False):
+    def __init__(self, model: MROAD, num_streams: int, device=None, precision=None, want_probs=False, host_labels=False):
         lib = _lib.load()
         if device is None:
             device = next(model.parameters()).device
@@ -249,7 +249,10 @@ class OnlineSession:
             model._ensure_handle(device)
             model._sync_weights(lib, device)
             self.h = torch.zeros(self.B, model.hidden_dim, dtype=torch.float32, device=device)
-            self.labels = torch.empty(self.B, 1, dtype=torch.int32, device=device)
+            # host_labels: the kernel stores the labels straight into pinned (device-mapped) host memory, so the caller
+            # reads them after a stream sync without a D2H copy on the per-frame critical path
+            self.labels = (torch.zeros(self.B, 1, dtype=torch.int32).pin_memory() if host_labels
+                           else torch.empty(self.B, 1, dtype=torch.int32, device=device))
             self.probs = torch.empty(self.B, 1, model.out_dim, dtype=torch.float32, device=device) if want_probs else None
             torch.cuda.current_stream(device).synchronize()  # weight packing done before the graph is built
             _lib.check(lib.prego_online_open(model._handle, self.B, _lib.PRECISIONS[prec_name], self.h.data_ptr(),
@@ -270,9 +273,18 @@ class OnlineSession:
     def reset(self):
         self.h.zero_()
 
+    def trace(self):
+        """Per-CTA SM-clock stamps [ctas, 16] of the last frame's phase boundaries (PREGO_ONLINE_TRACE=1 sessions)."""
+        import numpy as np
+        out = np.zeros((256, 16), dtype=np.int64)
+        n = C.c_int32(0)
+        _lib.check(self._lib.prego_online_trace(self._session, out.ctypes.data, 256, C.byref(n)), "prego_online_trace")
+        return out[:n.value]
+
     def step(self, rgb_frame, flow_frame):
         """rgb_frame / flow_frame: contiguous fp32 CUDA tensors with B * D elements ([B, D] or [B, 1, D]).
-        Returns the int32 label tensor [B, 1] (device; overwritten by the next step)."""
+        Returns the int32 label tensor [B, 1] (device, or pinned host memory for ``host_labels`` sessions: valid
+        after the stream is synchronized; overwritten by the next step)."""
         rc = self._lib.prego_online_step(self._session, rgb_frame.data_ptr() if rgb_frame is not None else None,
                                          flow_frame.data_ptr() if flow_frame is not None else None,
                                          torch.cuda.current_stream(self.device).cuda_stream)

@@ -456,3 +456,30 @@ def test_full_size_batch_invariance(dev):
     assert (full["probs"][perm] - sub["probs"]).abs().max().item() <= 1e-6
     assert torch.equal(full["labels"][perm], sub["labels"])
     assert model.device_error() == 0  # no dependency spin of the persistent recurrence timed out
+
+
+@pytest.mark.parametrize("streams", [1, 3, 8])
+def test_online_session_multi_stream_host_labels(dev, golden_meta, streams):
+    """Fused per-frame kernel with R = 1 / 3 / 8 streams, labels stored into pinned host memory: every stream must
+    reproduce the reference's whole-sequence labels on clear margins and its final GRU state."""
+    name = "asm_b40_t24"
+    gold = load_model_case(name)
+    cfg, rgb, flow = case_inputs(golden_meta, name, dev)
+    rgb, flow = rgb[:streams].contiguous(), flow[:streams].contiguous()
+    model = seeded_weights_checked(golden_meta, name, dev)
+    sess = model.online_session(streams, dev, "fp16", want_probs=True, host_labels=True)
+    n = rgb.shape[1]
+    got = np.zeros((streams, n), dtype=np.int64)
+    for t in range(n):
+        lab = sess.step(rgb[:, t].contiguous(), flow[:, t].contiguous())
+        torch.cuda.synchronize()
+        got[:, t] = lab.numpy()[:, 0]
+        assert (sess.probs.sum(-1) - 1).abs().max().item() < 1e-5
+    ref_logits = gold["logits"][:streams, :n]
+    ref = ref_logits.argmax(-1)
+    margin = miniroad_np.top2_margin(ref_logits)
+    clear = margin > 4e-3
+    assert clear.mean() > 0.5
+    assert np.array_equal(got[clear], ref[clear])
+    assert np.abs(sess.h.cpu().numpy() - gold["h_last"][:streams]).max() < 5e-3
+    assert model.device_error() == 0
