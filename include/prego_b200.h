@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define PREGO_ABI_VERSION 1
+#define PREGO_ABI_VERSION 2
 
 #define PREGO_OK 0
 #define PREGO_ERR_INVALID 1     /* bad argument / unsupported shape */
@@ -33,6 +33,15 @@ extern "C" {
 #define PREGO_PREC_TF32 3       /* training only: fp32 storage, tcgen05 kind::tf32 operands, fp32 accumulate */
 #define PREGO_PREC_F16 2        /* tcgen05 kind::f16, fp16 operands (10-bit mantissa = TF32 accuracy at the bf16 rate),
                                    fp32 accumulate; inputs saturate at +-65504 (default throughput path) */
+
+/* Storage format of the rgb / flow feature tensors handed to prego_forward (feature ingest).
+ * The reference loader produces fp32 (datasets/dataset.py:129-131).  PREGO_FEAT_16 declares that the caller already
+ * keeps the features in the 16-bit operand format of `precision` (fp16 for PREGO_PREC_F16, bf16 for PREGO_PREC_BF16):
+ * results are bit-identical to passing the same values as fp32 (the fp32 path rounds to that format first), the
+ * staging pass disappears (the projection GEMM's TMA reads the caller's tensors in place) and host->device traffic
+ * halves. */
+#define PREGO_FEAT_F32 0
+#define PREGO_FEAT_16 1
 
 typedef struct prego_model prego_model_t;
 
@@ -62,8 +71,8 @@ typedef struct prego_weights {
 } prego_weights_t;
 
 typedef struct prego_forward_args {
-    const float* rgb;        /* [B, T, d_rgb]  fp32 contiguous (ignored when d_rgb == 0)  */
-    const float* flow;       /* [B, T, d_flow] fp32 contiguous (ignored when d_flow == 0) */
+    const void* rgb;         /* [B, T, d_rgb]  contiguous, fp32 or 16-bit per feature_dtype (ignored when d_rgb == 0)  */
+    const void* flow;        /* [B, T, d_flow] contiguous, same type (ignored when d_flow == 0 or flow_is_zero)        */
     int64_t B;
     int64_t T;
     float* h_state;          /* [B, H] GRU state, read before / written after; NULL = zeros in, dropped out
@@ -75,6 +84,10 @@ typedef struct prego_forward_args {
     size_t workspace_bytes;
     int32_t precision;       /* PREGO_PREC_* */
     int32_t chunk_T;         /* frames per stream processed per pass (time chunk with carried h); 0 = T */
+    int32_t feature_dtype;   /* PREGO_FEAT_* */
+    int32_t flow_is_zero;    /* 1: the caller asserts flow == 0 everywhere, as both shipped configs feed it
+                                (datasets/dataset.py:63-69); flow may be NULL and its half of the projection is skipped.
+                                Results are bit-identical to passing an all-zero flow tensor. */
 } prego_forward_args_t;
 
 int prego_abi_version(void);

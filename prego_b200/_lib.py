@@ -35,7 +35,10 @@ class ForwardArgs(C.Structure):
     _fields_ = [("rgb", C.c_void_p), ("flow", C.c_void_p), ("B", C.c_int64), ("T", C.c_int64),
                 ("h_state", C.c_void_p), ("probs", C.c_void_p), ("logits", C.c_void_p),
                 ("labels", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("precision", C.c_int32), ("chunk_T", C.c_int32)]
+                ("precision", C.c_int32), ("chunk_T", C.c_int32), ("feature_dtype", C.c_int32), ("flow_is_zero", C.c_int32)]
+
+
+FEAT_F32, FEAT_16 = 0, 1
 
 
 class Grads(C.Structure):

@@ -251,7 +251,8 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N,
 // CTA-pair (cta_group::2) launch of the same GEMM contract; tmB must be encoded with box rows TILE_N / 2.
 template <int TILE_N, int STAGES, int FMT, class Epi>
 int launch_gemm_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int a_c1, const Epi& epi,
-                    int sm_count, cudaStream_t stream, const char* name) {
+                    int sm_count, cudaStream_t stream, const char* name, const CUtensorMap* tmA2 = nullptr, int k_split = 0,
+                    int rows_per_c1 = 0) {
     using Cfg = Gemm2Cfg<TILE_N>;
     auto kfn = gemm_tc2_kernel<TILE_N, STAGES, FMT, Epi>;
     static bool attr_set = false;
@@ -262,7 +263,8 @@ int launch_gemm_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N
     }
     const int tiles = (N / TILE_N) * ((M + 2 * kTileM - 1) / (2 * kTileM));
     int grid = 2 * tiles < sm_count ? 2 * tiles : (sm_count & ~1);
-    kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, a_c1, epi);
+    if (tmA2 == nullptr) kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, a_c1, epi, tmA, K, 0);
+    else kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, a_c1, epi, *tmA2, k_split, rows_per_c1);
     LAUNCH_CHECK(name);
     return PREGO_OK;
 }
@@ -287,14 +289,17 @@ bool use_persistent_gru() {
     return v == 1;
 }
 
-bool use_overlap() {
+// PREGO_STAGE_OVERLAP: 0 = stage every chunk on the main stream; 1 (default) = stage chunk c + 1 on the side stream
+// under chunk c's GEMM1; 2 = under chunk c's recurrence (tensor/epilogue-bound with HBM to spare).
+int overlap_mode() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("PREGO_STAGE_OVERLAP");
-        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+        v = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
     }
-    return v == 1;
+    return v;
 }
+bool use_overlap() { return overlap_mode() != 0; }
 
 bool use_2cta() {
     static int v = -1;
@@ -375,16 +380,32 @@ int run_latency_recurrence(prego_model* m, const float* gi, float*& h_cur, float
     return PREGO_OK;
 }
 
-// One time chunk of the 16-bit tensor-core path.
+// Width of the projection input actually read: the flow half is skipped when the caller declares it all-zero.
+inline int eff_dflow(const prego_model* m, const prego_forward_args_t* a) { return a->flow_is_zero ? 0 : m->d.d_flow; }
+
+// Feature staging of one time chunk of the 16-bit tensor-core path: time-major operand rows [Mc, d_rgb + eff_dflow].
 template <int FMT>
 int stage_chunk(prego_model* m, const prego_forward_args_t* a, void* xb, int64_t t0, int tc, int blocks_per_sm, cudaStream_t s) {
     using OpT = typename Op16<FMT>::T;
     const int64_t Mc = a->B * tc;
-    int grid = grid_for(Mc * (m->din / 8), 256, m->sm_count);
+    const int Df = eff_dflow(m, a), D = m->d.d_rgb + Df;
+    int grid = grid_for(Mc * (D / 8), 256, m->sm_count);
     if (blocks_per_sm > 0 && grid > m->sm_count * blocks_per_sm) grid = m->sm_count * blocks_per_sm;
-    stage_features_16<FMT><<<grid, 256, 0, s>>>(a->rgb, a->flow, reinterpret_cast<OpT*>(xb), Mc, m->d.d_rgb, m->d.d_flow, (int)a->B, (int)a->T, (int)t0);
+    if (a->feature_dtype == PREGO_FEAT_16)
+        stage_features_16from16<<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(a->rgb), static_cast<const uint16_t*>(a->flow),
+                                                      static_cast<uint16_t*>(xb), Mc, m->d.d_rgb, Df, (int)a->B, (int)a->T, (int)t0);
+    else
+        stage_features_16<FMT><<<grid, 256, 0, s>>>(static_cast<const float*>(a->rgb), static_cast<const float*>(a->flow),
+                                                    reinterpret_cast<OpT*>(xb), Mc, m->d.d_rgb, Df, (int)a->B, (int)a->T, (int)t0);
     LAUNCH_CHECK("stage_features_16");
     return PREGO_OK;
+}
+
+// 16-bit features of a [B, T, D] tensor read in place by the projection GEMM: (k, t, b) view, box (64, 1, 128).
+int make_tmap_feat(CUtensorMap* tm, DType dt, const void* base, uint64_t D, uint64_t T, uint64_t B) {
+    const uint64_t dims[3] = {D, T, B}, str[2] = {D * 2, T * D * 2};
+    const uint32_t box[3] = {kTileK, 1, kTileM};
+    return make_tmap(tm, dt, 3, base, dims, str, box);
 }
 
 // ci = chunk index; with overlap the features of chunk ci were staged into xb[ci & 1] ahead of time on the side
@@ -398,7 +419,11 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     const int64_t B = a->B, T = a->T, Mc = B * tc;
     const int Mi = static_cast<int>(Mc);
     const int H = d.hidden_dim, E = d.embed_dim, K = d.num_classes, Din = m->din;
+    const int Dfe = eff_dflow(m, a), Dine = d.d_rgb + Dfe;  // projection columns actually read
     const bool batched = B > kLatencyMaxB;
+    // 16-bit features + whole 128-row tiles per time step: GEMM1's TMA gathers the time-major rows from the caller's
+    // tensors, no staging pass and no xb traffic
+    const bool direct = a->feature_dtype == PREGO_FEAT_16 && B % kTileM == 0 && use_2cta();
     OpT* xb = reinterpret_cast<OpT*>(ws + ((overlap && (ci & 1)) ? p.xb2 : p.xb));
     void* ye = ws + p.ye;
     void* gi = ws + p.gi;
@@ -407,29 +432,45 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     CUtensorMap tmA, tmB;
 
     // 1. stage features: concat + operand rounding (replaces torch.cat, rnn.py:53)
-    if (!overlap) {
+    if (direct) {
+    } else if (!overlap) {
         RC_TRY(stage_chunk<FMT>(m, a, xb, t0, tc, 0, s));
     } else {
         CUDA_TRY(cudaStreamWaitEvent(s, m->ev_ready[ci & 1], 0));  // staged on the side stream (or by the prologue)
     }
     prof_mark(m, s, PREGO_PHASE_STAGE, 1);
     // 2. y = x W1^T + b1  (fp16 out; rows stay time-major, m = t*B + b)
-    RC_TRY(make_tmap_a(&tmA, dt, xb, Din, Mc));
-    if (use_2cta()) {
+    if (direct) {
+        CUtensorMap tmA2;
+        const bool both = d.d_rgb > 0 && Dfe > 0;
+        if (d.d_rgb > 0) RC_TRY(make_tmap_feat(&tmA, dt, a->rgb, d.d_rgb, T, B));
+        else RC_TRY(make_tmap_feat(&tmA, dt, a->flow, d.d_flow, T, B));
+        if (both) RC_TRY(make_tmap_feat(&tmA2, dt, a->flow, d.d_flow, T, B));
         RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 128));
-        RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, E, Din, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1 (2cta)")));
+        RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, E, Dine, (int)t0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s,
+                                             "gemm1 (2cta, features in place)", both ? &tmA2 : &tmA, both ? d.d_rgb : Dine, (int)B)));
+    } else if (use_2cta()) {
+        RC_TRY(make_tmap_a(&tmA, dt, xb, Dine, Mc));
+        RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 128));
+        RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, E, Dine, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1 (2cta)")));
     } else {
+        RC_TRY(make_tmap_a(&tmA, dt, xb, Dine, Mc));
         RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 256));
-        RC_TRY((launch_gemm_tc<256, 4, FMT>(tmA, tmB, Mi, E, Din, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1")));
+        RC_TRY((launch_gemm_tc<256, 4, FMT>(tmA, tmB, Mi, E, Dine, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1")));
     }
+    auto stage_next = [&]() -> int {
+        // next chunk's features -> the other buffer, on the side stream
+        CUDA_TRY(cudaStreamWaitEvent(m->side, m->ev_free[(ci + 1) & 1], 0));
+        RC_TRY(stage_chunk<FMT>(m, a, ws + (((ci + 1) & 1) ? p.xb2 : p.xb), t_next, tc_next, 4, m->side));
+        CUDA_TRY(cudaEventRecord(m->ev_ready[(ci + 1) & 1], m->side));
+        return PREGO_OK;
+    };
     if (overlap) {
         CUDA_TRY(cudaEventRecord(m->ev_free[ci & 1], s));  // GEMM1 has consumed this staging buffer
-        if (tc_next > 0) {
-            // next chunk's features -> the other buffer, on the side stream, issued AFTER GEMM1 so the GEMM's CTAs are
-            // placed first; a capped grid leaves room for them to co-reside (HBM-bound next to tensor-bound work)
-            CUDA_TRY(cudaStreamWaitEvent(m->side, m->ev_free[(ci + 1) & 1], 0));
-            RC_TRY(stage_chunk<FMT>(m, a, ws + (((ci + 1) & 1) ? p.xb2 : p.xb), t_next, tc_next, 4, m->side));
-            CUDA_TRY(cudaEventRecord(m->ev_ready[(ci + 1) & 1], m->side));
+        if (tc_next > 0 && overlap_mode() == 1) {
+            // issued AFTER GEMM1 so the GEMM's CTAs are placed first; a capped grid leaves room for them to co-reside
+            // (HBM-bound next to tensor-bound work)
+            RC_TRY(stage_next());
         }
     }
     prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
@@ -454,6 +495,11 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
             RC_TRY((launch_gemm_tc<192, 5, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<192, -1>{gi, m->bih_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2")));
     }
     prof_mark(m, s, PREGO_PHASE_GEMM2, 1);
+    if (overlap && tc_next > 0 && overlap_mode() == 2) {
+        CUDA_TRY(cudaEventRecord(m->ev_begin, s));  // GEMM2 done -> the side stream may start staging under the recurrence
+        CUDA_TRY(cudaStreamWaitEvent(m->side, m->ev_begin, 0));
+        RC_TRY(stage_next());
+    }
 
     // 5. recurrence
     if (batched) {
@@ -545,7 +591,7 @@ int online_step_r(prego_model* m, const prego_forward_args_t* a, const Plan& p, 
         attr_max = smem1;
     }
     const int wpb = kOnlineThreads / 32;
-    online_proj1<FMT, R><<<(E + wpb - 1) / wpb, kOnlineThreads, smem1, s>>>(a->rgb, a->flow, reinterpret_cast<const OpT*>(m->w1_16[FMT]), m->b1, y,
+    online_proj1<FMT, R><<<(E + wpb - 1) / wpb, kOnlineThreads, smem1, s>>>(static_cast<const float*>(a->rgb), static_cast<const float*>(a->flow), reinterpret_cast<const OpT*>(m->w1_16[FMT]), m->b1, y,
                                                                             rows, d.d_rgb, d.d_flow, E, a->T, 0);
     prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
     online_proj2<FMT, R><<<(3 * H + wpb - 1) / wpb, kOnlineThreads, R * E * 2, s>>>(y, m->ln_g, m->ln_b, reinterpret_cast<const OpT*>(m->wih_16p[FMT]),
@@ -573,7 +619,7 @@ void online_fused_carve(float* scratch, int E, int K, OnlineFusedArgs* fa) {
 int online_step_fused(prego_model* m, const prego_forward_args_t* a, float* h, int fmt, cudaStream_t s) {
     const prego_dims_t& d = m->d;
     OnlineFusedArgs fa{};
-    fa.rgb = a->rgb; fa.flow = a->flow;
+    fa.rgb = static_cast<const float*>(a->rgb); fa.flow = static_cast<const float*>(a->flow);
     fa.w1 = m->w1_16[fmt]; fa.wih = m->wih_16p[fmt]; fa.whh = m->whh_16p[fmt];
     fa.b1 = m->b1; fa.ln_g = m->ln_g; fa.ln_b = m->ln_b; fa.bih = m->bih_p; fa.bhh = m->bhh_p; fa.wct = m->wct_f32; fa.bc = m->bc;
     online_fused_carve(m->online_scratch, d.embed_dim, d.num_classes, &fa);
@@ -613,10 +659,13 @@ int chunk_f32(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint
     float* gh = reinterpret_cast<float*>(ws + p.gh);
     float* logits_ws = reinterpret_cast<float*>(ws + p.logits);
 
-    SgemmA A1{a->rgb, a->flow, d.d_rgb, d.d_rgb, d.d_flow, 1, tc, (int)T, (int)t0};
-    if (d.d_rgb == 0) { A1.a0 = a->flow; A1.a1 = nullptr; A1.k_split = Din; A1.lda0 = d.d_flow; }
+    const float *rgb32 = static_cast<const float*>(a->rgb), *flow32 = static_cast<const float*>(a->flow);
+    SgemmA A1{rgb32, flow32, d.d_rgb, d.d_rgb, d.d_flow, 1, tc, (int)T, (int)t0};
+    int K1 = Din;
+    if (d.d_rgb == 0) { A1.a0 = flow32; A1.a1 = nullptr; A1.k_split = Din; A1.lda0 = d.d_flow; }
     if (d.d_flow == 0) { A1.a1 = nullptr; A1.k_split = Din; }
-    sgemm_nt_f32<<<dim3(E / 128, (Mi + 127) / 128), 256, 0, s>>>(A1, m->w1_f32, m->b1, y32, Mi, E, Din, E);
+    if (a->flow_is_zero && d.d_flow > 0) { A1.a1 = nullptr; A1.k_split = d.d_rgb; A1.ldw = Din; K1 = d.d_rgb; }  // rgb columns of W1 only
+    sgemm_nt_f32<<<dim3(E / 128, (Mi + 127) / 128), 256, 0, s>>>(A1, m->w1_f32, m->b1, y32, Mi, E, K1, E);
     LAUNCH_CHECK("sgemm gemm1");
     prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
     layernorm_relu_f32<<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(y32, y32, m->ln_g, m->ln_b, Mc, E, 1e-5f);
@@ -797,7 +846,11 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
     const prego_dims_t& d = m->d;
     const int64_t B = a->B, T = a->T;
     if (B <= 0 || T <= 0) return fail(PREGO_ERR_INVALID, "B and T must be positive (got B=%lld, T=%lld)", (long long)B, (long long)T);
-    if ((d.d_rgb > 0 && a->rgb == nullptr) || (d.d_flow > 0 && a->flow == nullptr)) return fail(PREGO_ERR_INVALID, "rgb / flow pointer is NULL");
+    if (a->feature_dtype != PREGO_FEAT_F32 && a->feature_dtype != PREGO_FEAT_16) return fail(PREGO_ERR_INVALID, "unknown feature_dtype %d", a->feature_dtype);
+    if (a->flow_is_zero && d.d_rgb == 0) return fail(PREGO_ERR_INVALID, "flow_is_zero on a flow-only model leaves no input");
+    if ((d.d_rgb > 0 && a->rgb == nullptr) || (d.d_flow > 0 && !a->flow_is_zero && a->flow == nullptr)) return fail(PREGO_ERR_INVALID, "rgb / flow pointer is NULL");
+    if (a->feature_dtype == PREGO_FEAT_16 && a->precision == PREGO_PREC_FP32)
+        return fail(PREGO_ERR_INVALID, "16-bit features (PREGO_FEAT_16) need PREGO_PREC_F16 or PREGO_PREC_BF16; the exact path reads fp32 features");
     if (a->precision != PREGO_PREC_BF16 && a->precision != PREGO_PREC_FP32 && a->precision != PREGO_PREC_F16)
         return fail(PREGO_ERR_INVALID, "unknown precision %d", a->precision);
     const bool h16 = a->precision != PREGO_PREC_FP32;
@@ -806,7 +859,8 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
     if (B * Tc >= (int64_t(1) << 31) / 4) return fail(PREGO_ERR_INVALID, "B * chunk_T = %lld is too large for one pass; lower chunk_T", (long long)(B * Tc));
     // double-buffered feature staging only when there is a next chunk to stage and the caller's workspace has room
     Plan p = make_plan(d, B, Tc, a->precision, true);
-    const bool overlap = h16 && T > Tc && B > kLatencyMaxB && p.xb2 != 0 && a->workspace_bytes >= (size_t)p.total && use_overlap();
+    const bool overlap = h16 && T > Tc && B > kLatencyMaxB && p.xb2 != 0 && a->workspace_bytes >= (size_t)p.total && use_overlap() &&
+                         a->feature_dtype == PREGO_FEAT_F32;
     if (!overlap) p = make_plan(d, B, Tc, a->precision, false);
     if (a->workspace == nullptr || a->workspace_bytes < (size_t)p.total)
         return fail(PREGO_ERR_WORKSPACE, "workspace too small: need %lld bytes, got %zu", (long long)p.total, a->workspace_bytes);
@@ -819,7 +873,8 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
     float* h_cur = reinterpret_cast<float*>(ws + p.h32_a);
     float* h_alt = reinterpret_cast<float*>(ws + p.h32_b);
 
-    const bool online = h16 && T == 1 && B <= kOnlineMaxRows && d.d_rgb % 2 == 0 && m->din % 8 == 0;
+    const bool online = h16 && T == 1 && B <= kOnlineMaxRows && d.d_rgb % 2 == 0 && m->din % 8 == 0 &&
+                        a->feature_dtype == PREGO_FEAT_F32 && !a->flow_is_zero;
     if (online && a->h_state != nullptr) {
         h_cur = a->h_state;  // per-frame path: read the caller's state in place (one copy back instead of two)
     } else if (a->h_state != nullptr) {

@@ -216,7 +216,10 @@ struct Gemm2Cfg {
 template <int TILE_N, int STAGES, int FMT, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                int a_c1, Epi epi) {
+                int a_c1, Epi epi, const __grid_constant__ CUtensorMap tmA2, int k_split, int rows_per_c1) {
+    // A operand, general form: columns [0, k_split) come from tmA, the rest from tmA2 (rgb | flow read in place from the
+    // caller's tensors); rows_per_c1 > 0 folds the row index into the middle coordinate (row m -> (a_c1 + m / rows_per_c1,
+    // m % rows_per_c1): time-major chunk rows gathered straight from a [B, T, D] tensor).  Plain use: k_split >= K, 0.
     using Cfg = Gemm2Cfg<TILE_N>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -241,6 +244,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmA2);
         ptx::prefetch_tmap(&tmB);
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
@@ -268,11 +272,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
                 const int m0 = (tile / n_tiles) * (2 * kTileM) + static_cast<int>(rank) * kTileM;
                 const int n0 = (tile % n_tiles) * TILE_N + static_cast<int>(rank) * (TILE_N / 2);
+                const int c1 = rows_per_c1 > 0 ? a_c1 + m0 / rows_per_c1 : a_c1;
+                const int mr = rows_per_c1 > 0 ? m0 % rows_per_c1 : m0;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-                    ptx::tma_load_3d_2sm(&tmA, sa, &full_bar[stage], kb * kElemsK, a_c1, m0, ptx::kEvictNormal);
+                    const int kk = kb * kElemsK;
+                    if (kk < k_split) ptx::tma_load_3d_2sm(&tmA, sa, &full_bar[stage], kk, c1, mr, ptx::kEvictNormal);
+                    else ptx::tma_load_3d_2sm(&tmA2, sa, &full_bar[stage], kk - k_split, c1, mr, ptx::kEvictNormal);
                     ptx::tma_load_2d_2sm(&tmB, sa + Cfg::kABytes, &full_bar[stage], kb * kElemsK, n0, ptx::kEvictLast);
                     if (++stage == STAGES) {
                         stage = 0;

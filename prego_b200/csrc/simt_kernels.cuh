@@ -46,6 +46,24 @@ stage_features_16(const float* __restrict__ rgb, const float* __restrict__ flow,
     }
 }
 
+// Same rearrangement for features the caller already keeps in the 16-bit operand format (PREGO_FEAT_16): pure
+// 16-byte copies.  Used when the projection GEMM cannot read the caller's tensors in place (B % 128 != 0).
+__global__ void __launch_bounds__(256)
+stage_features_16from16(const uint16_t* __restrict__ rgb, const uint16_t* __restrict__ flow, uint16_t* __restrict__ xb,
+                        int64_t Mc, int Dr, int Df, int B, int T, int t0) {
+    const int D = Dr + Df;
+    const int vec_per_row = D / 8;
+    const int64_t total = Mc * vec_per_row;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t m = i / vec_per_row;
+        const int c = static_cast<int>(i % vec_per_row) * 8;
+        const int64_t g = (m % B) * static_cast<int64_t>(T) + t0 + (m / B);
+        const uint16_t* src = (c < Dr) ? (rgb + g * Dr + c) : (flow + g * Df + (c - Dr));
+        *reinterpret_cast<uint4*>(xb + m * D + c) = __ldcs(reinterpret_cast<const uint4*>(src));
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // LayerNorm (biased variance, eps inside the sqrt) + ReLU over rows of width E
 // (rnn.py:41-42).  One warp per row, the row lives in registers; two-pass variance.
@@ -172,6 +190,7 @@ struct SgemmA {
     int64_t lda0, lda1;
     int remap;        // 1: row m -> chunk_row_to_global(m, Tc, T, t0)
     int Tc, T, t0;
+    int64_t ldw = 0;  // row stride of W (0 = K)
 };
 
 __global__ void __launch_bounds__(256)
@@ -185,6 +204,7 @@ sgemm_nt_f32(SgemmA A, const float* __restrict__ W, const float* __restrict__ bi
     const int n0 = blockIdx.x * BN;
     const int tx = tid % 16;  // column group
     const int ty = tid / 16;  // row group
+    const int64_t ldw = A.ldw > 0 ? A.ldw : K;
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -219,7 +239,7 @@ sgemm_nt_f32(SgemmA A, const float* __restrict__ W, const float* __restrict__ bi
             As[lk + 2][lr + 64 * h] = a.z;
             As[lk + 3][lr + 64 * h] = a.w;
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (wval[h]) w = __ldg(reinterpret_cast<const float4*>(W + static_cast<int64_t>(n0 + lr + 64 * h) * K + k));
+            if (wval[h]) w = __ldg(reinterpret_cast<const float4*>(W + static_cast<int64_t>(n0 + lr + 64 * h) * ldw + k));
             Ws[lk + 0][lr + 64 * h] = w.x;
             Ws[lk + 1][lr + 64 * h] = w.y;
             Ws[lk + 2][lr + 64 * h] = w.z;

@@ -141,24 +141,33 @@ class MROAD(nn.Module):
     # ------------------------------------------------------------------------ inference
     @torch.no_grad()
     def infer(self, rgb_input, flow_input, h_state=None, want_probs=True, want_logits=False, want_labels=True,
-              precision=None, chunk_T=None, out=None):
-        """Run the CUDA path.  rgb/flow: fp32 CUDA tensors [B, T, D].  ``h_state`` ([B, H] fp32 CUDA)
-        is updated in place when given (streaming / time-chunked online inference)."""
+              precision=None, chunk_T=None, out=None, zero_flow=False):
+        """Run the CUDA path.  rgb/flow: CUDA tensors [B, T, D], fp32 (the reference loader's format) or already in the
+        16-bit operand format of ``precision`` (torch.float16 for 'fp16', torch.bfloat16 for 'bf16': same results, no
+        staging pass, half the bytes).  ``zero_flow``: the caller asserts the flow stream is all zero, as the shipped
+        configs feed it (datasets/dataset.py:63-69); ``flow_input`` may then be None and its half of the projection
+        is skipped (bit-identical to passing zeros).  ``h_state`` ([B, H] fp32 CUDA) is updated in place when given
+        (streaming / time-chunked online inference)."""
         ref = rgb_input if self.use_rgb else flow_input
         if not isinstance(ref, torch.Tensor) or not ref.is_cuda:
             raise RuntimeError("prego_b200.MROAD runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
         device = ref.device
         B, T = int(ref.shape[0]), int(ref.shape[1])
+        prec_name = precision or self.precision
+        feat_dtype = ref.dtype
+        want16 = {"fp16": torch.float16, "bf16": torch.bfloat16}.get(prec_name)
+        if feat_dtype != torch.float32 and feat_dtype != want16:
+            raise RuntimeError(f"features must be fp32, or {want16} for precision '{prec_name}'; got {feat_dtype}")
 
         def prep(x, d, name):
             if d == 0:
                 return None
-            if x.device != device or x.dtype != torch.float32 or tuple(x.shape) != (B, T, d):
-                raise RuntimeError(f"{name} must be fp32 [{B}, {T}, {d}] on {device}, got {x.dtype} {tuple(x.shape)} on {x.device}")
+            if x.device != device or x.dtype != feat_dtype or tuple(x.shape) != (B, T, d):
+                raise RuntimeError(f"{name} must be {feat_dtype} [{B}, {T}, {d}] on {device}, got {x.dtype} {tuple(x.shape)} on {x.device}")
             return x.contiguous()
 
         rgb = prep(rgb_input, self.d_rgb, "rgb_input")
-        flow = prep(flow_input, self.d_flow, "flow_input")
+        flow = None if (zero_flow and flow_input is None) else prep(flow_input, self.d_flow, "flow_input")
         prec = _lib.PRECISIONS[precision or self.precision]
         with torch.cuda.device(device):
             lib = self._ensure_handle(device)
@@ -185,7 +194,7 @@ class MROAD(nn.Module):
                 probs.data_ptr() if probs is not None else None,
                 logits.data_ptr() if logits is not None else None,
                 labels.data_ptr() if labels is not None else None,
-                ws_ptr, need, prec, chunk_T)
+                ws_ptr, need, prec, chunk_T, _lib.FEAT_F32 if feat_dtype == torch.float32 else _lib.FEAT_16, 1 if zero_flow else 0)
             stream = torch.cuda.current_stream(device).cuda_stream
             _lib.check(lib.prego_forward(self._handle, C.byref(args), stream), "prego_forward")
         return {"probs": probs, "logits": logits, "labels": labels}
