@@ -42,6 +42,10 @@ struct GruLatencyArgs {
     uint32_t tag_base;     // tags used: tag_base + 1 .. tag_base + Tc
     int out_fmt;
     int64_t row_sb, row_st;
+    // training forward (rnn.py:61 in train mode): gates and states saved for BPTT, time-major [T][sv_B][H]
+    // (sv_h: [T + 1][sv_B][H], slot t + 1 = h_t); all NULL in inference
+    float *sv_r = nullptr, *sv_z = nullptr, *sv_n = nullptr, *sv_ghn = nullptr, *sv_h = nullptr;
+    int sv_B = 0;
 };
 
 // REGW = true (H == 1024): the warp's three weight rows live in REGISTERS (96 per lane) -- the per-step
@@ -191,7 +195,123 @@ gru_latency_kernel(GruLatencyArgs a) {
             else
                 reinterpret_cast<__nv_bfloat16*>(a.hrelu)[orow * H + u] = __float2bfloat16_rn(fmaxf(hn, 0.f));
             if (t == a.Tc - 1) a.h_out[static_cast<int64_t>(a.b0 + lane) * H + u] = hn;
+            if (a.sv_r != nullptr) {
+                const int64_t si = (static_cast<int64_t>(t) * a.sv_B + a.b0 + lane) * H + u;
+                a.sv_r[si] = r;
+                a.sv_z[si] = z;
+                a.sv_n[si] = n;
+                a.sv_ghn[si] = ghn + bh[2];
+                a.sv_h[si + static_cast<int64_t>(a.sv_B) * H] = hn;
+            }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent BPTT through the GRU recurrence (the backward of rnn.py:61), same structure run in reverse: one warp
+// owns hidden unit u, keeps COLUMN u of W_hh' (3H fp32 = 96 registers per lane) for the whole sequence and carries
+// d h[:, u] in registers.  Per step t (descending):
+//   dh   = dh_carry + dhrelu_t * [h_t > 0]
+//   dn~  = dh (1 - z) (1 - n^2);  dz~ = dh (h_{t-1} - n) z (1 - z);  dr~ = dn~ ghn r (1 - r)
+//   dgi_t = (dr~, dz~, dn~),  dgh_t = (dr~, dz~, dn~ r)            -> global (inputs of the weight-gradient GEMMs)
+//   dh_carry' = dh z + sum_p dgh_t[p] W_hh'[p, u]                   (all-to-all of dgh_t: tagged 8-byte words, as above)
+struct GruBpttArgs {
+    const float* whhT;     // [H, 3H] fp32: W_hh' transposed (row u = column u of the packed matrix)
+    const float *r, *z, *n, *ghn;  // [T][B][H]
+    const float* hall;     // [T + 1][B][H]
+    const float* dhrelu;   // [T][B][H]
+    float *dgi, *dgh;      // [T][B][3H] packed columns
+    uint2* xchg;           // [2][NB][3H] tagged exchange words
+    int* err_flag;
+    int T, B, b0, nb;
+    uint32_t tag_base;     // tags used: tag_base + 1 .. tag_base + T
+};
+
+template <int NB>
+__global__ void __launch_bounds__(kLatThreads, 1)
+gru_bptt_kernel(GruBpttArgs a) {
+    constexpr int H = 1024, H3 = 3 * H;
+    extern __shared__ float smem_f[];  // [2][NB][3H]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int u = blockIdx.x * kLatUnitsPerCta + warp;
+    const int pcol = (u / 64) * 192 + (u % 64);
+    float wcol[96];
+#pragma unroll
+    for (int i = 0; i < 96; ++i) wcol[i] = __ldg(a.whhT + static_cast<int64_t>(u) * H3 + lane + 32 * i);
+    float dh_carry = 0.f;  // lane s: d h_t[stream b0 + s, u] flowing in from step t + 1
+    for (int step = 0; step < a.T; ++step) {
+        const int t = a.T - 1 - step;
+        float dgate_n_r = 0.f, dhz = 0.f;
+        if (lane < a.nb) {
+            const int64_t si = (static_cast<int64_t>(t) * a.B + a.b0 + lane) * H + u;
+            const float r = __ldcs(a.r + si), z = __ldcs(a.z + si), n = __ldcs(a.n + si), ghn = __ldcs(a.ghn + si);
+            const float h_t = __ldcs(a.hall + si + static_cast<int64_t>(a.B) * H), h_prev = __ldcs(a.hall + si);
+            const float dh = dh_carry + (h_t > 0.f ? __ldcs(a.dhrelu + si) : 0.f);
+            const float dn = dh * (1.0f - z);
+            const float dz = dh * (h_prev - n);
+            const float dan = dn * (1.0f - n * n);
+            const float dar = dan * ghn * r * (1.0f - r);
+            const float daz = dz * z * (1.0f - z);
+            dgate_n_r = dan * r;
+            dhz = dh * z;
+            const int64_t gi = (static_cast<int64_t>(t) * a.B + a.b0 + lane) * H3 + pcol;
+            a.dgi[gi] = dar; a.dgi[gi + 64] = daz; a.dgi[gi + 128] = dan;
+            a.dgh[gi] = dar; a.dgh[gi + 64] = daz; a.dgh[gi + 128] = dgate_n_r;
+            uint2* xs = a.xchg + (static_cast<int64_t>(step & 1) * NB + lane) * H3 + pcol;
+            const uint32_t tag = a.tag_base + static_cast<uint32_t>(step) + 1u;
+            ptx::st_volatile_u64(xs, __float_as_uint(dar), tag);
+            ptx::st_volatile_u64(xs + 64, __float_as_uint(daz), tag);
+            ptx::st_volatile_u64(xs + 128, __float_as_uint(dgate_n_r), tag);
+        }
+        if (t == 0) break;  // d h_{-1} is not needed (h0 is a constant, rnn.py:49)
+        // gather dgh_t of all units
+        float* db = smem_f + (step & 1) * NB * H3;
+        const uint32_t want = a.tag_base + static_cast<uint32_t>(step) + 1u;
+        const uint2* xs = a.xchg + static_cast<int64_t>(step & 1) * NB * H3;
+        int timed_out = 0;
+        for (int idx = tid; idx < NB * H3; idx += 4 * kLatThreads) {
+            uint2 v[4];
+            long long spins = 0;
+            bool done;
+            do {
+                done = true;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ii = idx + j * kLatThreads;
+                    const bool live = ii < NB * H3 && (ii / H3) < a.nb;
+                    v[j] = live ? ptx::ld_volatile_u64(xs + ii) : make_uint2(0u, want);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) done = done && (v[j].y == want);
+                if (!done && ++spins > (1ll << 22)) {
+                    *a.err_flag = 2;
+                    timed_out = 1;
+                    done = true;
+                }
+            } while (!done);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ii = idx + j * kLatThreads;
+                if (ii < NB * H3) db[ii] = __uint_as_float(v[j].x);
+            }
+        }
+        if (__syncthreads_or(timed_out)) return;
+        float acc[NB];
+#pragma unroll
+        for (int s = 0; s < NB; ++s) acc[s] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 96; ++i)
+#pragma unroll
+            for (int s = 0; s < NB; ++s) acc[s] = fmaf(wcol[i], db[s * H3 + lane + 32 * i], acc[s]);
+#pragma unroll
+        for (int s = 0; s < NB; ++s)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+        float mine = 0.f;
+#pragma unroll
+        for (int s = 0; s < NB; ++s)
+            if (lane == s) mine = acc[s];
+        dh_carry = dhz + mine;
     }
 }
 
