@@ -244,28 +244,33 @@ def training_leg(dev, world):
     crit = OadLoss(cfg)
     opt = torch.optim.AdamW([{"params": model.parameters(), "initial_lr": 1e-4}], lr=1e-4, weight_decay=0.05)
     out = {}
-    for B in (16, 256):
-        T = 128
-        rgb, flow = synthetic.device_features(B, T, dev, seed=7, zero_flow=True)
-        target = torch.nn.functional.one_hot(torch.randint(0, 86, (B, T), device=dev), 86).float()
-        for _ in range(2):
-            train_one_step(model, crit, opt, rgb, flow, target)
-        torch.cuda.synchronize()
-        n = 5 if B == 16 else 3
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if world > 1:
-            dist.barrier()
-        e0.record()
-        for _ in range(n):
-            loss = train_one_step(model, crit, opt, rgb, flow, target)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        out[f"B{B}_T{T}"] = {"ms_per_step": float(ms), "frames_per_s": world * B * T / float(ms) * 1e3, "loss": float(loss)}
-        del rgb, flow, target
-    out["note"] = "fwd + BPTT + torch AdamW, dropout 0.2, flow = 0, fp32 CUDA-core GEMMs; grads all-reduced (NCCL) when n_gpus > 1"
+    for prec in ("fp32", "tf32"):
+        model.train_precision = prec
+        for B in (16, 256):
+            T = 128
+            rgb, flow = synthetic.device_features(B, T, dev, seed=7, zero_flow=True)
+            target = torch.nn.functional.one_hot(torch.randint(0, 86, (B, T), device=dev), 86).float()
+            for _ in range(2):
+                train_one_step(model, crit, opt, rgb, flow, target)
+            torch.cuda.synchronize()
+            n = 5 if B == 16 else 3
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            e0.record()
+            for _ in range(n):
+                loss = train_one_step(model, crit, opt, rgb, flow, target)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            out[f"B{B}_T{T}" + ("" if prec == "fp32" else "_tf32")] = {"ms_per_step": float(ms), "frames_per_s": world * B * T / float(ms) * 1e3,
+                                                                       "loss": float(loss)}
+            del rgb, flow, target
+    out["note"] = ("fwd + BPTT + torch AdamW, dropout 0.2, flow = 0; recurrence (forward and BPTT) on the persistent exact-fp32 kernels "
+                   "for B <= 64; plain keys: every GEMM exact fp32 on CUDA cores (parity mode); *_tf32: large projections and their "
+                   "gradients on tcgen05 kind::tf32; grads all-reduced (NCCL) when n_gpus > 1")
     return out
 
 

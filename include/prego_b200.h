@@ -157,6 +157,12 @@ typedef struct prego_train_args {
     size_t workspace_bytes;
     float dropout_p;         /* cfg['dropout']; 0 disables */
     uint64_t seed;           /* dropout mask stream */
+    int32_t precision;       /* PREGO_PREC_FP32 (0 is read as FP32 too): every GEMM exact fp32 on CUDA cores (the parity
+                                mode); PREGO_PREC_TF32: the large projections and their weight / input gradients run on
+                                tcgen05 kind::tf32 (fp32 storage, 10-bit-mantissa operands, fp32 accumulate) -- the
+                                reference's own GPU practice (cuDNN RNN allows TF32; main.py --amp trains in fp16).
+                                The recurrence, LayerNorm, loss and the classifier stay exact fp32 either way. */
+    int32_t reserved;
 } prego_train_args_t;
 
 size_t prego_train_workspace_bytes(const prego_model_t* model, int64_t B, int64_t T);

@@ -15,7 +15,9 @@ LIB_PATH = os.path.join(_HERE, "libprego_b200.so")
 PREC_BF16 = 0
 PREC_FP32 = 1
 PREC_F16 = 2
+PREC_TF32 = 3  # training only
 PRECISIONS = {"bf16": PREC_BF16, "fp32": PREC_FP32, "fp16": PREC_F16}
+TRAIN_PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32}
 PHASES = ("stage", "gemm1", "layernorm", "gemm2", "recurrence", "head")
 
 
@@ -49,7 +51,7 @@ class TrainArgs(C.Structure):
     _fields_ = [("rgb", C.c_void_p), ("flow", C.c_void_p), ("B", C.c_int64), ("T", C.c_int64),
                 ("logits", C.c_void_p), ("dlogits", C.c_void_p), ("grads", C.POINTER(Grads)),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("dropout_p", C.c_float),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("precision", C.c_int32), ("reserved", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/prego_b200.h declares

@@ -158,7 +158,7 @@ struct prego_model {
          *wc_16p[2] = {nullptr, nullptr};
     // latency-kernel exchange
     uint2* xchg = nullptr;
-    uint2* xchg_bwd = nullptr;  // [2][4][3H] exchange words of the persistent BPTT kernel
+    uint4* xchg_bwd = nullptr;  // [2][4][H] exchange words of the persistent BPTT kernel
     int* err_flag = nullptr;
     uint32_t tag_base = 0;
     // side stream: stages the features of the next time chunk (HBM-bound) under the current chunk's GEMMs
@@ -776,8 +776,8 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
 #undef ALLOC
     CUDA_TRY(cudaMemset(m->online_scratch, 0, online_fused_scratch_floats((int)E, (int)K) * 4));
     CUDA_TRY(cudaMemset(m->xchg, 0, 2 * 4 * H * sizeof(uint2)));
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->xchg_bwd), 2 * 4 * 3 * H * sizeof(uint2)));
-    CUDA_TRY(cudaMemset(m->xchg_bwd, 0, 2 * 4 * 3 * H * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->xchg_bwd), 2 * 4 * H * sizeof(uint4)));
+    CUDA_TRY(cudaMemset(m->xchg_bwd, 0, 2 * 4 * H * sizeof(uint4)));
     CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
     CUDA_TRY(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&m->ev_begin, cudaEventDisableTiming));

@@ -101,20 +101,22 @@ gru_latency_kernel(GruLatencyArgs a) {
         } else {
             const uint32_t want = a.tag_base + static_cast<uint32_t>(t);
             const uint2* xs = a.xchg + ((t - 1) & 1) * NB * H;
-            for (int idx = tid; idx < NB * H; idx += 4 * kLatThreads) {
-                uint2 v[4];
+            // all of this thread's words are requested in one batch per poll round: the step costs ~one L2 round trip
+            constexpr int PW = REGW ? NB * 1024 / kLatThreads : 4;  // words per thread per batch
+            for (int idx = tid; idx < NB * H; idx += PW * kLatThreads) {
+                uint2 v[PW];
                 long long spins = 0;
                 bool done;
                 do {
                     done = true;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < PW; ++j) {
                         const int ii = idx + j * kLatThreads;
                         const bool live = ii < NB * H && (ii / H) < a.nb;
                         v[j] = live ? ptx::ld_volatile_u64(xs + ii) : make_uint2(0u, want);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) done = done && (v[j].y == want);
+                    for (int j = 0; j < PW; ++j) done = done && (v[j].y == want);
                     if (!done && ++spins > (1ll << 22)) {  // ~seconds: a peer CTA is missing
                         *a.err_flag = 1;
                         timed_out = 1;
@@ -122,7 +124,7 @@ gru_latency_kernel(GruLatencyArgs a) {
                     }
                 } while (!done);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < PW; ++j) {
                     const int ii = idx + j * kLatThreads;
                     if (ii < NB * H) hb[ii] = __uint_as_float(v[j].x);
                 }
@@ -221,7 +223,7 @@ struct GruBpttArgs {
     const float* hall;     // [T + 1][B][H]
     const float* dhrelu;   // [T][B][H]
     float *dgi, *dgh;      // [T][B][3H] packed columns
-    uint2* xchg;           // [2][NB][3H] tagged exchange words
+    uint4* xchg;           // [2][NB][H] tagged exchange words {dr~, dz~, dn~ r, tag}: one aligned 16-byte store each
     int* err_flag;
     int T, B, b0, nb;
     uint32_t tag_base;     // tags used: tag_base + 1 .. tag_base + T
@@ -257,32 +259,30 @@ gru_bptt_kernel(GruBpttArgs a) {
             const int64_t gi = (static_cast<int64_t>(t) * a.B + a.b0 + lane) * H3 + pcol;
             a.dgi[gi] = dar; a.dgi[gi + 64] = daz; a.dgi[gi + 128] = dan;
             a.dgh[gi] = dar; a.dgh[gi + 64] = daz; a.dgh[gi + 128] = dgate_n_r;
-            uint2* xs = a.xchg + (static_cast<int64_t>(step & 1) * NB + lane) * H3 + pcol;
-            const uint32_t tag = a.tag_base + static_cast<uint32_t>(step) + 1u;
-            ptx::st_volatile_u64(xs, __float_as_uint(dar), tag);
-            ptx::st_volatile_u64(xs + 64, __float_as_uint(daz), tag);
-            ptx::st_volatile_u64(xs + 128, __float_as_uint(dgate_n_r), tag);
+            ptx::st_volatile_u128(a.xchg + (static_cast<int64_t>(step & 1) * NB + lane) * H + u,
+                                  make_uint4(__float_as_uint(dar), __float_as_uint(daz), __float_as_uint(dgate_n_r),
+                                             a.tag_base + static_cast<uint32_t>(step) + 1u));
         }
         if (t == 0) break;  // d h_{-1} is not needed (h0 is a constant, rnn.py:49)
         // gather dgh_t of all units
         float* db = smem_f + (step & 1) * NB * H3;
         const uint32_t want = a.tag_base + static_cast<uint32_t>(step) + 1u;
-        const uint2* xs = a.xchg + static_cast<int64_t>(step & 1) * NB * H3;
+        const uint4* xs = a.xchg + static_cast<int64_t>(step & 1) * NB * H;
         int timed_out = 0;
-        for (int idx = tid; idx < NB * H3; idx += 4 * kLatThreads) {
-            uint2 v[4];
+        constexpr int PW = NB * H / kLatThreads;  // words per thread, all requested in one batch per poll round
+        {
+            uint4 v[PW];
             long long spins = 0;
             bool done;
             do {
                 done = true;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int ii = idx + j * kLatThreads;
-                    const bool live = ii < NB * H3 && (ii / H3) < a.nb;
-                    v[j] = live ? ptx::ld_volatile_u64(xs + ii) : make_uint2(0u, want);
+                for (int j = 0; j < PW; ++j) {
+                    const int ii = tid + j * kLatThreads;
+                    v[j] = (ii / H) < a.nb ? ptx::ld_volatile_u128(xs + ii) : make_uint4(0u, 0u, 0u, want);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) done = done && (v[j].y == want);
+                for (int j = 0; j < PW; ++j) done = done && (v[j].w == want);
                 if (!done && ++spins > (1ll << 22)) {
                     *a.err_flag = 2;
                     timed_out = 1;
@@ -290,9 +290,13 @@ gru_bptt_kernel(GruBpttArgs a) {
                 }
             } while (!done);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int ii = idx + j * kLatThreads;
-                if (ii < NB * H3) db[ii] = __uint_as_float(v[j].x);
+            for (int j = 0; j < PW; ++j) {
+                const int ii = tid + j * kLatThreads;
+                const int sidx = ii / H, uu = ii % H;
+                float* d = db + sidx * H3 + (uu / 64) * 192 + (uu % 64);
+                d[0] = __uint_as_float(v[j].x);
+                d[64] = __uint_as_float(v[j].y);
+                d[128] = __uint_as_float(v[j].z);
             }
         }
         if (__syncthreads_or(timed_out)) return;

@@ -359,5 +359,17 @@ __device__ __forceinline__ void st_volatile_u64(void* p, uint32_t lo, uint32_t h
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
 }
 
+// 16-byte aligned vector accesses travel as one request to one 32-byte sector: a reader sees all four words of a
+// store or none (what the {payload x 3, tag} exchange words of the BPTT kernel rely on).
+__device__ __forceinline__ uint4 ld_volatile_u128(const void* p) {
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+__device__ __forceinline__ void st_volatile_u128(void* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 }  // namespace ptx
 }  // namespace prego

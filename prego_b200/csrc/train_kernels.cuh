@@ -366,6 +366,26 @@ __global__ void unpack_rows_f32(const float* __restrict__ src, float* __restrict
     }
 }
 
+// dst[c, r] = src[r, c] through 32 x 32 shared-memory tiles (both sides coalesced).  The TN / NN operand forms of the
+// backward pass become the K-major NT form of the tensor-core GEMM through these (a few hundred MB per step, HBM-bound).
+__global__ void __launch_bounds__(256)
+transpose_tiled_f32(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = r0 + ty + 8 * j, c = c0 + tx;
+        tile[ty + 8 * j][tx] = (r < rows && c < cols) ? src[static_cast<int64_t>(r) * lds + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + ty + 8 * j, r = r0 + tx;
+        if (c < cols && r < rows) dst[static_cast<int64_t>(c) * ldd + r] = tile[tx][ty + 8 * j];
+    }
+}
+
 // time-major [T, B, K] -> caller's [B, T, K] (logits out) and back (dlogits in).
 __global__ void transpose_tb_f32(const float* __restrict__ src, float* __restrict__ dst, int B, int T, int K, int to_bt) {
     const int64_t total = static_cast<int64_t>(B) * T * K;

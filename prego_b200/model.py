@@ -48,7 +48,8 @@ _STATE_KEYS = (
 @META_ARCHITECTURES.register("MiniROAD")
 class MROAD(nn.Module):
     """B200-native MiniROAD.  Extra (optional) cfg keys: ``precision`` ('fp16' default | 'bf16' | 'fp32'),
-    ``chunk_frames`` (frames per pass over all streams; bounds the workspace)."""
+    ``chunk_frames`` (frames per pass over all streams; bounds the workspace), ``train_precision`` ('fp32' default:
+    exact CUDA-core GEMMs | 'tf32': the large projections and their gradients on tcgen05 kind::tf32)."""
 
     def __init__(self, cfg):
         super().__init__()
@@ -76,6 +77,7 @@ class MROAD(nn.Module):
         self.h0 = torch.zeros(self.num_layers, 1, self.hidden_dim)  # rnn.py:49 (not in state_dict)
 
         self.precision = cfg.get("precision", "fp16")
+        self.train_precision = cfg.get("train_precision", "fp32")
         self.chunk_frames = int(cfg.get("chunk_frames", 1 << 17))
         self._handle = None
         self._handle_device = None

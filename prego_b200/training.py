@@ -65,10 +65,12 @@ class MiniROADTrainFn(torch.autograd.Function):
             logits = torch.empty(B, T, module.out_dim, dtype=torch.float32, device=device)
             args = _lib.TrainArgs(rgb_c.data_ptr() if rgb_c is not None else None,
                                   flow_c.data_ptr() if flow_c is not None else None, B, T, logits.data_ptr(), None, None,
-                                  ws_ptr, need, float(module.layer1[3].p), int(seed))
+                                  ws_ptr, need, float(module.layer1[3].p), int(seed),
+                                  _lib.TRAIN_PRECISIONS[getattr(module, "train_precision", "fp32")])
             stream = torch.cuda.current_stream(device).cuda_stream
             _lib.check(lib.prego_train_forward(module._handle, C.byref(args), stream), "prego_train_forward")
         ctx.module, ctx.rgb, ctx.flow, ctx.seed = module, rgb_c, flow_c, int(seed)
+        ctx.prec = args.precision
         ctx.ws_ptr, ctx.need, ctx.B, ctx.T = ws_ptr, need, B, T
         ctx.shapes = [tuple(p.shape) for p in params]
         return logits
@@ -84,7 +86,8 @@ class MiniROADTrainFn(torch.autograd.Function):
             g = _lib.Grads(*[t.data_ptr() for t in grads])
             args = _lib.TrainArgs(ctx.rgb.data_ptr() if ctx.rgb is not None else None,
                                   ctx.flow.data_ptr() if ctx.flow is not None else None, ctx.B, ctx.T, None,
-                                  dlogits.data_ptr(), C.pointer(g), ctx.ws_ptr, ctx.need, float(module.layer1[3].p), ctx.seed)
+                                  dlogits.data_ptr(), C.pointer(g), ctx.ws_ptr, ctx.need, float(module.layer1[3].p), ctx.seed,
+                                  ctx.prec)
             stream = torch.cuda.current_stream(device).cuda_stream
             _lib.check(lib.prego_train_backward(module._handle, C.byref(args), stream), "prego_train_backward")
         return (None, None, None, None, *grads)
