@@ -66,6 +66,7 @@ SIGNATURES = {
     "prego_online_open": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_void_p)]),
     "prego_online_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prego_online_wait": (C.c_int, [C.c_void_p]),
     "prego_online_close": (C.c_int, [C.c_void_p]),
     "prego_online_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "prego_device_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),

@@ -53,6 +53,8 @@ struct OnlineFusedArgs {
     unsigned* sync;  // [2] zero before the first launch; the kernel re-arms them
     int* err_flag;
     long long* trace;  // optional [grid][16] SM-clock stamps of the phase boundaries (diagnostics; NULL = off)
+    unsigned* host_seq;  // optional host-mapped word: receives `seq` after the frame's outputs are visible system-wide
+    unsigned seq;
     int rows, Dr, Df, E, H, K;
     int64_t T, t0;  // output row of stream r is r * T + t0
     float eps;
@@ -503,6 +505,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
             }
         }
         if (lane == 0 && a.labels != nullptr) a.labels[go] = arg;
+    }
+    if (a.host_seq != nullptr) {  // completion doorbell for a host that polls instead of synchronizing the stream
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned*>(a.host_seq) = a.seq;
+        }
     }
     FUSED_STAMP(8);
 }

@@ -264,11 +264,22 @@ class OnlineSession:
             # reads them after a stream sync without a D2H copy on the per-frame critical path
             self.labels = (torch.zeros(self.B, 1, dtype=torch.int32).pin_memory() if host_labels
                            else torch.empty(self.B, 1, dtype=torch.int32, device=device))
+            self.labels_np = self.labels.numpy() if host_labels else None
             self.probs = torch.empty(self.B, 1, model.out_dim, dtype=torch.float32, device=device) if want_probs else None
             torch.cuda.current_stream(device).synchronize()  # weight packing done before the graph is built
             _lib.check(lib.prego_online_open(model._handle, self.B, _lib.PRECISIONS[prec_name], self.h.data_ptr(),
                                              self.probs.data_ptr() if want_probs else None, None, self.labels.data_ptr(),
                                              C.byref(self._session)), "prego_online_open")
+
+    def step_wait(self, rgb_frame, flow_frame):
+        """``step`` + host-side completion without a stream synchronize (``prego_online_wait``): returns once the
+        frame's labels are readable.  For ``host_labels`` sessions this is the whole per-frame round trip; the labels
+        are also exposed as the numpy view ``labels_np`` (no torch dispatch on the per-frame path)."""
+        self.step(rgb_frame, flow_frame)
+        rc = self._lib.prego_online_wait(self._session)
+        if rc:
+            _lib.check(rc, "prego_online_wait")
+        return self.labels
 
     def close(self):
         if self._session is not None and self._session.value:

@@ -471,9 +471,12 @@ def test_online_session_multi_stream_host_labels(dev, golden_meta, streams):
     n = rgb.shape[1]
     got = np.zeros((streams, n), dtype=np.int64)
     for t in range(n):
-        lab = sess.step(rgb[:, t].contiguous(), flow[:, t].contiguous())
-        torch.cuda.synchronize()
-        got[:, t] = lab.numpy()[:, 0]
+        if t % 2 == 0:  # alternate the two completion paths: pinned doorbell word / stream synchronize
+            sess.step_wait(rgb[:, t].contiguous(), flow[:, t].contiguous())
+        else:
+            sess.step(rgb[:, t].contiguous(), flow[:, t].contiguous())
+            torch.cuda.synchronize()
+        got[:, t] = sess.labels_np[:, 0]
         assert (sess.probs.sum(-1) - 1).abs().max().item() < 1e-5
     ref_logits = gold["logits"][:streams, :n]
     ref = ref_logits.argmax(-1)
