@@ -478,12 +478,12 @@ def run_ours(args, world, rank, local):
         "recurrence": FLOP_REC * Mc * K / (prof["recurrence"]["ms"] * 1e-3) / 1e12,
     }
     stage_gbs = (BYTES_FEATURES + 8192) * Mc * K / (prof["stage"]["ms"] * 1e-3) / 1e9
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<256,4,...> (Linear 4096->2048, tcgen05 kind::f16)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel<256,6,...> (Linear 4096->2048, tcgen05 cta_group::2 kind::f16)",
                 "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops_sustained"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` capture
-                # (profiles/r01_ncu_bench_shape.txt): 3.341 GB + 1.060 GB per launch vs 3.238 GB algorithmic
-                "traffic": 4.400951e9 if (B, Tc, args.precision) == (4096, 64, "fp16") and min(Tc, args.subchunk) == 64 else None,
+                # (profiles/r01_ncu_session2.txt): 3.462 GB + 1.062 GB per launch vs 3.238 GB algorithmic
+                "traffic": 4.523928e9 if (B, Tc, args.precision) == (4096, 64, "fp16") and min(Tc, args.subchunk) == 64 else None,
                 "traffic_note": "ncu capture at chunk 64; with internal_subchunk 32 a launch moves half of it",
                 "algorithmic_bytes_per_launch": (8192 + 4096) * rows_per_launch + 4096 * 2048 * 2,
                 "tensor_pipe_active_pct_ncu": 99.6,

@@ -153,6 +153,7 @@ struct prego_model {
     float *wc_f32 = nullptr, *bc = nullptr;
     float* wct_f32 = nullptr;         // classifier transposed [H, K] (per-frame kernel)
     float* online_scratch = nullptr;  // y | LayerNorm partials | logit partials | counters of the per-frame kernel
+    uint4* online_stream[2] = {nullptr, nullptr};  // weights in the per-frame kernel's load order ([0] fp16, [1] bf16)
     // 16-bit operands of the tcgen05 path, [0] = fp16, [1] = bf16
     void *w1_16[2] = {nullptr, nullptr}, *wih_16p[2] = {nullptr, nullptr}, *whh_16p[2] = {nullptr, nullptr},
          *wc_16p[2] = {nullptr, nullptr};
@@ -621,7 +622,7 @@ int online_step_fused(prego_model* m, const prego_forward_args_t* a, float* h, i
     const prego_dims_t& d = m->d;
     OnlineFusedArgs fa{};
     fa.rgb = static_cast<const float*>(a->rgb); fa.flow = static_cast<const float*>(a->flow);
-    fa.w1 = m->w1_16[fmt]; fa.wih = m->wih_16p[fmt]; fa.whh = m->whh_16p[fmt];
+    fa.wstream = m->online_stream[fmt];
     fa.b1 = m->b1; fa.ln_g = m->ln_g; fa.ln_b = m->ln_b; fa.bih = m->bih_p; fa.bhh = m->bhh_p; fa.wct = m->wct_f32; fa.bc = m->bc;
     online_fused_carve(m->online_scratch, d.embed_dim, d.num_classes, &fa);
     fa.h = h; fa.probs = a->probs; fa.logits = a->logits; fa.labels = a->labels; fa.err_flag = m->err_flag; fa.trace = nullptr; fa.host_seq = nullptr; fa.seq = 0;
@@ -709,6 +710,10 @@ int pack16(prego_model* m, const prego_weights_t* w, cudaStream_t s) {
     pack_rows_16<FMT><<<g((int64_t)3 * H * H), T, 0, s>>>(w->gru_weight_hh_l0, reinterpret_cast<OpT*>(m->whh_16p[FMT]), 3 * H, 3 * H, H, H, 1);
     if (m->kpad)
         pack_rows_16<FMT><<<g((int64_t)m->kpad * H), T, 0, s>>>(w->f_classification_0_weight, reinterpret_cast<OpT*>(m->wc_16p[FMT]), m->kpad, K, H, H, 0);
+    if (m->online_stream[FMT] != nullptr)
+        online_pack_stream<FMT><<<g((int64_t)m->sm_count * kFusedWarps * online_stream_loads(din / 1024) * 32), T, 0, s>>>(
+            reinterpret_cast<const OpT*>(m->w1_16[FMT]), reinterpret_cast<const OpT*>(m->wih_16p[FMT]), reinterpret_cast<const OpT*>(m->whh_16p[FMT]),
+            m->online_stream[FMT], m->sm_count, din, E, H);
     LAUNCH_CHECK("16-bit weight packing");
     return PREGO_OK;
 }
@@ -764,6 +769,7 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
     m->kpad = d.num_classes <= 96 ? 96 : (d.num_classes <= 128 ? 128 : 0);
     const int64_t H = d.hidden_dim, E = d.embed_dim, K = d.num_classes;
 #define ALLOC(ptr, bytes) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes)))
+#define ALLOC2(ptr, bytes) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes)))
     ALLOC(m->w1_f32, E * din * 4); ALLOC(m->b1, E * 4); ALLOC(m->ln_g, E * 4); ALLOC(m->ln_b, E * 4);
     ALLOC(m->wih_f32p, 3 * H * E * 4); ALLOC(m->whh_f32p, 3 * H * H * 4); ALLOC(m->bih_p, 3 * H * 4); ALLOC(m->bhh_p, 3 * H * 4); ALLOC(m->bgi_p, 3 * H * 4);
     ALLOC(m->wc_f32, K * H * 4); ALLOC(m->bc, K * 4);
@@ -775,6 +781,8 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
     ALLOC(m->online_scratch, online_fused_scratch_floats((int)E, (int)K) * 4);
 #undef ALLOC
     CUDA_TRY(cudaMemset(m->online_scratch, 0, online_fused_scratch_floats((int)E, (int)K) * 4));
+    if (online_fused_ok(m))
+        for (int f = 0; f < 2; ++f) ALLOC2(m->online_stream[f], (size_t)m->sm_count * kFusedWarps * online_stream_loads(din / 1024) * 512);
     CUDA_TRY(cudaMemset(m->xchg, 0, 2 * 4 * H * sizeof(uint2)));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->xchg_bwd), 2 * 4 * H * sizeof(uint4)));
     CUDA_TRY(cudaMemset(m->xchg_bwd, 0, 2 * 4 * H * sizeof(uint4)));
@@ -794,7 +802,7 @@ int prego_model_destroy(prego_model_t* m) {
     cudaSetDevice(m->device);
     void* ptrs[] = {m->w1_f32, m->b1, m->ln_g, m->ln_b, m->wih_f32p, m->whh_f32p, m->bih_p, m->bhh_p, m->bgi_p, m->wc_f32, m->bc,
                     m->w1_16[0], m->w1_16[1], m->wih_16p[0], m->wih_16p[1], m->whh_16p[0], m->whh_16p[1], m->wc_16p[0],
-                    m->wc_16p[1], m->xchg, m->xchg_bwd, m->err_flag, m->wct_f32, m->online_scratch};
+                    m->wc_16p[1], m->xchg, m->xchg_bwd, m->err_flag, m->wct_f32, m->online_scratch, m->online_stream[0], m->online_stream[1]};
     for (void* p : ptrs)
         if (p != nullptr) cudaFree(p);
     for (cudaEvent_t e : m->prof_ev)

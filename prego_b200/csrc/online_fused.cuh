@@ -38,9 +38,8 @@ constexpr uint32_t kFusedSpinMax = 1u << 22;  // bounded spins: a lost CTA raise
 struct OnlineFusedArgs {
     const float* rgb;
     const float* flow;
-    const void* w1;   // [E, D] 16-bit
-    const void* wih;  // [3H, E] 16-bit, gate-interleaved rows (packed row = (u/64)*192 + gate*64 + u%64)
-    const void* whh;  // [3H, H] 16-bit, same row order
+    const uint4* wstream;  // the three 16-bit weight matrices re-ordered into per-CTA, per-warp, per-load 512-byte
+                           // blocks (online_pack_stream): every warp-level 16-byte load reads 4 full cache lines
     const float *b1, *ln_g, *ln_b, *bih, *bhh;  // bih / bhh in packed row order
     const float *wct, *bc;                       // fp32 classifier, transposed [H, K]
     float* y;       // [8, E] scratch
@@ -70,21 +69,48 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
                      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// 32 bytes of one weight row (two independent 16-byte loads; zeros when the row is not this lane's to fetch)
+// 32 bytes of one weight row = two consecutive 16-byte loads of this lane from the packed stream
 struct W32 {
     uint4 lo, hi;
 };
-__device__ __forceinline__ W32 ldw32(const void* base, int64_t elem_off, bool valid) {
+__device__ __forceinline__ W32 ldw32(const uint4* ws, int i) {  // ws: this lane's slot of load 0; loads are 32 slots apart
     W32 w;
-    if (valid) {
-        const uint4* p = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(base) + elem_off);
-        w.lo = __ldg(p);
-        w.hi = __ldg(p + 1);
-    } else {
-        w.lo = make_uint4(0u, 0u, 0u, 0u);
-        w.hi = w.lo;
-    }
+    w.lo = __ldg(ws + i * 32);
+    w.hi = __ldg(ws + (i + 1) * 32);
     return w;
+}
+
+// Load order of one warp (index i of its 512-byte blocks), C1 = D / 1024:
+//   [0, 6)            W_hh' rows of (unit u0 + g, gate i / 2), k = warp * 64 + 16 t + 8 (i % 2) ..
+//   [6, 6 + 4 C1)     W1: chunk c = (i - 6) / 4, row n0 + g (+ 8 for (i - 6) % 4 >= 2), k = (warp * C1 + c) * 64 + 16 t + 8 (i % 2) ..
+//   [.., + 12)        W_ih': chunk c = j / 6, gate (j % 6) / 2, k = (warp * 2 + c) * 64 + 16 t + 8 (j % 2) ..
+// Rows a CTA does not own are zero blocks, so the kernel needs no predicates.
+__host__ __device__ constexpr int online_stream_loads(int C1) { return 6 + 4 * C1 + 12; }
+
+template <int FMT>
+__global__ void online_pack_stream(const typename Op16<FMT>::T* __restrict__ w1, const typename Op16<FMT>::T* __restrict__ wih,
+                                   const typename Op16<FMT>::T* __restrict__ whh, uint4* __restrict__ out, int G, int D, int E, int H) {
+    const int C1 = D / 1024, NI = online_stream_loads(C1);
+    const int upc = (H + G - 1) / G, rpc = (E + G - 1) / G;
+    const int64_t total = static_cast<int64_t>(G) * kFusedWarps * NI * 32;
+    for (int64_t s = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; s < total; s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int lane = static_cast<int>(s % 32), i = static_cast<int>((s / 32) % NI);
+        const int warp = static_cast<int>((s / (32 * NI)) % kFusedWarps), cta = static_cast<int>(s / (32 * NI * kFusedWarps));
+        const int g = lane >> 2, t = lane & 3, half = i & 1;
+        const int u0 = cta * upc, n0 = cta * rpc;
+        const int nu = min(upc, max(H - u0, 0)), nr = min(rpc, max(E - n0, 0));
+        const typename Op16<FMT>::T* src = nullptr;
+        if (i < 6) {
+            if (g < nu) src = whh + static_cast<int64_t>(((u0 + g) >> 6) * 192 + (i / 2) * 64 + ((u0 + g) & 63)) * H + warp * 64 + t * 16 + half * 8;
+        } else if (i < 6 + 4 * C1) {
+            const int j = i - 6, c = j / 4, row = g + ((j % 4) >= 2 ? 8 : 0);
+            if (row < nr) src = w1 + static_cast<int64_t>(n0 + row) * D + (warp * C1 + c) * 64 + t * 16 + half * 8;
+        } else {
+            const int j = i - 6 - 4 * C1, c = j / 6, gt = (j % 6) / 2;
+            if (g < nu) src = wih + static_cast<int64_t>(((u0 + g) >> 6) * 192 + gt * 64 + ((u0 + g) & 63)) * E + (warp * 2 + c) * 64 + t * 16 + half * 8;
+        }
+        out[s] = src != nullptr ? *reinterpret_cast<const uint4*>(src) : make_uint4(0u, 0u, 0u, 0u);
+    }
 }
 
 // one 64-wide K chunk: rows (ra | rb) x the activation fragment xa (32 bytes of this lane's stream row)
@@ -190,21 +216,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
     }
 
     // ---- weight requests of phase A (nothing they depend on): W_hh' rows of (u, r|z|n), first half of the W1 chunks
+    const uint4* ws = a.wstream + (static_cast<int64_t>(cta) * kFusedWarps + warp) * online_stream_loads(C1) * 32 + lane;
     W32 wh[CH][3];
 #pragma unroll
     for (int c = 0; c < CH; ++c)
 #pragma unroll
         for (int gt = 0; gt < 3; ++gt)
-            wh[c][gt] = ldw32(a.whh, static_cast<int64_t>(packed_row(uval ? u : 0, gt)) * H + (warp * CH + c) * 64 + t * 16, uval);
-    const bool v1a = g < nr, v1b = g + 8 < nr;
-    const int64_t r1a = static_cast<int64_t>(n0 + (v1a ? g : 0)) * D, r1b = static_cast<int64_t>(n0 + (v1b ? g + 8 : 0)) * D;
+            wh[c][gt] = ldw32(ws, 2 * gt);
     constexpr int C1A = C1 / 2;
     W32 w1a[C1A], w1b[C1A];
 #pragma unroll
     for (int c = 0; c < C1A; ++c) {
-        const int k = (warp * C1 + c) * 64 + t * 16;
-        w1a[c] = ldw32(a.w1, r1a + k, v1a);
-        w1b[c] = ldw32(a.w1, r1b + k, v1b);
+        w1a[c] = ldw32(ws, 6 + 4 * c);
+        w1b[c] = ldw32(ws, 6 + 4 * c + 2);
     }
 
     // ---- activations -> 16-bit smem rows (warp-private slices: __syncwarp only)
@@ -249,14 +273,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
         mma_chunk<FMT>(crz, wh[c][0], wh[c][1], x);
         mma_chunk<FMT>(cn, wh[c][2], zero, x);
     }
-    // second half of the W1 chunks goes out while the first half is consumed (registers are the landing zone; the
-    // L2 -> SM path is the limit anyway: ~47 GB/s per SM with all SMs streaming, measured)
+    // second half of the W1 chunks goes out while the first half is consumed (requesting it at t = 0 as well was slower:
+    // the x / h slices then queue behind 50 % more weight bytes on the L2 -> SM path)
     W32 w1c[C1 - C1A], w1d[C1 - C1A];
 #pragma unroll
     for (int c = C1A; c < C1; ++c) {
-        const int k = (warp * C1 + c) * 64 + t * 16;
-        w1c[c - C1A] = ldw32(a.w1, r1a + k, v1a);
-        w1d[c - C1A] = ldw32(a.w1, r1b + k, v1b);
+        w1c[c - C1A] = ldw32(ws, 6 + 4 * c);
+        w1d[c - C1A] = ldw32(ws, 6 + 4 * c + 2);
     }
 #pragma unroll
     for (int c = 0; c < C1A; ++c) {
@@ -269,7 +292,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
     for (int c = 0; c < C2; ++c)
 #pragma unroll
         for (int gt = 0; gt < 3; ++gt)
-            wi[c][gt] = ldw32(a.wih, static_cast<int64_t>(packed_row(uval ? u : 0, gt)) * E + (warp * C2 + c) * 64 + t * 16, uval);
+            wi[c][gt] = ldw32(ws, 6 + 4 * C1 + 6 * c + 2 * gt);
 #pragma unroll
     for (int c = C1A; c < C1; ++c) {
         const W32 x = lds_act(xs + g * XS, (warp * C1 + c) * 64 + t * 16, sval);
