@@ -528,3 +528,27 @@ def test_zero_flow_elision_bit_identical(dev, prec, feat16, B, T):
     torch.cuda.synchronize()
     assert torch.equal(a["logits"], b["logits"])
     assert torch.equal(a["labels"], b["labels"])
+
+
+@pytest.mark.parametrize("zero_flow", [True, False])
+def test_streamed_ingest_matches_per_video_path(dev, zero_flow):
+    """prego_b200.ingest: ragged videos converted once to fp16 (zero flow dropped), bucketed, streamed through pinned
+    staging -> labels identical to running each video alone on fp32 features (same operand rounding, causal GRU)."""
+    from prego_b200 import ingest, synthetic
+    cfg = dict(synthetic.EPIC_TENT_O)
+    model = synthetic.seeded_model(cfg, seed=20, device=dev)
+    lens = [37, 5, 130, 64, 129, 1, 77]
+    items, ref = [], {}
+    for i, T in enumerate(lens):
+        rgb, flow = synthetic.features(50 + i, T, "cpu", zero_flow)
+        items.append((f"v{i}", rgb.numpy().astype(np.float64), flow.numpy(), synthetic.targets(50 + i, T, 12).numpy()))
+        ref[f"v{i}"] = model.infer(rgb[None].to(dev), flow[None].to(dev), want_probs=False, precision="fp16")["labels"][0].cpu()
+    store = ingest.FeatureStore.from_arrays(items, "fp16")
+    assert store.zero_flow == zero_flow and store.frames == sum(lens)
+    got = ingest.predict_labels_streamed(model, store, dev, batch_streams=3)
+    torch.cuda.synchronize()
+    assert list(got) == [f"v{i}" for i in range(len(lens))]
+    for k, v in got.items():
+        assert torch.equal(v.cpu(), ref[k]), k
+    with pytest.raises(RuntimeError):
+        ingest.predict_labels_streamed(model, store, dev, precision="bf16")

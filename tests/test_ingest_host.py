@@ -1,0 +1,83 @@
+"""Host side of the feature ingest (prego_b200/ingest.py): conversion rules, the reference's
+on-disk layout and zero-flow rule (datasets/dataset.py:45-95), length bucketing.  No GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from prego_b200 import ingest
+
+
+def test_to_operand_matches_device_rounding_rules():
+    x = np.array([0.1, -2.5, 70000.0, -1e9, 3.0e-8, 1.0009765625], dtype=np.float64)
+    h = ingest.to_operand(x, torch.float16)
+    assert h.dtype == torch.float16 and h.is_contiguous()
+    assert float(h[2]) == 65504.0 and float(h[3]) == -65504.0          # saturating, like Op16<0>::pack2
+    assert torch.equal(h[:2], torch.tensor([0.1, -2.5], dtype=torch.float32).half())
+    b = ingest.to_operand(x, torch.bfloat16)
+    assert b.dtype == torch.bfloat16 and torch.isfinite(b.float()).all()
+    assert torch.equal(b, torch.from_numpy(x).float().bfloat16())
+    f = ingest.to_operand(x, torch.float32)
+    assert f.dtype == torch.float32
+
+
+def test_bucket_order_longest_first_and_complete():
+    lens = [5, 900, 17, 900, 33, 1, 64]
+    b = ingest.bucket_order(lens, 3)
+    assert [len(x) for x in b] == [3, 3, 1]
+    flat = [i for x in b for i in x]
+    assert sorted(flat) == list(range(len(lens)))
+    assert [lens[i] for i in flat] == sorted(lens, reverse=True)
+    assert b[0][:2] == [1, 3]  # ties keep input order
+
+
+def _write_layout(root, cfg, vids, rng, flow_dir=False):
+    os.makedirs(os.path.join(root, cfg["rgb_type"]), exist_ok=True)
+    os.makedirs(os.path.join(root, cfg["annotation_type"]), exist_ok=True)
+    data = {}
+    for v, T in vids:
+        rgb = np.abs(rng.standard_normal((T, 2048)))          # float64 on disk, as the reference's extractor wrote them
+        tgt = np.eye(cfg["num_classes"])[rng.integers(0, cfg["num_classes"], T)]
+        np.save(os.path.join(root, cfg["rgb_type"], v + ".npy"), rgb)
+        np.save(os.path.join(root, cfg["annotation_type"], v + ".npy"), tgt)
+        if flow_dir:
+            d = os.path.join(root, cfg["flow_type"], "assembly_optical_flow_BNInception", v)
+            os.makedirs(d, exist_ok=True)
+            np.save(os.path.join(d, "assembling.npy"), np.abs(rng.standard_normal((T, 2048))))
+        data[v] = (rgb, tgt)
+    lst = os.path.join(root, "list.json")
+    json.dump({cfg["data_name"]: {"test_session_set": [v for v, _ in vids] + ["missing_video"]}}, open(lst, "w"))
+    cfg["root_path"], cfg["video_list_path"] = root, lst
+    return data
+
+
+def test_reference_layout_zero_flow_rule(tmp_path):
+    cfg = dict(data_name="ASSEMBLY101-O", rgb_type="rgb_anet_resnet50", flow_type="flow_anet_resnet50", annotation_type="target_perframe",
+               num_classes=7)
+    data = _write_layout(str(tmp_path), cfg, [("a", 11), ("b", 40)], np.random.default_rng(0))
+    store = ingest.FeatureStore.from_reference_layout(cfg, "fp16", pin=False)
+    assert len(store) == 2 and store.zero_flow                  # the unreadable video is skipped, the dummy flow is not stored
+    assert store.frames == 51 and store.host_bytes_per_frame() == 4096.0
+    for v in store.videos:
+        rgb, tgt = data[v.vid]
+        assert v.rgb.dtype == torch.float16 and tuple(v.rgb.shape) == rgb.shape and v.flow is None
+        assert torch.equal(v.rgb, torch.from_numpy(rgb).float().half())
+        assert np.array_equal(v.gt, tgt.argmax(1))
+
+
+def test_reference_layout_real_flow_and_mixed_store(tmp_path):
+    cfg = dict(data_name="X", rgb_type="rgb_anet_resnet50", flow_type="flow_kinetics_bninception", annotation_type="target_perframe", num_classes=5)
+    _write_layout(str(tmp_path), cfg, [("a", 9)], np.random.default_rng(1), flow_dir=True)
+    store = ingest.FeatureStore.from_reference_layout(cfg, "bf16", pin=False)
+    assert not store.zero_flow and store.videos[0].flow.dtype == torch.bfloat16 and store.host_bytes_per_frame() == 8192.0
+    z = ingest.FeatureStore.from_arrays([("z", np.ones((4, 2048)), np.zeros((4, 2048)), None), ("r", np.ones((3, 2048)), np.ones((3, 2048)), None)],
+                                        "fp16", pin=False)
+    assert z.videos[0].flow is None and z.videos[1].flow is not None and not z.zero_flow
+
+
+def test_streaming_needs_cuda():
+    store = ingest.FeatureStore.from_arrays([("a", np.ones((4, 2048)), None, None)], "fp16", pin=False)
+    with pytest.raises(RuntimeError):
+        next(ingest.stream_batches(store, "cpu"))
