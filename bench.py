@@ -249,7 +249,8 @@ def training_leg(dev, world):
     cfg = dict(synthetic.ASSEMBLY101_O)
     model = synthetic.seeded_model(cfg, seed=20, device=dev)
     crit = OadLoss(cfg)
-    opt = torch.optim.AdamW([{"params": model.parameters(), "initial_lr": 1e-4}], lr=1e-4, weight_decay=0.05)
+    from prego_b200 import build_optimizer
+    opt = build_optimizer({"optimizer": "AdamW", "lr": 1e-4, "weight_decay": 0.05}, model)  # one-launch fused AdamW
     out = {}
     for prec in ("fp32", "tf32"):
         model.train_precision = prec
@@ -275,7 +276,7 @@ def training_leg(dev, world):
             out[f"B{B}_T{T}" + ("" if prec == "fp32" else "_tf32")] = {"ms_per_step": float(ms), "frames_per_s": world * B * T / float(ms) * 1e3,
                                                                        "loss": float(loss)}
             del rgb, flow, target
-    out["note"] = ("fwd + BPTT + torch AdamW, dropout 0.2, flow = 0; recurrence (forward and BPTT) on the persistent exact-fp32 kernels "
+    out["note"] = ("fwd + BPTT + fused AdamW (one launch), dropout 0.2, flow = 0; recurrence (forward and BPTT) on the persistent exact-fp32 kernels "
                    "for B <= 64; plain keys: every GEMM exact fp32 on CUDA cores (parity mode); *_tf32: large projections and their "
                    "gradients on tcgen05 kind::tf32; grads all-reduced (NCCL) when n_gpus > 1")
     return out

@@ -217,6 +217,24 @@ int prego_gemm_tf32_nt(const float* A, const float* W, const float* bias, float*
 int prego_gemm_f32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
                       void* stream);
 
+/* ---- Fused AdamW over a list of fp32 tensors (one launch for all of them): the optimizer step of main.py:62-67
+ * (torch.optim.AdamW, amsgrad = False, maximize = False), same update order as torch's single-tensor rule:
+ *   p *= 1 - lr * wd;  m = lerp(m, g, 1 - b1);  v = b2 * v + (1 - b2) * g * g;
+ *   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+ * grad_scale multiplies every gradient first (1 / world_size after a sum all-reduce; 1 otherwise). */
+#define PREGO_ADAMW_MAX_TENSORS 16
+typedef struct prego_adamw_args {
+    float* params[PREGO_ADAMW_MAX_TENSORS];
+    const float* grads[PREGO_ADAMW_MAX_TENSORS];
+    float* exp_avg[PREGO_ADAMW_MAX_TENSORS];
+    float* exp_avg_sq[PREGO_ADAMW_MAX_TENSORS];
+    int64_t numel[PREGO_ADAMW_MAX_TENSORS];
+    int32_t num_tensors;
+    int32_t step;            /* t >= 1, after the increment */
+    float lr, beta1, beta2, eps, weight_decay, grad_scale;
+} prego_adamw_args_t;
+int prego_adamw_step(const prego_adamw_args_t* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

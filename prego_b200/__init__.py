@@ -9,6 +9,8 @@ from .model import MROAD, FEATURE_SIZES  # noqa: F401
 from .aggregate import aggregate, aggregate_labels  # noqa: F401
 from .evaluate import Evaluate  # noqa: F401
 from .pipeline import predict_labels, recognize_and_aggregate  # noqa: F401
-from .training import OadLoss, build_criterion, train_one_step, allreduce_gradients  # noqa: F401
+from .training import (OadLoss, build_criterion, train_one_step, allreduce_gradients, FusedAdamW, TRAINER, train_one_epoch,  # noqa: F401
+                       build_trainer, build_optimizer, WindowDataset)
+from . import ingest  # noqa: F401
 
 __version__ = "0.1.0"

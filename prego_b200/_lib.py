@@ -54,6 +54,17 @@ class TrainArgs(C.Structure):
                 ("seed", C.c_uint64), ("precision", C.c_int32), ("reserved", C.c_int32)]
 
 
+ADAMW_MAX_TENSORS = 16
+
+
+class AdamWArgs(C.Structure):
+    _fields_ = [("params", C.c_void_p * ADAMW_MAX_TENSORS), ("grads", C.c_void_p * ADAMW_MAX_TENSORS),
+                ("exp_avg", C.c_void_p * ADAMW_MAX_TENSORS), ("exp_avg_sq", C.c_void_p * ADAMW_MAX_TENSORS),
+                ("numel", C.c_int64 * ADAMW_MAX_TENSORS), ("num_tensors", C.c_int32), ("step", C.c_int32),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("grad_scale", C.c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/prego_b200.h declares
 SIGNATURES = {
     "prego_abi_version": (C.c_int, []),
@@ -73,6 +84,7 @@ SIGNATURES = {
     "prego_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64]),
     "prego_train_forward": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
     "prego_train_backward": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
+    "prego_adamw_step": (C.c_int, [C.POINTER(AdamWArgs), C.c_void_p]),
     "prego_profile_begin": (C.c_int, [C.c_void_p]),
     "prego_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "prego_window_mode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,

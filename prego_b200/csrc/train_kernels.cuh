@@ -386,6 +386,37 @@ transpose_tiled_f32(const float* __restrict__ src, int64_t lds, float* __restric
     }
 }
 
+// Fused AdamW over up to 16 tensors in one launch (main.py:62-67; torch.optim.AdamW's single-tensor update order).
+struct AdamWTensors {
+    float* p[16];
+    const float* g[16];
+    float* m[16];
+    float* v[16];
+    int64_t start[17];  // prefix sums of numel (float4-granular work split uses the flat index)
+    int n;
+};
+__global__ void __launch_bounds__(256)
+adamw_fused(AdamWTensors t, float lr, float beta1, float beta2, float eps, float wd, float grad_scale, float bc1, float bc2_sqrt) {
+    const int64_t total = t.start[t.n];
+    const float step_size = lr / bc1, decay = 1.0f - lr * wd;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < 16; ++j) k += (j < t.n && i >= t.start[j]) ? 1 : 0;
+        const int64_t o = i - t.start[k];
+        const float g = t.g[k][o] * grad_scale;
+        float p = t.p[k][o] * decay;
+        float m = t.m[k][o];
+        m = m + (1.0f - beta1) * (g - m);                     // lerp_(grad, 1 - beta1)
+        const float v = beta2 * t.v[k][o] + (1.0f - beta2) * g * g;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        p = p - step_size * (m / denom);
+        t.p[k][o] = p;
+        t.m[k][o] = m;
+        t.v[k][o] = v;
+    }
+}
+
 // time-major [T, B, K] -> caller's [B, T, K] (logits out) and back (dlogits in).
 __global__ void transpose_tb_f32(const float* __restrict__ src, float* __restrict__ dst, int B, int T, int K, int to_bt) {
     const int64_t total = static_cast<int64_t>(B) * T * K;

@@ -1,6 +1,7 @@
-"""`main.py --eval` compatible entry point (reference: ``step_recognition/main.py:15-57``).
+"""`main.py` compatible entry point (reference: ``step_recognition/main.py:15-115``).
 
     python -m prego_b200.main --config <yaml> --eval <ckpt.pth> [--no_rgb] [--no_flow] [--synthetic N]
+    python -m prego_b200.main --config <yaml> [--amp] [--synthetic N]          # training (main.py:59-115)
 
 Same flow as the reference's eval branch -- flat YAML merged with argparse (main.py:28-30),
 ``set_seed(20)`` (main.py:32), ``build_model`` -> ``load_state_dict`` (main.py:44-48), ``build_eval`` ->
@@ -8,7 +9,11 @@ Same flow as the reference's eval branch -- flat YAML merged with argparse (main
 ``output_miniRoad/output_miniROAD.json`` -- without the reference's landmines (hard-coded ``cuda:1``,
 ``ipdb`` breakpoints).  ``--synthetic N`` replaces the ``.npy`` feature files by N seeded
 synthetic videos (no dataset ships with the repo); ``--eval synthetic`` keeps the seeded default weights.
-Training (main.py:59-115) is not part of this entry point.
+Without ``--eval`` the reference's training loop runs (main.py:59-115): sliding-window train loader
+(dataset.py:96-135), ``OadLoss``, AdamW (fused), ``train_one_epoch`` + evaluation every epoch, ``best.pth`` kept and
+renamed to ``best_<mAP>.pth`` at the end.  ``--amp`` selects ``train_precision = 'tf32'`` (this implementation's
+reduced-precision training mode); ``--tensorboard`` / ``--lr_scheduler`` are accepted for CLI compatibility
+(the reference's scheduler path raises KeyError on both shipped configs).
 """
 from __future__ import annotations
 
@@ -98,12 +103,17 @@ def main(argv=None):
     parser.add_argument("--synthetic", type=int, default=0, help="evaluate on N synthetic videos instead of .npy features")
     parser.add_argument("--device", type=str, default="cuda:0")
     parser.add_argument("--precision", type=str, default=None, choices=["fp16", "bf16", "fp32"])
+    parser.add_argument("--amp", action="store_true")
+    parser.add_argument("--tensorboard", action="store_true")
+    parser.add_argument("--lr_scheduler", action="store_true")
+    parser.add_argument("--num_epoch", type=int, default=None)
+    parser.add_argument("--output_path", type=str, default=None)
     args = parser.parse_args(argv)
 
     cfg = yaml.load(open(args.config), Loader=yaml.FullLoader)
-    cfg.update({k: v for k, v in vars(args).items() if k not in ("precision",) or v is not None})
-    if args.eval is None:
-        parser.error("this entry point implements the --eval branch (main.py:47-57); training is not built yet")
+    cfg.update({k: v for k, v in vars(args).items() if k not in ("precision", "num_epoch", "output_path") or v is not None})
+    if args.amp:
+        cfg["train_precision"] = "tf32"
     set_seed(20)
     device = torch.device(args.device)
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(message)s")
@@ -115,11 +125,71 @@ def main(argv=None):
                                              num_workers=0, pin_memory=True)
     model = build_model(cfg, device)
     evaluate = build_eval(cfg)
-    if args.eval != "synthetic":
-        model.load_state_dict(torch.load(args.eval, map_location=device))
-    mAP = evaluate(model, testloader, logger, device)
-    logger.info(f'{cfg["task"]} result: {mAP * 100:.2f} m{cfg["metric"]}')
-    return mAP
+    if args.eval is not None:
+        if args.eval != "synthetic":
+            model.load_state_dict(torch.load(args.eval, map_location=device))
+        mAP = evaluate(model, testloader, logger, device)
+        logger.info(f'{cfg["task"]} result: {mAP * 100:.2f} m{cfg["metric"]}')
+        return mAP
+    return train(cfg, args, model, evaluate, testloader, dataset, logger, device)
+
+
+def _train_videos(cfg, args, test_dataset):
+    """{vid: (rgb, flow | None, target)} of the TRAIN split (synthetic: a second set of seeded videos)."""
+    if args.synthetic > 0:
+        zero_flow = cfg["flow_type"] == "flow_anet_resnet50"
+        out = {}
+        for i in range(args.synthetic):
+            T = 256 + 64 * (i % 3)
+            rgb, flow = synthetic.features(10_000 + i, T, "cpu", zero_flow, FEATURE_SIZES[cfg["rgb_type"]], FEATURE_SIZES[cfg["flow_type"]])
+            out[f"train_synthetic_{i}"] = (rgb, None if zero_flow else flow, synthetic.targets(10_000 + i, T, cfg["num_classes"]))
+        return out
+    vids = json.load(open(cfg["video_list_path"]))[cfg["data_name"]]["train_session_set"]
+    root, out = cfg["root_path"], {}
+    for vid in vids:
+        try:
+            target = np.load(osp.join(root, cfg["annotation_type"], vid + ".npy"))
+            rgb = np.load(osp.join(root, cfg["rgb_type"], vid + ".npy"))
+            flow = None if cfg["flow_type"] == "flow_anet_resnet50" else np.load(
+                osp.join(root, cfg["flow_type"], "assembly_optical_flow_BNInception", vid, "assembling.npy"))
+            out[vid] = (rgb, flow, target)
+        except Exception as e:
+            print("---- Exception in loading video ", e)
+    return out
+
+
+def train(cfg, args, model, evaluate, testloader, test_dataset, logger, device):
+    """main.py:59-115."""
+    from .training import WindowDataset, build_criterion, build_optimizer, build_trainer
+
+    result_path = cfg.get("output_path") or "checkpoint_miniROAD"
+    os.makedirs(osp.join(result_path, "ckpts"), exist_ok=True)
+    train_set = WindowDataset(_train_videos(cfg, args, test_dataset), cfg["window_size"], cfg["stride"], FEATURE_SIZES[cfg["flow_type"]])
+    trainloader = torch.utils.data.DataLoader(train_set, batch_size=cfg["batch_size"], shuffle=True, num_workers=0, pin_memory=True,
+                                              drop_last=False)
+    criterion = build_criterion(cfg, device)
+    train_one_epoch = build_trainer(cfg)
+    optimizer = build_optimizer(cfg, model)
+    total_params = sum(p.numel() for p in model.parameters())
+    logger.info(f'Dataset: {cfg["data_name"]},  Model: {cfg["model"]}')
+    logger.info(f'lr:{cfg["lr"]} | Weight Decay:{cfg["weight_decay"]} | Window Size:{cfg["window_size"]} | Batch Size:{cfg["batch_size"]}')
+    logger.info(f'Total epoch:{cfg["num_epoch"]} | Total Params:{total_params / 1e6:.1f} M | Optimizer: {cfg["optimizer"]}')
+    logger.info(f"Output Path:{result_path}")
+    best_mAP, best_epoch = 0, 0
+    for epoch in range(1, cfg["num_epoch"] + 1):
+        epoch_loss = train_one_epoch(trainloader, model, criterion, optimizer, None, epoch, device, None, scheduler=None)
+        trainloader.dataset._init_features()
+        mAP = evaluate(model, testloader, logger, device)
+        print("Current mAP:", mAP)
+        if mAP > best_mAP or epoch == 1:
+            best_mAP, best_epoch = mAP, epoch
+            torch.save(model.state_dict(), osp.join(result_path, "ckpts", "best.pth"))
+            logger.info(f'Epoch {epoch} mAP: {mAP * 100:.2f} | Best mAP: {best_mAP * 100:.2f} at epoch {best_epoch}, '
+                        f'iter {epoch * cfg["batch_size"] * len(trainloader)} | train_loss: {epoch_loss / max(len(trainloader), 1):.4f}, '
+                        f'lr: {optimizer.param_groups[0]["lr"]:.7f}')
+    final = osp.join(result_path, "ckpts", f"best_{best_mAP * 100:.2f}.pth")
+    os.replace(osp.join(result_path, "ckpts", "best.pth"), final)
+    return best_mAP
 
 
 if __name__ == "__main__":

@@ -120,6 +120,108 @@ def allreduce_gradients(module, group=None):
         off += n
 
 
+class FusedAdamW(torch.optim.Optimizer):
+    """``torch.optim.AdamW`` (amsgrad = False) with the whole step -- decoupled weight decay, moment updates, bias
+    correction, parameter update of every tensor -- in ONE kernel launch through ``prego_adamw_step`` (the reference
+    builds ``torch.optim.AdamW(lr=1e-4, weight_decay=0.05)``, main.py:62-67).  ``grad_scale`` multiplies the gradients on
+    the fly (1 / world_size after a SUM all-reduce).  CUDA fp32 parameters only; no CPU path."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.grad is not None]
+            for s0 in range(0, len(ps), _lib.ADAMW_MAX_TENSORS):
+                chunk = ps[s0:s0 + _lib.ADAMW_MAX_TENSORS]
+                a = _lib.AdamWArgs()
+                for i, p in enumerate(chunk):
+                    if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                        raise RuntimeError("FusedAdamW takes contiguous fp32 CUDA parameters (there is no CPU path)")
+                    st = self.state[p]
+                    if not st:
+                        st["step"] = 0
+                        st["exp_avg"] = torch.zeros_like(p)
+                        st["exp_avg_sq"] = torch.zeros_like(p)
+                    st["step"] += 1
+                    a.params[i], a.grads[i] = p.data_ptr(), p.grad.data_ptr()
+                    a.exp_avg[i], a.exp_avg_sq[i], a.numel[i] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()
+                a.num_tensors, a.step = len(chunk), self.state[chunk[0]]["step"]
+                a.lr, (a.beta1, a.beta2), a.eps = group["lr"], group["betas"], group["eps"]
+                a.weight_decay, a.grad_scale = group["weight_decay"], grad_scale
+                with torch.cuda.device(chunk[0].device):
+                    _lib.check(lib.prego_adamw_step(C.byref(a), torch.cuda.current_stream(chunk[0].device).cuda_stream), "prego_adamw_step")
+                for p in chunk:  # the kernel wrote through raw pointers: tell autograd / the weight re-pack check (MROAD._sync_weights)
+                    torch.autograd.graph.increment_version(p)
+        return loss
+
+
+TRAINER = Registry()
+
+
+@TRAINER.register("OAD")
+def train_one_epoch(trainloader, model, criterion, optimizer, scaler, epoch, device, writer=None, scheduler=None):
+    """trainer/train.py:5-29 with the same signature.  ``scaler`` (the reference's ``--amp`` GradScaler) is accepted and
+    ignored: the reduced-precision mode of this implementation is ``cfg['train_precision'] = 'tf32'`` (fp32 storage, no
+    loss scaling needed).  Returns the summed loss of the epoch like the reference."""
+    epoch_loss = torch.zeros((), device=device)
+    for it, (rgb_input, flow_input, target, vid, start, end) in enumerate(trainloader):
+        rgb_input, flow_input, target = rgb_input.to(device, non_blocking=True), flow_input.to(device, non_blocking=True), target.to(device, non_blocking=True)
+        loss = train_one_step(model, criterion, optimizer, rgb_input, flow_input, target)
+        epoch_loss += loss  # stays on the device: no per-iteration sync (the reference calls loss.item() every step)
+        if scheduler is not None:
+            scheduler.step()
+        if writer is not None:
+            writer.add_scalar("Train Loss", loss.item(), it + epoch * len(trainloader))
+    return float(epoch_loss)
+
+
+def build_trainer(cfg):
+    """trainer/train_builder.py:9-11."""
+    return TRAINER[cfg["task"]]
+
+
+class WindowDataset(torch.utils.data.Dataset):
+    """Train-mode view of the reference dataset (datasets/dataset.py:96-135): every video is cut into windows of
+    ``window_size`` frames every ``stride`` frames, starting at a random offset in [0, stride) that is re-drawn by
+    ``_init_features()`` (the reference calls it after every epoch, main.py:101).  Items:
+    ``(rgb[W, Dr], flow[W, Df], target[W, K], vid, start, end)`` fp32, like ``THUMOSDataset.__getitem__``.
+
+    ``videos``: ``{vid: (rgb[T, Dr], flow[T, Df] | None, target[T, K])}`` numpy / torch arrays; a ``None`` flow is the
+    all-zero dummy of dataset.py:63-69."""
+
+    def __init__(self, videos, window_size: int, stride: int, d_flow: int = 2048, rng=None):
+        import numpy as np
+        self.videos, self.window_size, self.stride, self.d_flow = videos, int(window_size), int(stride), d_flow
+        self.rng = rng if rng is not None else np.random
+        self.inputs = []
+        self._init_features()
+
+    def _init_features(self):
+        self.inputs = []
+        for vid, (rgb, flow, target) in self.videos.items():
+            n = int(target.shape[0])
+            seed = int(self.rng.randint(self.stride))
+            for start, end in zip(range(seed, n, self.stride), range(seed + self.window_size, n + 1, self.stride)):
+                self.inputs.append((vid, start, end))
+
+    def __len__(self):
+        return len(self.inputs)
+
+    def __getitem__(self, index):
+        vid, start, end = self.inputs[index]
+        rgb, flow, target = self.videos[vid]
+        f32 = lambda a: torch.as_tensor(a[start:end]).to(torch.float32)
+        fl = torch.zeros(end - start, self.d_flow, dtype=torch.float32) if flow is None else f32(flow)
+        return f32(rgb), fl, f32(target), vid, start, end
+
+
 def train_one_step(model, criterion, optimizer, rgb, flow, target, group=None):
     """One iteration of trainer/train.py:8-24 (+ the gradient all-reduce when run data-parallel)."""
     model.train()
@@ -130,3 +232,12 @@ def train_one_step(model, criterion, optimizer, rgb, flow, target, group=None):
     allreduce_gradients(model, group)
     optimizer.step()
     return loss.detach()
+
+
+def build_optimizer(cfg, model, fused: bool = True):
+    """main.py:62-67: AdamW (or Adam) over all parameters with ``lr`` / ``weight_decay`` from the config.  ``fused``
+    selects the one-launch CUDA AdamW; Adam (coupled L2) stays on torch."""
+    if cfg.get("optimizer", "AdamW") == "AdamW" and fused:
+        return FusedAdamW([{"params": list(model.parameters()), "initial_lr": cfg["lr"]}], lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+    optim = torch.optim.AdamW if cfg.get("optimizer", "AdamW") == "AdamW" else torch.optim.Adam
+    return optim([{"params": model.parameters(), "initial_lr": cfg["lr"]}], lr=cfg["lr"], weight_decay=cfg["weight_decay"])
