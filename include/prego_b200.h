@@ -116,11 +116,12 @@ typedef struct prego_online prego_online_t;
 int prego_online_open(prego_model_t* model, int32_t num_streams, int32_t precision, float* h_state, float* probs,
                       float* logits, int32_t* labels, prego_online_t** out);
 int prego_online_step(prego_online_t* session, const float* rgb, const float* flow, void* stream);
-/* Host-side completion of the last prego_online_step without a stream synchronize: spins on a pinned word the frame's
- * kernel writes (after a system-scope fence) once its outputs are visible.  Meant for sessions whose label / probs
- * buffers live in pinned host memory (the kernel stores into them directly): step + wait is the whole per-frame
- * round trip.  Only sessions on the one-kernel-per-frame path opened with `labels` in pinned host memory support it
- * (PREGO_ERR_STATE otherwise): device-resident sessions do not pay the per-frame system fence. */
+/* Host-side completion of the last prego_online_step without a stream synchronize: spins on pinned doorbell words the
+ * frame's kernel writes, one 8-byte store {frame number, label} per stream (label and flag in the same store: no
+ * system-scope fence on the device), and copies the labels into the session's label buffer.  Meant for sessions whose
+ * label buffer lives in pinned host memory: step + wait is the whole per-frame round trip (no D2H copy).  Only sessions
+ * on the one-kernel-per-frame path opened with `labels` in pinned host memory support it (PREGO_ERR_STATE otherwise):
+ * device-resident sessions do not pay the per-frame PCIe store.  probs / logits in host memory are fenced first. */
 int prego_online_wait(prego_online_t* session);
 int prego_online_close(prego_online_t* session);
 /* Diagnostics: SM-clock stamps of the phase boundaries of the last frame, out[ctas][16] (host memory), for sessions

@@ -625,7 +625,7 @@ int online_step_fused(prego_model* m, const prego_forward_args_t* a, float* h, i
     fa.wstream = m->online_stream[fmt];
     fa.b1 = m->b1; fa.ln_g = m->ln_g; fa.ln_b = m->ln_b; fa.bih = m->bih_p; fa.bhh = m->bhh_p; fa.wct = m->wct_f32; fa.bc = m->bc;
     online_fused_carve(m->online_scratch, d.embed_dim, d.num_classes, &fa);
-    fa.h = h; fa.probs = a->probs; fa.logits = a->logits; fa.labels = a->labels; fa.err_flag = m->err_flag; fa.trace = nullptr; fa.host_seq = nullptr; fa.seq = 0;
+    fa.h = h; fa.probs = a->probs; fa.logits = a->logits; fa.labels = a->labels; fa.err_flag = m->err_flag; fa.trace = nullptr; fa.host_seq = nullptr; fa.seq = 0; fa.fence_outputs = 0;
     fa.rows = (int)a->B; fa.Dr = d.d_rgb; fa.Df = d.d_flow; fa.E = d.embed_dim; fa.H = d.hidden_dim; fa.K = d.num_classes;
     fa.T = a->T; fa.t0 = 0; fa.eps = 1e-5f;
     void* fn = online_fused_fn(fmt, m->din);

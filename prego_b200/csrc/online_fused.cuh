@@ -52,8 +52,10 @@ struct OnlineFusedArgs {
     unsigned* sync;  // [2] zero before the first launch; the kernel re-arms them
     int* err_flag;
     long long* trace;  // optional [grid][16] SM-clock stamps of the phase boundaries (diagnostics; NULL = off)
-    unsigned* host_seq;  // optional host-mapped word: receives `seq` after the frame's outputs are visible system-wide
+    unsigned long long* host_seq;  // optional host-mapped doorbell words [rows]: {frame number << 32 | label} -- the label and
+                                   // its completion flag travel in ONE 8-byte store, so no system-scope fence is needed
     unsigned seq;
+    int fence_outputs;             // probs / logits also live in host memory: fence them before ringing the doorbell
     int rows, Dr, Df, E, H, K;
     int64_t T, t0;  // output row of stream r is r * T + t0
     float eps;
@@ -527,14 +529,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
                 arg = oa;
             }
         }
-        if (lane == 0 && a.labels != nullptr) a.labels[go] = arg;
-    }
-    if (a.host_seq != nullptr) {  // completion doorbell for a host that polls instead of synchronizing the stream
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned*>(a.host_seq) = a.seq;
+        if (a.host_seq != nullptr) {  // completion doorbell for a host that polls instead of synchronizing the stream
+            if (a.fence_outputs) __threadfence_system();  // this warp's probs / logits stores first
+            if (lane == 0)
+                *reinterpret_cast<volatile unsigned long long*>(a.host_seq + r) =
+                    (static_cast<unsigned long long>(a.seq) << 32) | static_cast<unsigned>(arg);
         }
+        if (lane == 0 && a.labels != nullptr) a.labels[go] = arg;  // (posted store: visible at the latest when the stream drains)
     }
     FUSED_STAMP(8);
 }
