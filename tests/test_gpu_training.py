@@ -75,14 +75,16 @@ def test_gradients_match_torch_autograd(dev, B, T, K):
         assert fro <= FRO_REL and err <= MAX_REL_LOOSE * q.grad.abs().max().item(), f"{k}: fro {fro}, max {err}"
 
 
-def test_gradients_tf32_mode(dev):
+@pytest.mark.parametrize("B,T", [(16, 128), (128, 12)])
+def test_gradients_tf32_mode(dev, B, T):
     """train_precision = 'tf32': the large projections and their weight / input gradients on tcgen05 kind::tf32
     (10-bit-mantissa operands, fp32 accumulate).  Judged in the Frobenius norm against ATen fp32 autograd at a TF32-class
     tolerance; the exact mode above is the parity mode.  Measured on B200 (scripts/diag_train_tf32.py): logits 5.9e-4
     relative; every gradient that flows through the 128-step recurrence 1.8e-2 .. 2.1e-2 -- including the bias
     gradients, whose own reductions are exact: the BPTT chain amplifies the 6e-4 forward perturbation, as it does for
-    any TF32 forward -- and 5.9e-4 for the classifier weight, which does not."""
-    B, T, K = 16, 128, 86
+    any TF32 forward -- and 5.9e-4 for the classifier weight, which does not.  (128, 12): the wide-batch variant, whose
+    per-step recurrent GEMMs run on the tensor cores as well."""
+    K = 86
     cfg = dict(synthetic.ASSEMBLY101_O, dropout=0.0, num_classes=K, train_precision="tf32")
     rgb, flow = synthetic.feature_batch(list(range(100, 100 + B)), T, "cpu", False)
     wts = torch.randn(B, T, K, generator=torch.Generator().manual_seed(1))
