@@ -235,7 +235,7 @@ def latency_leg(dev, precision):
     gpu_us = e0.elapsed_time(e1) / 200 * 1e3  # back-to-back graph launches: device-side cost of one frame
     out["per_frame_online"] = {"frames": n, "p50_ms": float(np.percentile(wall, 50)), "p99_ms": float(np.percentile(wall, 99)),
                                "p50_ms_stream_sync": float(np.percentile(wall_sync, 50)), "gpu_us_per_frame": gpu_us,
-                               "note": "OnlineSession.step per frame: one CUDA-graph launch (one cooperative kernel: all layers, carried state in place), label stored by the kernel into pinned host memory, completion = host spin on a pinned doorbell word the kernel writes after a system fence (prego_online_wait); p50_ms_stream_sync: the same with cudaStreamSynchronize instead; wall clock"}
+                               "note": "OnlineSession.step per frame: one CUDA-graph launch (one cooperative kernel: all layers, carried state in place), label stored by the kernel into pinned host memory, completion = host spin on a pinned doorbell word per stream {frame number, label} written by the kernel in one 8-byte store (prego_online_wait); p50_ms_stream_sync: the same with cudaStreamSynchronize instead; wall clock"}
     return out
 
 
