@@ -107,3 +107,38 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle"
                 assert "/root/reference" not in src, f"{f} reads the reference at run time"
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """Every ctypes mirror in prego_b200/_lib.py has the size and field offsets of the C struct it stands for
+    (checked by compiling a probe against include/prego_b200.h with the host C compiler)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no host C compiler")
+    pairs = {"prego_dims_t": _lib.Dims, "prego_weights_t": _lib.Weights, "prego_forward_args_t": _lib.ForwardArgs,
+             "prego_grads_t": _lib.Grads, "prego_train_args_t": _lib.TrainArgs, "prego_adamw_args_t": _lib.AdamWArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "prego_b200.h"', 'int main(void) {']
+    for cname, ct in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call([cc, "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split("\n")
+    seen = 0
+    for ln in out:
+        if not ln:
+            continue
+        cname, what, val = ln.split()
+        ct = pairs[cname]
+        if what == "size":
+            assert C.sizeof(ct) == int(val), f"{cname}: ctypes size {C.sizeof(ct)} vs C {val}"
+        else:
+            assert getattr(ct, what).offset == int(val), f"{cname}.{what}: ctypes offset {getattr(ct, what).offset} vs C {val}"
+        seen += 1
+    assert seen > 60
