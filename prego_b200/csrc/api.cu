@@ -38,8 +38,10 @@ int fail(int code, const char* fmt, ...) {
 #define CUDA_TRY(expr)                                                                              \
     do {                                                                                            \
         cudaError_t _e = (expr);                                                                    \
-        if (_e != cudaSuccess)                                                                      \
+        if (_e != cudaSuccess) {                                                                    \
+            (void)cudaGetLastError(); /* do not leave it for the next launch check to trip over */  \
             return fail(PREGO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                           \
     } while (0)
 
 #define LAUNCH_CHECK(name)                                                                          \
@@ -754,7 +756,8 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
     if (d.d_rgb < 0 || d.d_flow < 0 || din <= 0) return fail(PREGO_ERR_INVALID, "need at least one of rgb / flow (rnn.py:23-29)");
     if (din % 64 != 0 || d.d_rgb % 8 != 0) return fail(PREGO_ERR_INVALID, "input feature widths must be multiples of 64 (got %d + %d)", d.d_rgb, d.d_flow);
     if (d.embed_dim != 2048) return fail(PREGO_ERR_INVALID, "embedding_dim must be 2048 (got %d)", d.embed_dim);
-    if (d.hidden_dim <= 0 || d.hidden_dim % 64 != 0 || d.hidden_dim > 2048) return fail(PREGO_ERR_INVALID, "hidden_dim must be a multiple of 64, <= 2048 (got %d)", d.hidden_dim);
+    // the few-stream recurrence runs H / 8 co-resident CTAs (one warp per hidden unit): H <= 1024 keeps that within any B200's SMs
+    if (d.hidden_dim <= 0 || d.hidden_dim % 64 != 0 || d.hidden_dim > 1024) return fail(PREGO_ERR_INVALID, "hidden_dim must be a multiple of 64, <= 1024 (got %d; the reference ships 1024)", d.hidden_dim);
     if (d.num_classes <= 0 || d.num_classes > 1024) return fail(PREGO_ERR_INVALID, "num_classes must be in [1, 1024] (got %d)", d.num_classes);
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;

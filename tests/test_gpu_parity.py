@@ -552,3 +552,30 @@ def test_streamed_ingest_matches_per_video_path(dev, zero_flow):
         assert torch.equal(v.cpu(), ref[k]), k
     with pytest.raises(RuntimeError):
         ingest.predict_labels_streamed(model, store, dev, precision="bf16")
+
+
+@pytest.mark.parametrize("H,K,B,T", [(512, 100, 3, 20), (512, 100, 40, 6), (1024, 128, 33, 5)])
+def test_non_shipped_shapes_vs_oracle(dev, H, K, B, T):
+    """Shapes outside the two shipped configs (hidden_dim 512, 100 / 128 classes -> the 128-wide head tile, ragged B):
+    whole-sequence fp32 / fp16 and the per-frame path against the numpy oracle; unsupported shapes fail loudly."""
+    from prego_b200 import synthetic
+    cfg = dict(synthetic.ASSEMBLY101_O, hidden_dim=H, num_classes=K)
+    model = synthetic.seeded_model(cfg, seed=20, device=dev)
+    rgb, flow = synthetic.device_features(B, T, dev, seed=3)
+    sd = {k: v.cpu() for k, v in model.state_dict().items()}
+    _, ref, _ = miniroad_np.forward(sd, rgb.cpu().numpy(), flow.cpu().numpy(), return_all=True)
+    scale = np.abs(ref).max()
+    for prec in ("fp32", "fp16"):
+        out = model.infer(rgb, flow, want_logits=True, precision=prec)["logits"].cpu().numpy()
+        assert np.abs(out - ref).max() <= REL[prec] * scale, prec
+    rows = min(B, 8)
+    h = torch.zeros(rows, H, device=dev)
+    lg = [model.infer(rgb[:rows, t:t + 1].contiguous(), flow[:rows, t:t + 1].contiguous(), h_state=h, want_logits=True, precision="fp16")["logits"]
+          for t in range(min(T, 6))]
+    assert np.abs(torch.cat(lg, 1).cpu().numpy() - ref[:rows, :min(T, 6)]).max() <= REL["fp16"] * scale
+    assert model.device_error() == 0
+    big = synthetic.seeded_model(dict(synthetic.ASSEMBLY101_O, num_classes=200), seed=20, device=dev)
+    with pytest.raises(RuntimeError, match="num_classes <= 128"):
+        big.infer(rgb, flow, precision="fp16")
+    with pytest.raises(RuntimeError, match="hidden_dim"):
+        synthetic.seeded_model(dict(synthetic.ASSEMBLY101_O, hidden_dim=2048), seed=20, device=dev).infer(rgb, flow)
