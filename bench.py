@@ -276,6 +276,24 @@ def training_leg(dev, world):
             out[f"B{B}_T{T}" + ("" if prec == "fp32" else "_tf32")] = {"ms_per_step": float(ms), "frames_per_s": world * B * T / float(ms) * 1e3,
                                                                        "loss": float(loss)}
             del rgb, flow, target
+    if world > 1:
+        # the data-parallel exchange on its own: one all-reduce of the flat gradient buffer (17.9 M fp32) over NCCL / NVLink
+        from prego_b200 import allreduce_gradients
+        for _ in range(3):
+            allreduce_gradients(model)
+        torch.cuda.synchronize()
+        dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            allreduce_gradients(model)
+        a1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a0.elapsed_time(a1) / 10], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        nbytes = sum(p.numel() for p in model.parameters()) * 4
+        out["grad_allreduce"] = {"ms": float(ms), "bytes": nbytes, "bus_gbs": 2 * (world - 1) / world * nbytes / (float(ms) * 1e-3) / 1e9,
+                                 "note": "flat-buffer gather + NCCL all-reduce (sum) + scatter back, per step; bus GB/s = 2 (N-1)/N x bytes / time"}
     out["note"] = ("fwd + BPTT + fused AdamW (one launch), dropout 0.2, flow = 0; recurrence (forward and BPTT) on the persistent exact-fp32 kernels "
                    "for B <= 64; plain keys: every GEMM exact fp32 on CUDA cores (parity mode); *_tf32: large projections and their "
                    "gradients on tcgen05 kind::tf32; grads all-reduced (NCCL) when n_gpus > 1")
