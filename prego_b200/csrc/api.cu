@@ -267,6 +267,14 @@ int launch_gemm_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N
     }
     const int tiles = (N / TILE_N) * ((M + 2 * kTileM - 1) / (2 * kTileM));
     int grid = 2 * tiles < sm_count ? 2 * tiles : (sm_count & ~1);
+    {   // experiment knob: cap the number of CTA pairs (e.g. a multiple of N / TILE_N so tiles sharing an A block stay in one wave)
+        static int cap = -1;
+        if (cap < 0) {
+            const char* e = getenv("PREGO_GEMM_PAIRS");
+            cap = e != nullptr ? atoi(e) : 0;
+        }
+        if (cap > 0 && 2 * cap < grid) grid = 2 * cap;
+    }
     if (tmA2 == nullptr) kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, a_c1, epi, tmA, K, 0);
     else kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, a_c1, epi, *tmA2, k_split, rows_per_c1);
     LAUNCH_CHECK(name);
