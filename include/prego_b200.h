@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define PREGO_ABI_VERSION 2
+#define PREGO_ABI_VERSION 3
 
 #define PREGO_OK 0
 #define PREGO_ERR_INVALID 1     /* bad argument / unsupported shape */
@@ -204,6 +204,46 @@ int prego_window_mode(const int32_t* labels, const int64_t* offsets, const int64
  * counts[b] = number of runs, -1 for an empty sequence (the reference raises IndexError). */
 int prego_rle(const int32_t* seq, const int64_t* seg_offsets, const int64_t* final_len, int32_t B, int64_t scale,
               int32_t* out_vals, int64_t* out_changes, int32_t* counts, void* stream);
+
+/* ---- MiniROADA anticipation head (reference: MROADA, rnn.py:73-137, registered "MiniROADA").
+ * Same trunk as MROAD (rnn.py:117-124), plus per frame
+ *     ant_h[a]      = anticipation_layer.0(relu(h_t))[a*H:(a+1)*H]            (rnn.py:108-110,125)
+ *     ant_logits[a] = f_classification(relu(ant_h[a])),  a = 0..A-1             (rnn.py:126, the SAME classifier)
+ * and, in eval mode, softmax over the classes (rnn.py:133).  prego_model_load_anticipation packs the two extra
+ * state_dict tensors (A = cfg['anticipation_length']); prego_forward_anticipation is prego_forward plus the
+ * anticipation outputs.  The [rows, A*H] activation is produced in row slabs sized by `workspace` (never the whole
+ * [B*T, A*H] tensor): any size >= prego_anticipation_workspace_bytes(model, 256, precision) works, larger slabs are
+ * faster.  The one-kernel-per-frame online path is not used by this entry point.  Inference only. */
+typedef struct prego_anticipation_args {
+    float* probs;            /* [B, T, A, K] softmax (eval-mode out['anticipation_logits'], rnn.py:133-135) or NULL */
+    float* logits;           /* [B, T, A, K] raw (train-mode out['anticipation_logits'], rnn.py:130) or NULL */
+    int32_t* labels;         /* [B, T, A] first-max argmax or NULL */
+    void* workspace;         /* slab buffer, 1024-aligned */
+    size_t workspace_bytes;
+} prego_anticipation_args_t;
+
+int prego_model_load_anticipation(prego_model_t* model, int32_t anticipation_length,
+                                  const float* anticipation_layer_0_weight /* [A*H, H] */,
+                                  const float* anticipation_layer_0_bias /* [A*H] */, void* stream);
+size_t prego_anticipation_workspace_bytes(const prego_model_t* model, int64_t slab_rows, int32_t precision);
+int prego_forward_anticipation(prego_model_t* model, const prego_forward_args_t* args,
+                               const prego_anticipation_args_t* ant, void* stream);
+
+/* ---- Per-frame average precision on the device (reference: perframe_average_precision,
+ * utils/metrics.py:25-62 with metrics == 'AP', i.e. sklearn.metrics.average_precision_score per class).
+ * scores: [N, K] fp32 probabilities in [0, 1] (the concatenated eval-mode outputs, trainer/eval.py:46-49);
+ * ground truth either `targets` [N, K] fp32 (non-zero = positive; the reference's one-hot target rows) or, when
+ * targets == NULL, `target_labels` [N] int32 (one-hot implied).  For every class k:
+ *     order frames by score descending; at each DISTINCT score threshold n: P_n = tp_n / (tp_n + fp_n),
+ *     R_n = tp_n / positives;  ap[k] = sum_n (R_n - R_{n-1}) * P_n                      (float64)
+ * num_pos[k] = positives of class k (ap[k] is NaN when 0: the reference skips such classes, metrics.py:54).
+ * Class 0 (background) is computed too; the caller drops it (metrics.py:47,53).  One CTA per class: 8-bit LSD radix
+ * sort of the 31-bit keys (score bits << 1 | positive) in `workspace`, then one scan over the sorted keys.
+ * err_flag (device int, caller-zeroed) becomes 1 if a score is outside [0, 1] or NaN. */
+size_t prego_ap_workspace_bytes(int64_t N, int32_t K);
+int prego_perframe_ap(const float* scores, const float* targets, const int32_t* target_labels, int64_t N, int32_t K,
+                      double* ap /*[K]*/, int64_t* num_pos /*[K]*/, void* workspace, size_t workspace_bytes,
+                      int32_t* err_flag, void* stream);
 
 /* Building blocks exposed for parity tests and micro-benchmarks. */
 /* C[M,N] (fp32, ldc = N) = A[M,K] * W[N,K]^T + bias[N] with 16-bit operands (precision = PREGO_PREC_F16 or

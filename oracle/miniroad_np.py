@@ -119,6 +119,32 @@ def forward(sd, rgb, flow, *, use_rgb=True, use_flow=True, h0=None,
     return out
 
 
+def forward_anticipation(sd, rgb, flow, anticipation_length, *, use_rgb=True, use_flow=True, training=False,
+                         dtype=np.float32):
+    """MROADA.forward restated (``rnn.py:112-137``; registered "MiniROADA", ``rnn.py:73``).
+
+    Same trunk as MROAD (``rnn.py:113-124``), then per frame
+    ``ant_h = anticipation_layer.0(relu(h_t)).view(A, H)`` (``rnn.py:108-110,125``) and the SAME classifier on
+    ``relu(ant_h)`` (``rnn.py:126``); softmax over classes in eval (``rnn.py:132-135``).
+    Returns (out['logits'] [B,T,K], out['anticipation_logits'] [B,T,A,K], raw logits, raw anticipation logits).
+    """
+    rgb = np.asarray(rgb)
+    flow = np.asarray(flow)
+    x = np.concatenate((rgb, flow), axis=2) if (use_rgb and use_flow) else (rgb if use_rgb else flow)
+    B, T, D = x.shape
+    e = embed(sd, x.reshape(B * T, D), dtype).reshape(B, T, -1)
+    ht, _ = gru_sequence(sd, e, None, dtype)
+    logits = head_logits(sd, ht, dtype)
+    wa = _w(sd, "anticipation_layer.0.weight", dtype)
+    ba = _w(sd, "anticipation_layer.0.bias", dtype)
+    H = ht.shape[-1]
+    ant_h = (np.maximum(ht, 0).astype(dtype) @ wa.T + ba).reshape(B, T, anticipation_length, H)
+    ant_logits = head_logits(sd, ant_h, dtype)
+    if training:
+        return logits, ant_logits, logits, ant_logits
+    return softmax(logits), softmax(ant_logits), logits, ant_logits
+
+
 def labels_from_probs(probs):
     """trainer/eval.py:53 -- np.argmax over the class axis, first max wins."""
     return np.argmax(probs, axis=-1)

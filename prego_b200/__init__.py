@@ -5,9 +5,10 @@ Drop-in for the hot path of aleflabo/PREGO (``step_recognition/model/rnn/rnn.py`
 behind the C ABI in ``include/prego_b200.h``.
 """
 from .registry import META_ARCHITECTURES, EVAL, Registry, build_model, build_eval  # noqa: F401
-from .model import MROAD, FEATURE_SIZES  # noqa: F401
+from .model import MROAD, MROADA, FEATURE_SIZES  # noqa: F401
 from .aggregate import aggregate, aggregate_labels  # noqa: F401
-from .evaluate import Evaluate  # noqa: F401
+from .evaluate import Evaluate, ANT_Evaluate  # noqa: F401
+from .metrics import perframe_average_precision  # noqa: F401
 from .pipeline import predict_labels, recognize_and_aggregate  # noqa: F401
 from .training import (OadLoss, build_criterion, train_one_step, allreduce_gradients, FusedAdamW, TRAINER, train_one_epoch,  # noqa: F401
                        build_trainer, build_optimizer, WindowDataset)

@@ -43,6 +43,11 @@ class ForwardArgs(C.Structure):
 FEAT_F32, FEAT_16 = 0, 1
 
 
+class AnticipationArgs(C.Structure):
+    _fields_ = [("probs", C.c_void_p), ("logits", C.c_void_p), ("labels", C.c_void_p), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_size_t)]
+
+
 class Grads(C.Structure):
     _fields_ = Weights._fields_
 
@@ -74,6 +79,12 @@ SIGNATURES = {
     "prego_model_load_weights": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_void_p]),
     "prego_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
     "prego_forward": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.c_void_p]),
+    "prego_model_load_anticipation": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prego_anticipation_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int32]),
+    "prego_forward_anticipation": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.POINTER(AnticipationArgs), C.c_void_p]),
+    "prego_ap_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "prego_perframe_ap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "prego_online_open": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_void_p)]),
     "prego_online_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -16,6 +16,7 @@
 #include "gemm_tc.cuh"
 #include "gru_latency.cuh"
 #include "gru_step.cuh"
+#include "metrics.cuh"
 #include "online_fused.cuh"
 #include "online_kernels.cuh"
 #include "simt_kernels.cuh"
@@ -154,6 +155,10 @@ struct prego_model {
     float* bgi_p = nullptr;  // b_ih' + (r, z parts of b_hh'): bias of the input-gate GEMM on the batched 16-bit path
     float *wc_f32 = nullptr, *bc = nullptr;
     float* wct_f32 = nullptr;         // classifier transposed [H, K] (per-frame kernel)
+    // MROADA anticipation layer (rnn.py:108-110): A = anticipation_length, weight [A*H, H], bias [A*H]; 0 = not loaded
+    int ant_len = 0;
+    float *wa_f32 = nullptr, *ba = nullptr;
+    void* wa_16[2] = {nullptr, nullptr};
     float* online_scratch = nullptr;  // y | LayerNorm partials | logit partials | counters of the per-frame kernel
     uint4* online_stream[2] = {nullptr, nullptr};  // weights in the per-frame kernel's load order ([0] fp16, [1] bf16)
     // 16-bit operands of the tcgen05 path, [0] = fp16, [1] = bf16
@@ -422,9 +427,70 @@ int make_tmap_feat(CUtensorMap* tm, DType dt, const void* base, uint64_t D, uint
 
 // ci = chunk index; with overlap the features of chunk ci were staged into xb[ci & 1] ahead of time on the side
 // stream, and this call stages chunk ci + 1 (starting at t_next, tc_next frames) behind its own GEMM1.
+// ---- MROADA anticipation head on one time chunk (rnn.py:125-126,133): ant = relu(relu(h) Wa^T + ba) viewed as
+// [rows * A, H], then the SAME classifier + softmax / argmax.  Produced in row slabs that fit the caller's buffer.
+inline int64_t ant_row_bytes(const prego_model* m, int prec) {
+    const int64_t A = m->ant_len, H = m->d.hidden_dim, K = m->d.num_classes;
+    return prec == PREGO_PREC_FP32 ? A * H * 4 + A * K * 4 : A * H * 2;
+}
+inline int64_t ant_slab_rows(const prego_model* m, const prego_anticipation_args_t* ant, int prec, int64_t Mc) {
+    int64_t rows = static_cast<int64_t>(ant->workspace_bytes) / ant_row_bytes(m, prec);
+    const int64_t cap = (int64_t(1) << 22) / m->ant_len;  // slab * A rows per head launch (grid.y / int limits)
+    if (rows > cap) rows = cap;
+    if (rows >= 128) rows = rows / 128 * 128;
+    return rows < Mc ? rows : Mc;
+}
+
+template <int FMT>
+int anticipation_16(prego_model* m, const prego_forward_args_t* a, const prego_anticipation_args_t* ant, const void* hrelu,
+                    int64_t Mc, int64_t t0, cudaStream_t s) {
+    using OpT = typename Op16<FMT>::T;
+    const DType dt = FMT == 0 ? kF16 : kBF16;
+    const int H = m->d.hidden_dim, K = m->d.num_classes, A = m->ant_len;
+    const int64_t slab = ant_slab_rows(m, ant, a->precision, Mc);
+    OpT* ant16 = static_cast<OpT*>(ant->workspace);
+    CUtensorMap tmA, tmB, tmH, tmC;
+    RC_TRY(make_tmap_w(&tmB, dt, m->wa_16[FMT], H, (uint64_t)A * H, use_2cta() ? 128 : 256));
+    RC_TRY(make_tmap_w(&tmC, dt, m->wc_16p[FMT], H, m->kpad, m->kpad));
+    for (int64_t r0 = 0; r0 < Mc; r0 += slab) {
+        const int ms = static_cast<int>(Mc - r0 < slab ? Mc - r0 : slab);
+        RC_TRY(make_tmap_a(&tmA, dt, static_cast<const OpT*>(hrelu) + r0 * H, H, ms));
+        EpiStore<256, FMT> epi{ant16, m->ba, (int64_t)A * H, 0, 0, 0, 1};
+        if (use_2cta()) RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, ms, A * H, H, 0, epi, m->sm_count, s, "anticipation layer (2cta)")));
+        else RC_TRY((launch_gemm_tc<256, 4, FMT>(tmA, tmB, ms, A * H, H, 0, epi, m->sm_count, s, "anticipation layer")));
+        RC_TRY(make_tmap_a(&tmH, dt, ant16, H, (uint64_t)ms * A));
+        if (m->kpad == 96)
+            RC_TRY((launch_gemm_tc<96, 6, FMT>(tmH, tmC, ms * A, 96, H, 0, EpiHead<96>{m->bc, ant->probs, ant->logits, ant->labels, K, (int)a->B, (int)a->T, (int)t0, A, r0 * A}, m->sm_count, s, "anticipation head96")));
+        else
+            RC_TRY((launch_gemm_tc<128, 6, FMT>(tmH, tmC, ms * A, 128, H, 0, EpiHead<128>{m->bc, ant->probs, ant->logits, ant->labels, K, (int)a->B, (int)a->T, (int)t0, A, r0 * A}, m->sm_count, s, "anticipation head128")));
+    }
+    return PREGO_OK;
+}
+
+// exact fp32: hr32 rows are stream-major inside the chunk (m = b*tc + t)
+int anticipation_f32(prego_model* m, const prego_forward_args_t* a, const prego_anticipation_args_t* ant, const float* hr32,
+                     int64_t Mc, int tc, int64_t t0, cudaStream_t s) {
+    const int H = m->d.hidden_dim, K = m->d.num_classes, A = m->ant_len;
+    const int64_t slab = ant_slab_rows(m, ant, a->precision, Mc);
+    float* ant32 = static_cast<float*>(ant->workspace);
+    float* lg = ant32 + slab * A * H;
+    for (int64_t r0 = 0; r0 < Mc; r0 += slab) {
+        const int ms = static_cast<int>(Mc - r0 < slab ? Mc - r0 : slab);
+        SgemmA Aa{hr32 + r0 * H, nullptr, H, H, 0, 0, tc, (int)a->T, (int)t0, 0, 1};
+        sgemm_nt_f32<<<dim3((A * H + 127) / 128, (ms + 127) / 128), 256, 0, s>>>(Aa, m->wa_f32, m->ba, ant32, ms, A * H, H, (int64_t)A * H);
+        SgemmA Ab{ant32, nullptr, H, H, 0, 0, tc, (int)a->T, (int)t0};
+        sgemm_nt_f32<<<dim3((K + 127) / 128, (ms * A + 127) / 128), 256, 0, s>>>(Ab, m->wc_f32, m->bc, lg, ms * A, K, H, K);
+        softmax_argmax_f32<<<grid_for((int64_t)ms * A * 32, 256, m->sm_count), 256, 0, s>>>(lg, ant->probs, ant->logits, ant->labels, (int64_t)ms * A, K, tc,
+                                                                                          (int)a->T, (int)t0, A, r0 * A);
+        LAUNCH_CHECK("fp32 anticipation head");
+    }
+    return PREGO_OK;
+}
+
 template <int FMT>
 int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt,
-             int64_t t0, int tc, cudaStream_t s, int ci = 0, bool overlap = false, int64_t t_next = 0, int tc_next = 0) {
+             int64_t t0, int tc, cudaStream_t s, int ci = 0, bool overlap = false, int64_t t_next = 0, int tc_next = 0,
+             const prego_anticipation_args_t* ant = nullptr) {
     using OpT = typename Op16<FMT>::T;
     const DType dt = FMT == 0 ? kF16 : kBF16;
     const prego_dims_t& d = m->d;
@@ -582,6 +648,7 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
         RC_TRY((launch_gemm_tc<96, 6, FMT>(tmA, tmB, Mi, 96, H, 0, EpiHead<96>{m->bc, a->probs, a->logits, a->labels, K, (int)B, (int)T, (int)t0}, m->sm_count, s, "head96")));
     else
         RC_TRY((launch_gemm_tc<128, 6, FMT>(tmA, tmB, Mi, 128, H, 0, EpiHead<128>{m->bc, a->probs, a->logits, a->labels, K, (int)B, (int)T, (int)t0}, m->sm_count, s, "head128")));
+    if (ant != nullptr) RC_TRY(anticipation_16<FMT>(m, a, ant, hrelu, Mc, t0, s));
     prof_mark(m, s, PREGO_PHASE_HEAD, 1);
     return PREGO_OK;
 }
@@ -660,7 +727,7 @@ int online_step(prego_model* m, const prego_forward_args_t* a, const Plan& p, ui
 
 // One time chunk of the exact-fp32 CUDA-core path (stream-major rows throughout).
 int chunk_f32(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt,
-              int64_t t0, int tc, cudaStream_t s) {
+              int64_t t0, int tc, cudaStream_t s, const prego_anticipation_args_t* ant = nullptr) {
     const prego_dims_t& d = m->d;
     const int64_t B = a->B, T = a->T, Mc = B * tc;
     const int Mi = static_cast<int>(Mc);
@@ -703,8 +770,9 @@ int chunk_f32(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint
 
     SgemmA Ah{hr32, nullptr, H, H, 0, 0, tc, (int)T, (int)t0};
     sgemm_nt_f32<<<dim3((K + 127) / 128, (Mi + 127) / 128), 256, 0, s>>>(Ah, m->wc_f32, m->bc, logits_ws, Mi, K, H, K);
-    softmax_argmax_f32<<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(logits_ws, a->probs, a->logits, a->labels, Mc, K, tc, (int)T, (int)t0);
+    softmax_argmax_f32<<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(logits_ws, a->probs, a->logits, a->labels, Mc, K, tc, (int)T, (int)t0, 1, 0);
     LAUNCH_CHECK("fp32 head");
+    if (ant != nullptr) RC_TRY(anticipation_f32(m, a, ant, hr32, Mc, tc, t0, s));
     prof_mark(m, s, PREGO_PHASE_HEAD, 2);
     return PREGO_OK;
 }
@@ -813,7 +881,8 @@ int prego_model_destroy(prego_model_t* m) {
     cudaSetDevice(m->device);
     void* ptrs[] = {m->w1_f32, m->b1, m->ln_g, m->ln_b, m->wih_f32p, m->whh_f32p, m->bih_p, m->bhh_p, m->bgi_p, m->wc_f32, m->bc,
                     m->w1_16[0], m->w1_16[1], m->wih_16p[0], m->wih_16p[1], m->whh_16p[0], m->whh_16p[1], m->wc_16p[0],
-                    m->wc_16p[1], m->xchg, m->xchg_bwd, m->err_flag, m->wct_f32, m->online_scratch, m->online_stream[0], m->online_stream[1]};
+                    m->wc_16p[1], m->xchg, m->xchg_bwd, m->err_flag, m->wct_f32, m->online_scratch, m->online_stream[0], m->online_stream[1],
+                    m->wa_f32, m->ba, m->wa_16[0], m->wa_16[1]};
     for (void* p : ptrs)
         if (p != nullptr) cudaFree(p);
     for (cudaEvent_t e : m->prof_ev)
@@ -862,7 +931,7 @@ size_t prego_workspace_bytes(const prego_model_t* m, int64_t B, int64_t chunk_T,
     return static_cast<size_t>(make_plan(m->d, B, chunk_T, precision).total);
 }
 
-int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_) {
+static int forward_impl(prego_model_t* m, const prego_forward_args_t* a, const prego_anticipation_args_t* ant, void* stream_) {
     RC_TRY(check_model(m, true));
     if (a == nullptr) return fail(PREGO_ERR_INVALID, "args is NULL");
     const prego_dims_t& d = m->d;
@@ -895,7 +964,18 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
     float* h_cur = reinterpret_cast<float*>(ws + p.h32_a);
     float* h_alt = reinterpret_cast<float*>(ws + p.h32_b);
 
-    const bool online = h16 && T == 1 && B <= kOnlineMaxRows && d.d_rgb % 2 == 0 && m->din % 8 == 0 &&
+    if (ant != nullptr) {
+        if (m->ant_len <= 0) return fail(PREGO_ERR_STATE, "anticipation weights not loaded (prego_model_load_anticipation)");
+        if (ant->workspace == nullptr || (reinterpret_cast<uintptr_t>(ant->workspace) & 1023) != 0)
+            return fail(PREGO_ERR_INVALID, "anticipation workspace must be non-NULL and 1024-byte aligned");
+        if (h16 && (static_cast<int64_t>(m->ant_len) * H) % 256 != 0)
+            return fail(PREGO_ERR_INVALID, "16-bit anticipation path needs anticipation_length * hidden_dim %% 256 == 0; use PREGO_PREC_FP32");
+        const int64_t need_rows = B * Tc < 128 ? B * Tc : 128;
+        if (ant_slab_rows(m, ant, a->precision, B * Tc) < need_rows)
+            return fail(PREGO_ERR_WORKSPACE, "anticipation workspace too small: need %lld bytes for a %lld-row slab, got %zu",
+                        (long long)(need_rows * ant_row_bytes(m, a->precision)), (long long)need_rows, ant->workspace_bytes);
+    }
+    const bool online = ant == nullptr && h16 && T == 1 && B <= kOnlineMaxRows && d.d_rgb % 2 == 0 && m->din % 8 == 0 &&
                         a->feature_dtype == PREGO_FEAT_F32 && !a->flow_is_zero;
     if (online && a->h_state != nullptr) {
         h_cur = a->h_state;  // per-frame path: read the caller's state in place (one copy back instead of two)
@@ -924,12 +1004,75 @@ int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_
             else RC_TRY(online_step<1>(m, a, p, ws, h_cur, h_alt, s));
             continue;
         }
-        if (a->precision == PREGO_PREC_F16) RC_TRY(chunk_16<0>(m, a, p, ws, h_cur, h_alt, t0, tc, s, ci, overlap, t_next, tc_next));
-        else if (a->precision == PREGO_PREC_BF16) RC_TRY(chunk_16<1>(m, a, p, ws, h_cur, h_alt, t0, tc, s, ci, overlap, t_next, tc_next));
-        else RC_TRY(chunk_f32(m, a, p, ws, h_cur, h_alt, t0, tc, s));
+        if (a->precision == PREGO_PREC_F16) RC_TRY(chunk_16<0>(m, a, p, ws, h_cur, h_alt, t0, tc, s, ci, overlap, t_next, tc_next, ant));
+        else if (a->precision == PREGO_PREC_BF16) RC_TRY(chunk_16<1>(m, a, p, ws, h_cur, h_alt, t0, tc, s, ci, overlap, t_next, tc_next, ant));
+        else RC_TRY(chunk_f32(m, a, p, ws, h_cur, h_alt, t0, tc, s, ant));
     }
     if (a->h_state != nullptr && h_cur != a->h_state)
         CUDA_TRY(cudaMemcpyAsync(a->h_state, h_cur, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, s));
+    return PREGO_OK;
+}
+
+int prego_forward(prego_model_t* m, const prego_forward_args_t* a, void* stream_) { return forward_impl(m, a, nullptr, stream_); }
+
+int prego_forward_anticipation(prego_model_t* m, const prego_forward_args_t* a, const prego_anticipation_args_t* ant, void* stream_) {
+    if (ant == nullptr) return fail(PREGO_ERR_INVALID, "anticipation args is NULL");
+    return forward_impl(m, a, ant, stream_);
+}
+
+int prego_model_load_anticipation(prego_model_t* m, int32_t A, const float* w, const float* b, void* stream_) {
+    RC_TRY(check_model(m, false));
+    if (A <= 0 || A > 1024) return fail(PREGO_ERR_INVALID, "anticipation_length must be in [1, 1024] (got %d)", A);
+    if (w == nullptr || b == nullptr) return fail(PREGO_ERR_INVALID, "anticipation weight / bias pointer is NULL");
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    CUDA_TRY(cudaSetDevice(m->device));
+    const int64_t H = m->d.hidden_dim, n = (int64_t)A * H * H;
+    if (A != m->ant_len) {
+        CUDA_TRY(cudaStreamSynchronize(s));  // nothing may still read the old copies
+        for (void* p : {(void*)m->wa_f32, (void*)m->ba, m->wa_16[0], m->wa_16[1]})
+            if (p != nullptr) cudaFree(p);
+        m->wa_f32 = m->ba = nullptr;
+        m->wa_16[0] = m->wa_16[1] = nullptr;
+        m->ant_len = 0;
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->wa_f32), n * 4));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->ba), (int64_t)A * H * 4));
+        CUDA_TRY(cudaMalloc(&m->wa_16[0], n * 2));
+        CUDA_TRY(cudaMalloc(&m->wa_16[1], n * 2));
+    }
+    CUDA_TRY(cudaMemcpyAsync(m->wa_f32, w, n * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(m->ba, b, (int64_t)A * H * 4, cudaMemcpyDeviceToDevice, s));
+    f32_to_16<0><<<grid_for(n, 256, m->sm_count), 256, 0, s>>>(w, static_cast<__half*>(m->wa_16[0]), n);
+    f32_to_16<1><<<grid_for(n, 256, m->sm_count), 256, 0, s>>>(w, static_cast<__nv_bfloat16*>(m->wa_16[1]), n);
+    LAUNCH_CHECK("anticipation weight packing");
+    m->ant_len = A;
+    return PREGO_OK;
+}
+
+size_t prego_anticipation_workspace_bytes(const prego_model_t* m, int64_t slab_rows, int32_t precision) {
+    if (m == nullptr || m->ant_len <= 0 || slab_rows <= 0) return 0;
+    return static_cast<size_t>(align_up(slab_rows * ant_row_bytes(m, precision), 1024));
+}
+
+size_t prego_ap_workspace_bytes(int64_t N, int32_t K) {
+    if (N <= 0 || K <= 0) return 0;
+    return static_cast<size_t>(2 * align_up(N * K * 4, 1024));
+}
+
+int prego_perframe_ap(const float* scores, const float* targets, const int32_t* target_labels, int64_t N, int32_t K, double* ap,
+                      int64_t* num_pos, void* workspace, size_t workspace_bytes, int32_t* err_flag, void* stream) {
+    if (scores == nullptr || (targets == nullptr && target_labels == nullptr) || ap == nullptr || num_pos == nullptr || err_flag == nullptr)
+        return fail(PREGO_ERR_INVALID, "NULL pointer argument");
+    if (N <= 0 || N >= (int64_t(1) << 31) || K <= 0 || K > 65535) return fail(PREGO_ERR_INVALID, "need 0 < N < 2^31 frames and 0 < K <= 65535 classes (got N=%lld, K=%d)", (long long)N, K);
+    if (workspace == nullptr || workspace_bytes < prego_ap_workspace_bytes(N, K))
+        return fail(PREGO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", prego_ap_workspace_bytes(N, K), workspace_bytes);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint32_t* keys_a = static_cast<uint32_t*>(workspace);
+    uint32_t* keys_b = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + align_up(N * K * 4, 1024));
+    int64_t gx = (N + 31) / 32;
+    if (gx > 148 * 16) gx = 148 * 16;
+    ap_build_keys<<<dim3((unsigned)gx, (K + 31) / 32), 256, 0, s>>>(scores, targets, target_labels, N, K, keys_a, err_flag);
+    ap_sort_scan_kernel<<<K, kApThreads, 0, s>>>(keys_a, keys_b, N, ap, num_pos);
+    LAUNCH_CHECK("perframe_ap kernels");
     return PREGO_OK;
 }
 

@@ -359,6 +359,7 @@ struct EpiStore {
     int64_t ldc;
     int Tc, B;          // Tc == 0: no re-ordering
     int accumulate = 0; // fp32 output only: out += acc (+ bias)
+    int relu = 0;       // out = max(acc + bias, 0)  (anticipation layer of MROADA, rnn.py:125-126)
 
     __device__ __forceinline__ void operator()(uint32_t taddr, int row, int n0, bool valid) const {
         const int64_t orow = Tc > 0 ? static_cast<int64_t>(row % Tc) * B + row / Tc : row;
@@ -377,6 +378,10 @@ struct EpiStore {
                 f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
                 f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
                 f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+            }
+            if (relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
             if constexpr (OUT_FMT < 0) {
                 float4* d4 = reinterpret_cast<float4*>(static_cast<float*>(out) + orow * ldc + n0 + c * 32);
@@ -417,6 +422,8 @@ struct EpiHead {
     float* logits;      // [B, T, K] or nullptr
     int32_t* labels;    // [B, T] or nullptr
     int K, B, T, t0;
+    int A = 1;          // anticipation head (rnn.py:125-126): input row = row0 + row = m * A + a, output [B, T, A, .]
+    int64_t row0 = 0;
 
     __device__ __forceinline__ void operator()(uint32_t taddr, int row, int /*n0*/, bool valid) const {
         float v[TILE_N];
@@ -429,7 +436,13 @@ struct EpiHead {
             for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(u[j]);
         }
         if (!valid) return;
-        const int64_t g = static_cast<int64_t>(row % B) * T + t0 + (row / B);
+        int64_t g;
+        if (A == 1) {
+            g = static_cast<int64_t>(row % B) * T + t0 + (row / B);
+        } else {
+            const int64_t r = row0 + row, mrow = r / A;
+            g = ((mrow % B) * T + t0 + mrow / B) * A + (r - mrow * A);
+        }
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < TILE_N; ++j) {

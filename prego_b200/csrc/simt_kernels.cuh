@@ -191,6 +191,7 @@ struct SgemmA {
     int remap;        // 1: row m -> chunk_row_to_global(m, Tc, T, t0)
     int Tc, T, t0;
     int64_t ldw = 0;  // row stride of W (0 = K)
+    int relu = 0;     // C = max(acc + bias, 0)
 };
 
 __global__ void __launch_bounds__(256)
@@ -269,7 +270,10 @@ sgemm_nt_f32(SgemmA A, const float* __restrict__ W, const float* __restrict__ bi
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-            if (n < N) C[static_cast<int64_t>(m) * ldc + n] = acc[i][j] + (bias != nullptr ? __ldg(bias + n) : 0.f);
+            if (n < N) {
+                const float v = acc[i][j] + (bias != nullptr ? __ldg(bias + n) : 0.f);
+                C[static_cast<int64_t>(m) * ldc + n] = A.relu ? fmaxf(v, 0.f) : v;
+            }
         }
     }
 }
@@ -301,12 +305,14 @@ gru_gates_f32(const float* __restrict__ gi, const float* __restrict__ gh, float*
 // softmax + first-max argmax over K classes, one warp per frame (exact-fp32 mode head).
 __global__ void __launch_bounds__(256)
 softmax_argmax_f32(const float* __restrict__ logits_chunk, float* __restrict__ probs, float* __restrict__ logits_out,
-                   int32_t* __restrict__ labels, int64_t Mc, int K, int Tc, int T, int t0) {
+                   int32_t* __restrict__ labels, int64_t Mc, int K, int Tc, int T, int t0, int A = 1, int64_t row0 = 0) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     for (int64_t m = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; m < Mc; m += warps) {
         const float* src = logits_chunk + m * K;
-        const int64_t g = chunk_row_to_global(m, Tc, T, t0);
+        // anticipation head: chunk row = (row0 + m) / A, output rows [B, T, A]
+        const int64_t g = A == 1 ? chunk_row_to_global(m, Tc, T, t0)
+                                 : chunk_row_to_global((row0 + m) / A, Tc, T, t0) * A + (row0 + m) % A;
         float mx = -INFINITY;
         for (int j = lane; j < K; j += 32) mx = fmaxf(mx, src[j]);
 #pragma unroll

@@ -84,6 +84,7 @@ class MROAD(nn.Module):
         self._packed_key = None
         self._workspace = None
         self._train_ws = None
+        self._ant_workspace = None
         self.last_labels = None  # int32 [B, T] labels of the last forward (fused argmax)
 
     # ------------------------------------------------------------------ C-ABI plumbing
@@ -143,13 +144,15 @@ class MROAD(nn.Module):
     # ------------------------------------------------------------------------ inference
     @torch.no_grad()
     def infer(self, rgb_input, flow_input, h_state=None, want_probs=True, want_logits=False, want_labels=True,
-              precision=None, chunk_T=None, out=None, zero_flow=False):
+              precision=None, chunk_T=None, out=None, zero_flow=False, want_anticipation=False,
+              want_anticipation_logits=False):
         """Run the CUDA path.  rgb/flow: CUDA tensors [B, T, D], fp32 (the reference loader's format) or already in the
         16-bit operand format of ``precision`` (torch.float16 for 'fp16', torch.bfloat16 for 'bf16': same results, no
         staging pass, half the bytes).  ``zero_flow``: the caller asserts the flow stream is all zero, as the shipped
         configs feed it (datasets/dataset.py:63-69); ``flow_input`` may then be None and its half of the projection
         is skipped (bit-identical to passing zeros).  ``h_state`` ([B, H] fp32 CUDA) is updated in place when given
-        (streaming / time-chunked online inference)."""
+        (streaming / time-chunked online inference).  ``want_anticipation`` / ``want_anticipation_logits`` (MROADA only)
+        add ``anticipation_probs`` / ``anticipation_logits`` [B, T, A, K] and ``anticipation_labels`` [B, T, A]."""
         ref = rgb_input if self.use_rgb else flow_input
         if not isinstance(ref, torch.Tensor) or not ref.is_cuda:
             raise RuntimeError("prego_b200.MROAD runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
@@ -198,8 +201,27 @@ class MROAD(nn.Module):
                 labels.data_ptr() if labels is not None else None,
                 ws_ptr, need, prec, chunk_T, _lib.FEAT_F32 if feat_dtype == torch.float32 else _lib.FEAT_16, 1 if zero_flow else 0)
             stream = torch.cuda.current_stream(device).cuda_stream
-            _lib.check(lib.prego_forward(self._handle, C.byref(args), stream), "prego_forward")
-        return {"probs": probs, "logits": logits, "labels": labels}
+            if not (want_anticipation or want_anticipation_logits):
+                _lib.check(lib.prego_forward(self._handle, C.byref(args), stream), "prego_forward")
+                return {"probs": probs, "logits": logits, "labels": labels}
+            A = int(getattr(self, "anticipation_length", 0))
+            if A <= 0:
+                raise RuntimeError("anticipation outputs need the MROADA module (model: MiniROADA)")
+            ant_probs = torch.empty(B, T, A, K, dtype=torch.float32, device=device) if want_anticipation else None
+            ant_logits = torch.empty(B, T, A, K, dtype=torch.float32, device=device) if want_anticipation_logits else None
+            ant_labels = torch.empty(B, T, A, dtype=torch.int32, device=device)
+            slab = min(B * chunk_T, int(self.anticipation_slab_rows))  # rows of the [rows, A * H] activation alive at once
+            ant_need = lib.prego_anticipation_workspace_bytes(self._handle, slab, prec)
+            if self._ant_workspace is None or self._ant_workspace.device != device or self._ant_workspace.numel() < ant_need + 1024:
+                self._ant_workspace = None
+                self._ant_workspace = torch.empty(ant_need + 1024, dtype=torch.uint8, device=device)
+            aws = self._ant_workspace.data_ptr() + (-self._ant_workspace.data_ptr()) % 1024
+            ant = _lib.AnticipationArgs(ant_probs.data_ptr() if ant_probs is not None else None,
+                                        ant_logits.data_ptr() if ant_logits is not None else None,
+                                        ant_labels.data_ptr(), aws, ant_need)
+            _lib.check(lib.prego_forward_anticipation(self._handle, C.byref(args), C.byref(ant), stream), "prego_forward_anticipation")
+        return {"probs": probs, "logits": logits, "labels": labels, "anticipation_probs": ant_probs,
+                "anticipation_logits": ant_logits, "anticipation_labels": ant_labels}
 
     def online_session(self, num_streams: int, device=None, precision=None, want_probs=False, host_labels=False):
         """Strict per-frame online inference: ``session.step(rgb_frame, flow_frame) -> labels`` with the GRU state
@@ -237,6 +259,99 @@ class MROAD(nn.Module):
         out = self.infer(rgb_input, flow_input, want_probs=True, want_labels=True)
         self.last_labels = out["labels"]
         return {"logits": out["probs"]}
+
+
+_ANT_KEYS = ("anticipation_layer.0.weight", "anticipation_layer.0.bias")
+
+
+@META_ARCHITECTURES.register("MiniROADA")
+class MROADA(MROAD):
+    """B200-native MiniROADA (``rnn.py:73-137``): the MROAD trunk plus the anticipation head
+    ``anticipation_layer = Linear(H, A * H)`` whose A hidden vectors per frame go through the SAME classifier.
+
+    Constructor contract of the reference (``rnn.py:76-110``): reads ``no_flow, no_rgb, rgb_type, flow_type,
+    embedding_dim, hidden_dim, num_layers, anticipation_length, num_classes, dropout, actionness``; parameters are
+    created in the reference's order (layer1, [f_actionness], gru, f_classification, anticipation_layer), so the
+    same ``torch.manual_seed`` gives the same default initialisation and ``state_dict`` has the same 12 (14 with
+    ``actionness``) tensors.  ``f_actionness`` is a parameter container only, exactly as in the reference, whose
+    forward never calls it (``rnn.py:112-137``).  Eval-mode forward returns ``{'logits': softmax [B, T, K],
+    'anticipation_logits': softmax [B, T, A, K]}`` (``rnn.py:132-135``).  Inference only: the train-mode forward
+    raises (the anticipation training loop and its dataset are outside the hot path)."""
+
+    def __init__(self, cfg):
+        nn.Module.__init__(self)
+        self.use_flow = not cfg["no_flow"]
+        self.use_rgb = not cfg["no_rgb"]
+        self.d_rgb = FEATURE_SIZES[cfg["rgb_type"]] if self.use_rgb else 0
+        self.d_flow = FEATURE_SIZES[cfg["flow_type"]] if self.use_flow else 0
+        self.input_dim = self.d_rgb + self.d_flow
+        self.embedding_dim = cfg["embedding_dim"]
+        self.hidden_dim = cfg["hidden_dim"]
+        self.num_layers = cfg["num_layers"]
+        self.anticipation_length = int(cfg["anticipation_length"])
+        self.out_dim = cfg["num_classes"]
+        if self.num_layers != 1:
+            raise ValueError("prego_b200 implements the shipped 1-layer GRU (configs/*.yaml: num_layers 1)")
+        if self.anticipation_length < 1:
+            raise ValueError("anticipation_length must be >= 1")
+        self.layer1 = nn.Sequential(
+            nn.Linear(self.input_dim, self.embedding_dim),
+            nn.LayerNorm(self.embedding_dim),
+            nn.ReLU(),
+            nn.Dropout(p=cfg["dropout"]),
+        )
+        self.actionness = cfg["actionness"]
+        if self.actionness:
+            self.f_actionness = nn.Sequential(nn.Linear(self.hidden_dim, 1))
+        self.relu = nn.ReLU()
+        self.gru = nn.GRU(self.embedding_dim, self.hidden_dim, self.num_layers, batch_first=True)
+        self.f_classification = nn.Sequential(nn.Linear(self.hidden_dim, self.out_dim))
+        self.anticipation_layer = nn.Sequential(nn.Linear(self.hidden_dim, self.anticipation_length * self.hidden_dim))
+
+        self.precision = cfg.get("precision", "fp16")
+        self.train_precision = cfg.get("train_precision", "fp32")
+        self.chunk_frames = int(cfg.get("chunk_frames", 1 << 17))
+        self._handle = None
+        self._handle_device = None
+        self._packed_key = None
+        self._ant_key = None
+        self._workspace = None
+        self._train_ws = None
+        self._ant_workspace = None
+        self.last_labels = None
+        self.last_anticipation_labels = None  # int32 [B, T, A]
+        self.anticipation_slab_rows = int(cfg.get("anticipation_slab_rows", 16384))
+
+    def _release(self):
+        super()._release()
+        self._ant_key = None
+
+    def _sync_weights(self, lib, device):
+        super()._sync_weights(lib, device)
+        lin = self.anticipation_layer[0]
+        key = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
+        if key == self._ant_key:
+            return
+        for k, t in zip(_ANT_KEYS, (lin.weight, lin.bias)):
+            if t.device != device or t.dtype != torch.float32:
+                raise RuntimeError(f"parameter {k} must be fp32 on {device} (got {t.dtype} on {t.device}); call model.to(device)")
+        w, b = lin.weight.detach().contiguous(), lin.bias.detach().contiguous()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(lib.prego_model_load_anticipation(self._handle, self.anticipation_length, w.data_ptr(), b.data_ptr(), stream),
+                   "prego_model_load_anticipation")
+        self._ant_key = key
+
+    def online_session(self, *args, **kwargs):
+        raise RuntimeError("per-frame online sessions serve the MROAD head only; use MROADA.infer(..., want_anticipation=True)")
+
+    def forward(self, rgb_input, flow_input):
+        """rnn.py:112-137, eval mode."""
+        if self.training:
+            raise RuntimeError("prego_b200.MROADA is inference-only (call model.eval()); training covers MiniROAD (MROAD)")
+        out = self.infer(rgb_input, flow_input, want_probs=True, want_labels=True, want_anticipation=True)
+        self.last_labels = out["labels"]
+        self.last_anticipation_labels = out["anticipation_labels"]
+        return {"logits": out["probs"], "anticipation_logits": out["anticipation_probs"]}
 
 
 class OnlineSession:

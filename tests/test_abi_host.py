@@ -31,7 +31,7 @@ def test_header_symbols_all_exported(lib):
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in include/prego_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes prototypes out of sync with the header"
-    assert lib.prego_abi_version() == 2
+    assert lib.prego_abi_version() == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -118,7 +118,7 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
     if cc is None:
         pytest.skip("no host C compiler")
     pairs = {"prego_dims_t": _lib.Dims, "prego_weights_t": _lib.Weights, "prego_forward_args_t": _lib.ForwardArgs,
-             "prego_grads_t": _lib.Grads, "prego_train_args_t": _lib.TrainArgs, "prego_adamw_args_t": _lib.AdamWArgs}
+             "prego_anticipation_args_t": _lib.AnticipationArgs, "prego_grads_t": _lib.Grads, "prego_train_args_t": _lib.TrainArgs, "prego_adamw_args_t": _lib.AdamWArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "prego_b200.h"', 'int main(void) {']
     for cname, ct in pairs.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')

@@ -1,0 +1,97 @@
+"""SURVEY 8f rank 4 on the CPU: the oracle restatements (MiniROADA forward, sklearn average precision) against the
+golden vectors the reference itself produced (oracle/gen_golden_rank4.py), and the host-side contract of the
+MROADA module / ANT evaluator mirror (no compute without a GPU)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD
+from oracle import metrics_np, miniroad_np
+from oracle.map_cases import map_cases, one_hot
+
+import prego_b200
+from prego_b200 import synthetic
+
+
+@pytest.fixture(scope="module")
+def meta4():
+    return json.load(open(os.path.join(GOLD, "meta_rank4.json")))
+
+
+def ant_case(meta4, name):
+    """(cfg, seeded MROADA whose tensors hash to the reference's seeded init, rgb, flow, golden arrays)."""
+    c = meta4["anticipation"][name]
+    cfg = dict(getattr(synthetic, c["cfg"]), model="MiniROADA", **c["overrides"])
+    torch.manual_seed(meta4["seed"])
+    m = prego_b200.MROADA(cfg)
+    sha = lambda t: hashlib.sha256(t.detach().contiguous().numpy().tobytes()).hexdigest()
+    # (the key ORDER is asserted against the live reference by the generator; the JSON stores them sorted)
+    assert sorted(m.state_dict().keys()) == sorted(c["weights_sha256"].keys()), "state_dict keys differ from the reference"
+    for k, v in m.state_dict().items():
+        assert sha(v) == c["weights_sha256"][k], f"seeded weight {k} differs from the reference's"
+    rgb, flow = synthetic.feature_batch(c["stream_ids"], c["T"], "cpu", False)
+    assert sha(rgb) == c["rgb_sha256"] and sha(flow) == c["flow_sha256"], "synthetic feature generator drifted"
+    z = np.load(os.path.join(GOLD, f"anticipation_{name}.npz"))
+    return cfg, m, rgb, flow, {k: z[k] for k in z.files}
+
+
+ANT_NAMES = ["epic_a4_b2_t40", "asm_a2_b3_t24_act", "asm_a3_b20_t6"]
+
+
+@pytest.mark.parametrize("name", ANT_NAMES)
+def test_anticipation_restatement_matches_reference(meta4, name):
+    cfg, m, rgb, flow, gold = ant_case(meta4, name)
+    probs, ant_probs, logits, ant_logits = miniroad_np.forward_anticipation(
+        m.state_dict(), rgb.numpy(), flow.numpy(), cfg["anticipation_length"])
+    assert ant_probs.shape == gold["ant_probs"].shape == (rgb.shape[0], rgb.shape[1], cfg["anticipation_length"], cfg["num_classes"])
+    # fp32 restatement vs ATen fp32: summation order only
+    assert np.abs(logits - gold["logits"]).max() <= 1e-4 * np.abs(gold["logits"]).max()
+    assert np.abs(ant_logits - gold["ant_logits"]).max() <= 1e-4 * np.abs(gold["ant_logits"]).max()
+    assert np.abs(probs - gold["probs"]).max() <= 2e-6
+    assert np.abs(ant_probs - gold["ant_probs"]).max() <= 2e-6
+
+
+def test_mroada_module_contract(meta4):
+    cfg, m, _, _, _ = ant_case(meta4, "asm_a2_b3_t24_act")
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert shapes["anticipation_layer.0.weight"] == (2 * 1024, 1024) and shapes["anticipation_layer.0.bias"] == (2048,)
+    assert shapes["f_actionness.0.weight"] == (1, 1024)  # cfg actionness: container only, as in the reference
+    assert len(shapes) == 14
+    assert isinstance(prego_b200.build_model(cfg, None), prego_b200.MROADA)
+    assert prego_b200.EVAL["ANTICIPATION"] is prego_b200.ANT_Evaluate
+    x = torch.zeros(1, 4, 2048)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.eval()(x, x)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m.train()(x, x)
+
+
+def test_map_case_inputs_regenerate_bit_identically(meta4):
+    for name, scores, labels in map_cases():
+        c = meta4["map"][name]
+        assert hashlib.sha256(scores.tobytes()).hexdigest() == c["scores_sha256"], name
+        assert hashlib.sha256(labels.tobytes()).hexdigest() == c["labels_sha256"], name
+
+
+def test_average_precision_restatement_matches_reference(meta4):
+    gold = np.load(os.path.join(GOLD, "map_cases.npz"))
+    for name, scores, labels in map_cases():
+        K = scores.shape[1]
+        r = metrics_np.perframe_average_precision(scores, one_hot(labels, K), [str(i) for i in range(K)])
+        want = gold[f"{name}.ap"]
+        assert [int(k) for k in r["per_class_AP"]] == [k for k in range(1, K) if not np.isnan(want[k])], name
+        for k, v in r["per_class_AP"].items():
+            assert abs(v - want[int(k)]) <= 1e-12, (name, k)
+        assert abs(r["mean_AP"] - float(gold[f"{name}.mean_ap"])) <= 1e-12
+        assert len(r["per_class_AP"]) == meta4["map"][name]["classes_scored"]
+
+
+def test_metrics_need_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("no-GPU failure mode")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        prego_b200.perframe_average_precision(torch.rand(8, 3), torch.zeros(8, dtype=torch.int32), ["a", "b", "c"])
