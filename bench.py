@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
+    ap.add_argument("--no-rank4", action="store_true", help="skip the MiniROADA anticipation / device mAP leg (SURVEY 8f rank 4)")
     ap.add_argument("--no-variants", action="store_true", help="skip the feature-format variants (16-bit features, zero flow)")
     ap.add_argument("--subchunk", type=int, default=64,
                     help="internal time-chunk of prego_forward inside one step; < --chunk stages the features of chunk c+1 on a side "
@@ -300,6 +301,58 @@ def training_leg(dev, world):
     return out
 
 
+# ----------------------------------------------------------------------------- SURVEY 8f rank 4 leg
+def rank4_leg(dev):
+    """MiniROADA (rnn.py:73-137) anticipation inference and the device per-frame mAP (utils/metrics.py:25-62), one GPU.
+    Anticipation: 1 024 streams x 64 frames, A = 4 (no shipped config selects MiniROADA, so A is ours), fp16 operands,
+    probabilities [B, T, A, K] materialised.  mAP: the 262 144 x 86 probabilities of one bench step."""
+    from prego_b200 import MROADA, synthetic
+    from prego_b200.metrics import average_precision_per_class
+    out = {}
+    A, B, T, K = 4, 1024, 64, 86
+    cfg = dict(synthetic.ASSEMBLY101_O, model="MiniROADA", anticipation_length=A, actionness=False)
+    torch.manual_seed(20)
+    model = MROADA(cfg).to(dev).eval()
+    rgb, flow = synthetic.device_features(B, T, dev, seed=11)
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, r
+
+    ms_ant, _ = timed(lambda: model.infer(rgb, flow, want_probs=False, want_anticipation=True), 5)
+    ms_plain, _ = timed(lambda: model.infer(rgb, flow, want_probs=False), 5)
+    extra_flop = (2 * 1024 * A * 1024 + 2 * 1024 * K * A) * B * T  # anticipation layer + A classifier rows per frame
+    out["anticipation"] = {"streams": B, "frames": T, "anticipation_length": A, "ms": ms_ant, "frames_per_s": B * T / ms_ant * 1e3,
+                           "ms_trunk_only": ms_plain, "head_tflops": extra_flop / max(ms_ant - ms_plain, 1e-6) / 1e9,
+                           "note": "prego_forward_anticipation, fp16 operands; head_tflops = (anticipation layer + A classifier rows) / (ms - ms_trunk_only), "
+                                   "includes writing the [B, T, A, K] fp32 probabilities (90 MB)"}
+    del rgb, flow, model
+    N = 262144
+    g = torch.Generator(device=dev).manual_seed(5)
+    scores = torch.softmax(torch.randn(N, K, generator=g, device=dev) * 3, -1)
+    labels = torch.randint(0, K, (N,), generator=g, device=dev, dtype=torch.int32)
+    ms_ap, (ap, _) = timed(lambda: average_precision_per_class(scores, labels), 5)
+    from sklearn.metrics import average_precision_score  # what the reference calls per class on the host (metrics.py:43,55)
+    s_h, l_h = scores[:, 1].cpu().numpy(), labels.cpu().numpy() == 1
+    t0 = time.perf_counter()
+    ref = average_precision_score(l_h, s_h)
+    host_ms = (time.perf_counter() - t0) * 1e3
+    assert abs(ref - ap[1]) <= 1e-12, "device AP differs from sklearn"
+    out["perframe_map"] = {"frames": N, "classes": K, "ms": ms_ap, "algorithmic_gbs": N * K * 64 / ms_ap / 1e6,
+                           "mean_ap": float(np.nanmean(ap[1:])), "host_sklearn_ms_per_class": host_ms,
+                           "note": "prego_perframe_ap incl. the K-double D2H; 64 algorithmic bytes per (frame, class): 4-pass LSD radix sort + scan; "
+                                   "the reference runs sklearn once per class on the host (85 classes here); class 1 checked against it to 1e-12"}
+    return out
+
+
 # ----------------------------------------------------------------------------- main arm
 def run_ours(args, world, rank, local):
     import torch.distributed as dist
@@ -518,6 +571,11 @@ def run_ours(args, world, rank, local):
         torch.cuda.empty_cache()
         lat = latency_leg(dev, args.precision)
 
+    rank4 = None
+    if not args.no_rank4 and world == 1:
+        torch.cuda.empty_cache()
+        rank4 = rank4_leg(dev)
+
     cpu = None
     if not args.no_cpu and world == 1:
         v, sample, cores = cpu_baseline_run(B, Tc)
@@ -531,7 +589,7 @@ def run_ours(args, world, rank, local):
                        "l2_policy": "inputs larger than L2 (4 GiB of features per step vs 126 MB L2)",
                        "weights": "seed-20 default init (no checkpoint ships with the reference)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "single_stream": lat, "train_step": train, "feature_formats": variants}
+            "single_stream": lat, "train_step": train, "feature_formats": variants, "rank4": rank4}
     emit(line)
     if world > 1:
         dist.barrier()

@@ -237,8 +237,9 @@ int prego_forward_anticipation(prego_model_t* model, const prego_forward_args_t*
  *     order frames by score descending; at each DISTINCT score threshold n: P_n = tp_n / (tp_n + fp_n),
  *     R_n = tp_n / positives;  ap[k] = sum_n (R_n - R_{n-1}) * P_n                      (float64)
  * num_pos[k] = positives of class k (ap[k] is NaN when 0: the reference skips such classes, metrics.py:54).
- * Class 0 (background) is computed too; the caller drops it (metrics.py:47,53).  One CTA per class: 8-bit LSD radix
- * sort of the 31-bit keys (score bits << 1 | positive) in `workspace`, then one scan over the sorted keys.
+ * Class 0 (background) is computed too; the caller drops it (metrics.py:47,53).  Every class is cut into slices so
+ * that the whole machine works on it: four stable 8-bit LSD radix passes over the 31-bit keys (score bits << 1 |
+ * positive) in `workspace`, then a sliced scan over the sorted keys (16 launches in all, on `stream`).
  * err_flag (device int, caller-zeroed) becomes 1 if a score is outside [0, 1] or NaN. */
 size_t prego_ap_workspace_bytes(int64_t N, int32_t K);
 int prego_perframe_ap(const float* scores, const float* targets, const int32_t* target_labels, int64_t N, int32_t K,

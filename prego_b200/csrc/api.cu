@@ -1055,7 +1055,9 @@ size_t prego_anticipation_workspace_bytes(const prego_model_t* m, int64_t slab_r
 
 size_t prego_ap_workspace_bytes(int64_t N, int32_t K) {
     if (N <= 0 || K <= 0) return 0;
-    return static_cast<size_t>(2 * align_up(N * K * 4, 1024));
+    const int64_t S = ap_num_slices(N, K);
+    // two key buffers | digit counts [K][256][S] | slice partials {positives, last threshold} | float64 slice sums
+    return static_cast<size_t>(2 * align_up(N * K * 4, 1024) + align_up((int64_t)K * 256 * S * 4, 1024) + 2 * align_up((int64_t)K * S * 8, 1024));
 }
 
 int prego_perframe_ap(const float* scores, const float* targets, const int32_t* target_labels, int64_t N, int32_t K, double* ap,
@@ -1065,13 +1067,31 @@ int prego_perframe_ap(const float* scores, const float* targets, const int32_t* 
     if (N <= 0 || N >= (int64_t(1) << 31) || K <= 0 || K > 65535) return fail(PREGO_ERR_INVALID, "need 0 < N < 2^31 frames and 0 < K <= 65535 classes (got N=%lld, K=%d)", (long long)N, K);
     if (workspace == nullptr || workspace_bytes < prego_ap_workspace_bytes(N, K))
         return fail(PREGO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", prego_ap_workspace_bytes(N, K), workspace_bytes);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return fail(PREGO_ERR_INVALID, "workspace must be 16-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    uint32_t* keys_a = static_cast<uint32_t*>(workspace);
-    uint32_t* keys_b = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(workspace) + align_up(N * K * 4, 1024));
+    const int S = ap_num_slices(N, K);
+    const int64_t L = ap_slice_len(N, S);
+    uint8_t* w = static_cast<uint8_t*>(workspace);
+    uint32_t* keys_a = reinterpret_cast<uint32_t*>(w);
+    uint32_t* keys_b = reinterpret_cast<uint32_t*>(w += align_up(N * K * 4, 1024));
+    uint32_t* hist = reinterpret_cast<uint32_t*>(w += align_up(N * K * 4, 1024));
+    uint2* part = reinterpret_cast<uint2*>(w += align_up((int64_t)K * 256 * S * 4, 1024));
+    double* acc_part = reinterpret_cast<double*>(w += align_up((int64_t)K * S * 8, 1024));
     int64_t gx = (N + 31) / 32;
     if (gx > 148 * 16) gx = 148 * 16;
-    ap_build_keys<<<dim3((unsigned)gx, (K + 31) / 32), 256, 0, s>>>(scores, targets, target_labels, N, K, keys_a, err_flag);
-    ap_sort_scan_kernel<<<K, kApThreads, 0, s>>>(keys_a, keys_b, N, ap, num_pos);
+    ap_build_keys<<<(unsigned)gx, 256, 0, s>>>(scores, targets, target_labels, N, K, keys_a, err_flag);
+    uint32_t *in = keys_a, *out = keys_b;
+    for (int pass = 0; pass < 4; ++pass) {  // keys are < 2^31: four 8-bit digits; the order ends up back in keys_a
+        ap_hist_kernel<<<K * S, kApThreads, 0, s>>>(in, N, S, L, 8 * pass, hist);
+        ap_offsets_kernel<<<K, 256, 0, s>>>(hist, S);
+        ap_scatter_kernel<<<K * S, kApThreads, 0, s>>>(in, out, N, S, L, 8 * pass, hist);
+        uint32_t* t = in;
+        in = out;
+        out = t;
+    }
+    ap_scan_local<<<K * S, kApThreads, 0, s>>>(in, N, S, L, part);
+    ap_scan_final<<<K * S, kApThreads, 0, s>>>(in, N, S, L, part, acc_part);
+    ap_reduce<<<(K + 127) / 128, 128, 0, s>>>(part, acc_part, K, S, ap, num_pos);
     LAUNCH_CHECK("perframe_ap kernels");
     return PREGO_OK;
 }
