@@ -23,7 +23,7 @@ constexpr int kApThreads = 256;
 constexpr int kApWarps = kApThreads / 32;
 constexpr int kApItems = 16;                         // keys per thread per tile (striped: warp w, item i, lane l)
 constexpr int kApTile = kApThreads * kApItems;       // 4096 keys
-constexpr int kApScanItems = 4;                      // consecutive positions per thread in the PR scan
+constexpr int kApScanItems = 8;                      // consecutive positions per thread in the PR scan
 constexpr uint32_t kApOneBits = 0x3F800000u;         // 1.0f
 constexpr uint32_t kApNoEnd = 0xFFFFFFFFu;
 
@@ -79,9 +79,9 @@ __device__ __forceinline__ uint32_t ap_peers8(uint32_t d, bool valid) {
     uint32_t peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
-        const bool bit = (d >> b) & 1u;
-        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? bal : ~bal;
+        const int32_t neg = static_cast<int32_t>(d << (31 - b)) >> 31;  // all ones when bit b of d is set
+        const uint32_t bal = __ballot_sync(0xffffffffu, neg < 0);
+        peers &= ~(bal ^ static_cast<uint32_t>(neg));                    // bit set: &= bal; clear: &= ~bal  (one LOP3)
     }
     return peers;
 }
@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(kApThreads, 4)
 ap_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out, int64_t N, int S, int64_t L, int shift,
                   const uint32_t* __restrict__ offsets) {
     __shared__ uint32_t base[256];             // running output cursor of every digit for this slice
-    __shared__ uint32_t whist[kApWarps][256];  // per-warp digit counts of the tile -> per-warp output offsets
+    __shared__ uint32_t delta[256];            // output index - tile-sorted index, per digit, for the current tile
+    __shared__ uint32_t whist[kApWarps][256];  // per-warp digit counts of the tile -> per-warp tile-sorted offsets
+    __shared__ uint32_t sorted[kApTile];       // the tile ordered by digit (stable)
+    __shared__ uint32_t wsum[kApWarps];
     const int k = blockIdx.x / S, s = blockIdx.x % S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -172,28 +175,59 @@ ap_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ k
             const bool valid = key[it] != 0xFFFFFFFFu;
             const uint32_t d = (key[it] >> shift) & 0xFFu;
             const uint32_t peers = ap_peers8(d, valid);
-            const uint32_t prior = valid ? whist[warp][d] : 0u;
-            __syncwarp();
             const uint32_t r = __popc(peers & lt_mask);
-            if (valid && r == 0u) whist[warp][d] = prior + __popc(peers);
-            __syncwarp();
+            // the group's first lane bumps the warp's digit counter and hands the old value to its peers.  One shared
+            // atomic per group instead of a load / store pair: the 16 items do not wait for each other's round trip
+            uint32_t prior = 0u;
+            if (valid && r == 0u) prior = atomicAdd(&whist[warp][d], static_cast<uint32_t>(__popc(peers)));
+            __syncwarp();  // item order = counter order
+            prior = __shfl_sync(0xffffffffu, prior, (__ffs(peers) - 1) & 31);
             rank[it] = static_cast<uint16_t>(prior + r);
         }
         __syncthreads();
-        {   // digit tid: counts of the warps -> offsets, cursor advanced past the tile
-            uint32_t run = base[tid];
+        {   // digit tid: tile count -> start of the digit inside the digit-sorted tile (block exclusive scan), per-warp
+            // offsets inside the tile, and the shift from tile-sorted index to output index
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int w = 0; w < kApWarps; ++w) cnt += whist[w][tid];
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            uint32_t start = inc - cnt;
+#pragma unroll
+            for (int w = 0; w < kApWarps; ++w)
+                if (w < warp) start += wsum[w];
+            uint32_t run = start;
 #pragma unroll
             for (int w = 0; w < kApWarps; ++w) {
                 const uint32_t c = whist[w][tid];
                 whist[w][tid] = run;
                 run += c;
             }
-            base[tid] = run;
+            delta[tid] = base[tid] - start;
+            base[tid] += cnt;
         }
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < kApItems; ++it)
-            if (key[it] != 0xFFFFFFFFu) out[whist[warp][(key[it] >> shift) & 0xFFu] + rank[it]] = key[it];
+            if (key[it] != 0xFFFFFFFFu) sorted[whist[warp][(key[it] >> shift) & 0xFFu] + rank[it]] = key[it];
+        __syncthreads();
+        // coalesced write-out: consecutive threads hold consecutive keys of the same digit run, which are consecutive in
+        // the output (a plain scatter costs one 32-byte sector per key on the random middle digits)
+        const int n_tile = static_cast<int>(hi - ts < kApTile ? hi - ts : kApTile);
+#pragma unroll
+        for (int it = 0; it < kApItems; ++it) {
+            const int j = it * kApThreads + tid;
+            if (j < n_tile) {
+                const uint32_t kk = sorted[j];
+                out[delta[(kk >> shift) & 0xFFu] + j] = kk;
+            }
+        }
         __syncthreads();
     }
 }
