@@ -246,6 +246,16 @@ int prego_perframe_ap(const float* scores, const float* targets, const int32_t* 
                       double* ap /*[K]*/, int64_t* num_pos /*[K]*/, void* workspace, size_t workspace_bytes,
                       int32_t* err_flag, void* stream);
 
+/* ---- Host half of the feature ingest (reference: datasets/dataset.py:120-132 hands the model fp32
+ * HOST tensors).  Rounds n fp32 values (host memory) to the 16-bit operand format of `precision` (PREGO_PREC_F16 /
+ * PREGO_PREC_BF16) with exactly the rounding the device applies in its staging pass (fp16: clamp to +-65504, NaN ->
+ * -65504, round to nearest even; bf16: round to nearest even), on `num_threads` host threads (AVX-512 / AVX2+F16C /
+ * scalar, picked at run time; prego_host_round_impl() = 2 / 1 / 0).  The result is what PREGO_FEAT_16 expects: the
+ * host->device link carries half the bytes and prego_forward returns bit-identical results.  Data-format staging only:
+ * nothing of the model is computed on the CPU.  Blocking; thread-safe. */
+int prego_host_round_features(const float* src, void* dst, int64_t n, int32_t precision, int32_t num_threads);
+int prego_host_round_impl(void);
+
 /* Building blocks exposed for parity tests and micro-benchmarks. */
 /* C[M,N] (fp32, ldc = N) = A[M,K] * W[N,K]^T + bias[N] with 16-bit operands (precision = PREGO_PREC_F16 or
  * PREGO_PREC_BF16) on the tcgen05 path; N % tile_n == 0, tile_n in {96, 128, 192, 256}, K % 64 == 0. */

@@ -85,6 +85,8 @@ SIGNATURES = {
     "prego_ap_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "prego_perframe_ap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "prego_host_round_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
+    "prego_host_round_impl": (C.c_int, []),
     "prego_online_open": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_void_p)]),
     "prego_online_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

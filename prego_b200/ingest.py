@@ -22,8 +22,13 @@ import os.path as osp
 from dataclasses import dataclass
 from typing import Dict, Iterator, List, Optional, Sequence, Tuple
 
+import ctypes as C
+import threading
+
 import numpy as np
 import torch
+
+from . import _lib
 
 OPERAND_DTYPES = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}
 _F16_MAX = 65504.0
@@ -214,3 +219,114 @@ def predict_labels_streamed(model, store: FeatureStore, device, batch_streams: i
             v = store.videos[i]
             out[v.vid] = labels[j, : v.T].clone()
     return {v.vid: out[v.vid] for v in store.videos}
+
+
+def round_features_host(src: torch.Tensor, dst: torch.Tensor, precision: str = "fp16", threads: Optional[int] = None) -> torch.Tensor:
+    """fp32 host tensor -> the 16-bit operand format of ``precision`` in ``dst`` (host, same numel) with the device
+    path's rounding, on ``threads`` host threads (``prego_host_round_features``; releases the GIL)."""
+    if src.is_cuda or dst.is_cuda or src.dtype != torch.float32 or dst.dtype != OPERAND_DTYPES[precision] or precision == "fp32":
+        raise RuntimeError("round_features_host: fp32 host source and fp16 / bf16 host destination expected")
+    if not src.is_contiguous() or not dst.is_contiguous() or src.numel() != dst.numel():
+        raise RuntimeError("round_features_host: contiguous tensors of equal size expected")
+    _lib.check(_lib.load().prego_host_round_features(src.data_ptr(), dst.data_ptr(), src.numel(), _lib.PRECISIONS[precision],
+                                                     int(threads or os.cpu_count() or 1)), "prego_host_round_features")
+    return dst
+
+
+class HostRoundingStager:
+    """fp32 HOST feature batches -> device tensors in the 16-bit operand format, with the rounding done on the host.
+
+    The reference hands the model fp32 host tensors (``datasets/dataset.py:120-132``, ``trainer/eval.py:40-42``); end to end
+    the path is bound by the host->device link, and the first thing the device does with a feature is round it to the
+    projection GEMM's operand format.  Rounding on the host with the same rule (``prego_host_round_features``) halves
+    the bytes on the link; ``MROAD.infer`` then reads the tensors in place (``PREGO_FEAT_16``) and returns bit-identical
+    results.  A batch is cut into ``slices`` along the stream axis: slice s is copied (copy stream) while slice s + 1 is
+    rounded (host threads), and the whole batch i + 1 is staged while the device computes batch i (two slots).
+
+        stager = HostRoundingStager(B, T, d_rgb, d_flow, "fp16", device)
+        stager.submit(0, rgb_host, flow_host)                # returns at once; a worker thread rounds and copies
+        rgb16, flow16 = stager.wait(0)                       # current stream now waits for the copies
+        out = model.infer(rgb16, flow16, precision="fp16"); stager.release(0)
+    """
+
+    def __init__(self, B: int, T: int, d_rgb: int, d_flow: int, precision: str, device, slices: int = 8,
+                 threads: Optional[int] = None, slots: int = 2):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("prego_b200 ingest streams to a CUDA device; there is no CPU path")
+        if precision not in ("fp16", "bf16"):
+            raise RuntimeError("host rounding targets the 16-bit operand formats ('fp16' / 'bf16')")
+        self.precision, self.dtype = precision, OPERAND_DTYPES[precision]
+        self.B, self.T, self.dims = int(B), int(T), (int(d_rgb), int(d_flow))
+        self.threads = int(threads or os.cpu_count() or 1)
+        self.slices = max(1, min(int(slices), self.B))
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots = []
+        for _ in range(slots):
+            pin = [torch.empty(self.B, self.T, d, dtype=self.dtype).pin_memory() if d else None for d in self.dims]
+            dev = [torch.empty(self.B, self.T, d, dtype=self.dtype, device=self.device) if d else None for d in self.dims]
+            self.slots.append({"pin": pin, "dev": dev, "ready": torch.cuda.Event(), "free": torch.cuda.Event(),
+                               "issued": threading.Event(), "thread": None, "error": None})
+        main = torch.cuda.current_stream(self.device)
+        for s in self.slots:
+            s["free"].record(main)
+            s["ready"].record(main)
+
+    def _work(self, slot, srcs):
+        try:
+            lib = _lib.load()
+            prec = _lib.PRECISIONS[self.precision]
+            slot["ready"].synchronize()  # the previous copies out of this slot's pinned staging have finished
+            bounds = [self.B * i // self.slices for i in range(self.slices + 1)]
+            with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(slot["free"])  # the consumer is done with this slot's device tensors
+                for b0, b1 in zip(bounds[:-1], bounds[1:]):
+                    for src, pin, dev in zip(srcs, slot["pin"], slot["dev"]):
+                        if src is None or pin is None:
+                            continue
+                        n = (b1 - b0) * src.shape[1] * src.shape[2]
+                        _lib.check(lib.prego_host_round_features(src[b0:b1].data_ptr(), pin[b0:b1].data_ptr(), n, prec, self.threads),
+                                   "prego_host_round_features")
+                        dev[b0:b1].copy_(pin[b0:b1], non_blocking=True)
+                slot["ready"].record(self.copy_stream)
+        except Exception as e:  # surfaced by wait()
+            slot["error"] = e
+        finally:
+            slot["issued"].set()
+
+    def submit(self, i: int, rgb_host: Optional[torch.Tensor], flow_host: Optional[torch.Tensor]) -> None:
+        slot = self.slots[i % len(self.slots)]
+        srcs = []
+        for x, d in zip((rgb_host, flow_host), self.dims):
+            if x is None or d == 0:
+                srcs.append(None)
+                continue
+            if x.is_cuda or x.dtype != torch.float32 or tuple(x.shape) != (self.B, self.T, d) or not x.is_contiguous():
+                raise RuntimeError(f"expected a contiguous fp32 host tensor [{self.B}, {self.T}, {d}], got {x.dtype} {tuple(x.shape)}")
+            srcs.append(x)
+        if slot["thread"] is not None:
+            slot["thread"].join()
+        slot["issued"].clear()
+        slot["error"] = None
+        slot["flow"] = srcs[1] is not None
+        slot["thread"] = threading.Thread(target=self._work, args=(slot, srcs), daemon=True)
+        slot["thread"].start()
+
+    def wait(self, i: int):
+        """-> (rgb16, flow16 | None) device tensors of submission ``i``; the current stream waits for their copies."""
+        slot = self.slots[i % len(self.slots)]
+        slot["issued"].wait()
+        if slot["error"] is not None:
+            raise slot["error"]
+        torch.cuda.current_stream(self.device).wait_event(slot["ready"])
+        return slot["dev"][0], (slot["dev"][1] if slot.get("flow") else None)
+
+    def release(self, i: int) -> None:
+        """The consumer's work on submission ``i`` has been enqueued: its device tensors may be overwritten after it."""
+        self.slots[i % len(self.slots)]["free"].record(torch.cuda.current_stream(self.device))
+
+    def close(self):
+        for s in self.slots:
+            if s["thread"] is not None:
+                s["thread"].join()
+                s["thread"] = None

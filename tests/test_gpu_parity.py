@@ -579,3 +579,32 @@ def test_non_shipped_shapes_vs_oracle(dev, H, K, B, T):
         big.infer(rgb, flow, precision="fp16")
     with pytest.raises(RuntimeError, match="hidden_dim"):
         synthetic.seeded_model(dict(synthetic.ASSEMBLY101_O, hidden_dim=2048), seed=20, device=dev).infer(rgb, flow)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("zero_flow", [False, True])
+def test_host_rounded_ingest_bit_identical(dev, prec, zero_flow):
+    """HostRoundingStager (fp32 HOST features rounded to the operand format on the host, half the bytes over the link,
+    read in place by the device) gives bit-identical logits / labels / state to handing the fp32 features to the device,
+    over several pipelined steps with carried state."""
+    from prego_b200 import synthetic
+    from prego_b200.ingest import HostRoundingStager
+    cfg = dict(synthetic.ASSEMBLY101_O)
+    model = synthetic.seeded_model(cfg, seed=20, device=dev)
+    B, T, steps = 256, 8, 4
+    feats = [synthetic.device_features(B, T, dev, seed=40 + i, zero_flow=zero_flow) for i in range(steps)]
+    host = [(r.cpu().pin_memory(), None if zero_flow else f.cpu().pin_memory()) for r, f in feats]
+    st = HostRoundingStager(B, T, 2048, 0 if zero_flow else 2048, prec, dev, slices=5, threads=3)
+    h_a = torch.zeros(B, 1024, device=dev)
+    h_b = torch.zeros(B, 1024, device=dev)
+    st.submit(0, *host[0])
+    for i in range(steps):
+        if i + 1 < steps:
+            st.submit(i + 1, *host[i + 1])
+        r16, f16 = st.wait(i)
+        got = model.infer(r16, f16, h_state=h_b, want_logits=True, precision=prec, zero_flow=zero_flow)
+        st.release(i)
+        want = model.infer(feats[i][0], None if zero_flow else feats[i][1], h_state=h_a, want_logits=True, precision=prec, zero_flow=zero_flow)
+        assert torch.equal(got["logits"], want["logits"]) and torch.equal(got["labels"], want["labels"]), i
+    st.close()
+    assert torch.equal(h_a, h_b)

@@ -81,3 +81,43 @@ def test_streaming_needs_cuda():
     store = ingest.FeatureStore.from_arrays([("a", np.ones((4, 2048)), None, None)], "fp16", pin=False)
     with pytest.raises(RuntimeError):
         next(ingest.stream_batches(store, "cpu"))
+
+
+def _adversarial_f32(n, seed=0):
+    rs = np.random.RandomState(seed)
+    x = rs.randint(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32).view(np.float32).copy()  # every exponent, NaNs, infs
+    x[:12] = [0.0, -0.0, 65504.0, 65520.0, 1e9, -1e9, np.inf, -np.inf, np.nan, 2.0 ** -25, 2.0 ** -24, 5.96e-8]
+    return x
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_host_rounding_is_the_device_rule_bit_for_bit(prec):
+    """prego_host_round_features == Op16<FMT>::from_float (csrc/gemm_tc.cuh): fp16 clamps to +-65504 (NaN -> -65504) and
+    rounds to nearest even, bf16 rounds to nearest even; checked against torch's converters on every kind of fp32 bit
+    pattern, on the SIMD path (1 and 5 threads), on the scalar path (short calls) and at unaligned offsets."""
+    from prego_b200 import _lib
+    lib = _lib.load()
+    x = _adversarial_f32(1 << 20)
+    t = torch.from_numpy(x)
+    dt = ingest.OPERAND_DTYPES[prec]
+    if prec == "fp16":
+        want = torch.where(torch.isnan(t), torch.full_like(t, -65504.0), t).clamp(-65504.0, 65504.0).to(dt)
+    else:
+        want = t.to(dt)
+    want = want.view(torch.int16).numpy().view(np.uint16)
+    keep = ~np.isnan(x) if prec == "bf16" else np.ones(x.size, bool)  # bf16 NaN: any quiet NaN pattern
+    for threads in (1, 5):
+        got = torch.empty(x.size, dtype=dt)
+        ingest.round_features_host(t, got, prec, threads)
+        got = got.view(torch.int16).numpy().view(np.uint16)
+        assert np.array_equal(got[keep], want[keep])
+        assert np.all((got[~keep] & 0x7FFF) > 0x7F80)
+    # scalar path: calls shorter than one SIMD vector, at odd offsets
+    out = np.zeros(7, np.uint16)
+    for off in range(0, 70000, 7):
+        assert lib.prego_host_round_features(x[off:].ctypes.data, out.ctypes.data, 7, _lib.PRECISIONS[prec], 1) == 0
+        k = keep[off:off + 7]
+        assert np.array_equal(out[k], want[off:off + 7][k]), off
+    assert lib.prego_host_round_impl() in (0, 1, 2)
+    with pytest.raises(RuntimeError):
+        ingest.round_features_host(t, torch.empty(x.size, dtype=torch.float32), "fp32")
