@@ -503,15 +503,17 @@ def run_ours(args, world, rank, local):
             h2d = hr.numel() * hr.element_size() + (0 if hf is None else hf.numel() * hf.element_size())
             return B * Tc * n_e2e / float(dt) * world, h2d, hl.numel() * 4, n_e2e
 
-        def e2e_host_round(hr, hf, zf):
+        def e2e_host_round(hr, hf, zf, direct):
             """The same loop with the operand rounding done on the HOST (prego_b200.ingest.HostRoundingStager): the fp32
             host features are rounded to the 16-bit operand format by host threads, slice by slice, and the link carries half
-            the bytes; the device reads them in place (PREGO_FEAT_16).  Bit-identical labels (tests/test_gpu_parity.py)."""
+            the bytes; the device reads them in place (PREGO_FEAT_16).  `direct` leading streams travel as plain fp32 so that
+            the link and the host's memory system finish together.  Bit-identical labels (tests/test_gpu_parity.py)."""
             from prego_b200.ingest import HostRoundingStager
             cores = os.cpu_count() or 1
             st = HostRoundingStager(B, Tc, 2048, 0 if hf is None else 2048, args.precision, dev, slices=8,
-                                    threads=max(1, cores // world))
+                                    threads=max(1, cores // world), direct_streams=direct)
             hl = torch.empty(B, Tc, dtype=torch.int32).pin_memory()
+            dl = torch.empty(B, Tc, dtype=torch.int32, device=dev)
             h2 = torch.zeros(B, 1024, device=dev)
 
             def run(n):
@@ -519,11 +521,8 @@ def run_ours(args, world, rank, local):
                 for i in range(n):
                     if i + 1 < n:
                         st.submit(i + 1, hr, hf)
-                    r16, f16 = st.wait(i)
-                    out = model.infer(r16, f16, h_state=h2, want_probs=False, precision=args.precision,
-                                      chunk_T=min(Tc, args.subchunk), zero_flow=zf)
-                    st.release(i)
-                    hl.copy_(out["labels"], non_blocking=True)
+                    st.infer(model, i, h_state=h2, labels=dl, chunk_T=min(Tc, args.subchunk), zero_flow=zf)
+                    hl.copy_(dl, non_blocking=True)
                 torch.cuda.synchronize()
 
             run(2)
@@ -535,7 +534,8 @@ def run_ours(args, world, rank, local):
             st.close()
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            h2d = (hr.numel() + (0 if hf is None else hf.numel())) * 2
+            n_dir = st.Bd * Tc * (2048 if hf is None else 4096)
+            h2d = n_dir * 4 + (hr.numel() + (0 if hf is None else hf.numel()) - n_dir) * 2
             return B * Tc * n_e2e / float(dt) * world, h2d, st.threads
 
         hr, hf = rgb.cpu().pin_memory(), flow.cpu().pin_memory()
@@ -546,12 +546,19 @@ def run_ours(args, world, rank, local):
                        "prego_forward -> int32 labels D2H; PCIe-bound (16 KiB/frame); all ranks concurrently, max over ranks"}
         e2e["fp32_over_link"] = {"value": v, "h2d_bytes_per_step": h2d}
         if args.precision != "fp32":
-            v2, h2d2, nthreads = e2e_host_round(hr, hf, False)
-            e2e["host_rounded"] = {"value": v2, "h2d_bytes_per_step": h2d2, "host_threads": nthreads,
-                                   "note": "same fp32 host buffers; host threads round them to the 16-bit operand format (the device's own first step, "
-                                           "same rule: bit-identical results), 8 slices per step pipelined with the H2D copies"}
-            if v2 > v:
-                e2e.update({"value": v2, "h2d_bytes_per_step": h2d2, "path": "fp32 host buffers rounded to 16 bit on the host, 8 KiB/frame over the link"})
+            best = None
+            for direct in (0, (3 * B // 16) // 128 * 128):  # all rounded | 3/16 of the streams as fp32 (link and host balanced)
+                v2, h2d2, nthreads = e2e_host_round(hr, hf, False, direct)
+                e2e["host_rounded" if direct == 0 else "host_rounded_hybrid"] = {"value": v2, "h2d_bytes_per_step": h2d2, "host_threads": nthreads,
+                                                                                  "fp32_streams": direct}
+                if best is None or v2 > best[0]:
+                    best = (v2, h2d2, direct)
+            e2e["host_rounded"]["note"] = ("same fp32 host buffers; host threads round them to the 16-bit operand format (the device's own first step, "
+                                           "same rule: bit-identical results), 8 slices per step pipelined with the H2D copies; hybrid: the first "
+                                           "fp32_streams streams travel as plain fp32 so that the link and the host memory system finish together")
+            if best[0] > v:
+                e2e.update({"value": best[0], "h2d_bytes_per_step": best[1],
+                            "path": f"fp32 host buffers, operand rounding on the host ({best[2]} of {B} streams as plain fp32)"})
         if variants is not None:
             # the same loop fed in the declared ingest formats: the link carries 8 / 8 / 4 KiB per frame instead of 16
             del hf

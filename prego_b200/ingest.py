@@ -243,14 +243,19 @@ class HostRoundingStager:
     results.  A batch is cut into ``slices`` along the stream axis: slice s is copied (copy stream) while slice s + 1 is
     rounded (host threads), and the whole batch i + 1 is staged while the device computes batch i (two slots).
 
+    Rounding costs host memory bandwidth (4 B read + 2 B written per value, then 2 B read by the DMA engine), and on a
+    host whose memory system is the limit the link idles part of the time.  ``direct_streams`` > 0 sends that many
+    leading streams as plain fp32 (no host work, 16 KiB per frame on the link) so that link and host finish together;
+    the device then runs the batch as two calls (fp32 rows, 16-bit rows) -- still bit-identical, every stream is
+    independent.
+
         stager = HostRoundingStager(B, T, d_rgb, d_flow, "fp16", device)
         stager.submit(0, rgb_host, flow_host)                # returns at once; a worker thread rounds and copies
-        rgb16, flow16 = stager.wait(0)                       # current stream now waits for the copies
-        out = model.infer(rgb16, flow16, precision="fp16"); stager.release(0)
+        labels = stager.infer(model, 0, h_state=h)["labels"] # waits for the copies on the current stream, runs, releases
     """
 
     def __init__(self, B: int, T: int, d_rgb: int, d_flow: int, precision: str, device, slices: int = 8,
-                 threads: Optional[int] = None, slots: int = 2):
+                 threads: Optional[int] = None, slots: int = 2, direct_streams: int = 0):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("prego_b200 ingest streams to a CUDA device; there is no CPU path")
@@ -258,14 +263,17 @@ class HostRoundingStager:
             raise RuntimeError("host rounding targets the 16-bit operand formats ('fp16' / 'bf16')")
         self.precision, self.dtype = precision, OPERAND_DTYPES[precision]
         self.B, self.T, self.dims = int(B), int(T), (int(d_rgb), int(d_flow))
+        self.Bd = max(0, min(int(direct_streams), self.B))
         self.threads = int(threads or os.cpu_count() or 1)
-        self.slices = max(1, min(int(slices), self.B))
+        self.slices = max(1, min(int(slices), max(self.B - self.Bd, 1)))
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.slots = []
+        B16 = self.B - self.Bd
         for _ in range(slots):
-            pin = [torch.empty(self.B, self.T, d, dtype=self.dtype).pin_memory() if d else None for d in self.dims]
-            dev = [torch.empty(self.B, self.T, d, dtype=self.dtype, device=self.device) if d else None for d in self.dims]
-            self.slots.append({"pin": pin, "dev": dev, "ready": torch.cuda.Event(), "free": torch.cuda.Event(),
+            pin = [torch.empty(B16, self.T, d, dtype=self.dtype).pin_memory() if d and B16 else None for d in self.dims]
+            dev = [torch.empty(B16, self.T, d, dtype=self.dtype, device=self.device) if d and B16 else None for d in self.dims]
+            dev32 = [torch.empty(self.Bd, self.T, d, dtype=torch.float32, device=self.device) if d and self.Bd else None for d in self.dims]
+            self.slots.append({"pin": pin, "dev": dev, "dev32": dev32, "ready": torch.cuda.Event(), "free": torch.cuda.Event(),
                                "issued": threading.Event(), "thread": None, "error": None})
         main = torch.cuda.current_stream(self.device)
         for s in self.slots:
@@ -277,16 +285,20 @@ class HostRoundingStager:
             lib = _lib.load()
             prec = _lib.PRECISIONS[self.precision]
             slot["ready"].synchronize()  # the previous copies out of this slot's pinned staging have finished
-            bounds = [self.B * i // self.slices for i in range(self.slices + 1)]
+            B16 = self.B - self.Bd
+            bounds = [B16 * i // self.slices for i in range(self.slices + 1)]
             with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(slot["free"])  # the consumer is done with this slot's device tensors
+                for src, d32 in zip(srcs, slot["dev32"]):  # fp32 rows first: they keep the link busy while the host rounds
+                    if src is not None and d32 is not None:
+                        d32.copy_(src[:self.Bd], non_blocking=True)
                 for b0, b1 in zip(bounds[:-1], bounds[1:]):
                     for src, pin, dev in zip(srcs, slot["pin"], slot["dev"]):
-                        if src is None or pin is None:
+                        if src is None or pin is None or b1 == b0:
                             continue
                         n = (b1 - b0) * src.shape[1] * src.shape[2]
-                        _lib.check(lib.prego_host_round_features(src[b0:b1].data_ptr(), pin[b0:b1].data_ptr(), n, prec, self.threads),
-                                   "prego_host_round_features")
+                        _lib.check(lib.prego_host_round_features(src[self.Bd + b0:self.Bd + b1].data_ptr(), pin[b0:b1].data_ptr(), n, prec,
+                                                                 self.threads), "prego_host_round_features")
                         dev[b0:b1].copy_(pin[b0:b1], non_blocking=True)
                 slot["ready"].record(self.copy_stream)
         except Exception as e:  # surfaced by wait()
@@ -313,17 +325,35 @@ class HostRoundingStager:
         slot["thread"].start()
 
     def wait(self, i: int):
-        """-> (rgb16, flow16 | None) device tensors of submission ``i``; the current stream waits for their copies."""
+        """-> ((rgb32, flow32 | None) of the first ``direct_streams`` streams or None, (rgb16, flow16 | None) of the rest
+        or None); the current stream waits for their copies."""
         slot = self.slots[i % len(self.slots)]
         slot["issued"].wait()
         if slot["error"] is not None:
             raise slot["error"]
         torch.cuda.current_stream(self.device).wait_event(slot["ready"])
-        return slot["dev"][0], (slot["dev"][1] if slot.get("flow") else None)
+        flow = bool(slot.get("flow"))
+        g32 = (slot["dev32"][0], slot["dev32"][1] if flow else None) if self.Bd else None
+        g16 = (slot["dev"][0], slot["dev"][1] if flow else None) if self.B > self.Bd else None
+        return g32, g16
 
     def release(self, i: int) -> None:
         """The consumer's work on submission ``i`` has been enqueued: its device tensors may be overwritten after it."""
         self.slots[i % len(self.slots)]["free"].record(torch.cuda.current_stream(self.device))
+
+    def infer(self, model, i: int, h_state: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None, **kw):
+        """wait(i) + ``model.infer`` on the staged tensors + release(i).  Returns {'labels': int32 [B, T]} (``labels`` is
+        reused when given).  ``h_state`` [B, H] is carried in place.  kw: chunk_T, zero_flow."""
+        g32, g16 = self.wait(i)
+        if labels is None:
+            labels = torch.empty(self.B, self.T, dtype=torch.int32, device=self.device)
+        for grp, b0, b1 in ((g32, 0, self.Bd), (g16, self.Bd, self.B)):
+            if grp is None:
+                continue
+            model.infer(grp[0], grp[1], h_state=None if h_state is None else h_state[b0:b1], want_probs=False,
+                        precision=self.precision, out={"labels": labels[b0:b1]}, **kw)
+        self.release(i)
+        return {"labels": labels}
 
     def close(self):
         for s in self.slots:

@@ -582,11 +582,11 @@ def test_non_shipped_shapes_vs_oracle(dev, H, K, B, T):
 
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
-@pytest.mark.parametrize("zero_flow", [False, True])
-def test_host_rounded_ingest_bit_identical(dev, prec, zero_flow):
+@pytest.mark.parametrize("zero_flow,direct", [(False, 0), (True, 0), (False, 128), (False, 256)])
+def test_host_rounded_ingest_bit_identical(dev, prec, zero_flow, direct):
     """HostRoundingStager (fp32 HOST features rounded to the operand format on the host, half the bytes over the link,
-    read in place by the device) gives bit-identical logits / labels / state to handing the fp32 features to the device,
-    over several pipelined steps with carried state."""
+    read in place by the device; optionally the first `direct` streams as plain fp32) gives bit-identical labels / state
+    to handing the fp32 features to the device, over several pipelined steps with carried state."""
     from prego_b200 import synthetic
     from prego_b200.ingest import HostRoundingStager
     cfg = dict(synthetic.ASSEMBLY101_O)
@@ -594,17 +594,15 @@ def test_host_rounded_ingest_bit_identical(dev, prec, zero_flow):
     B, T, steps = 256, 8, 4
     feats = [synthetic.device_features(B, T, dev, seed=40 + i, zero_flow=zero_flow) for i in range(steps)]
     host = [(r.cpu().pin_memory(), None if zero_flow else f.cpu().pin_memory()) for r, f in feats]
-    st = HostRoundingStager(B, T, 2048, 0 if zero_flow else 2048, prec, dev, slices=5, threads=3)
+    st = HostRoundingStager(B, T, 2048, 0 if zero_flow else 2048, prec, dev, slices=5, threads=3, direct_streams=direct)
     h_a = torch.zeros(B, 1024, device=dev)
     h_b = torch.zeros(B, 1024, device=dev)
     st.submit(0, *host[0])
     for i in range(steps):
         if i + 1 < steps:
             st.submit(i + 1, *host[i + 1])
-        r16, f16 = st.wait(i)
-        got = model.infer(r16, f16, h_state=h_b, want_logits=True, precision=prec, zero_flow=zero_flow)
-        st.release(i)
-        want = model.infer(feats[i][0], None if zero_flow else feats[i][1], h_state=h_a, want_logits=True, precision=prec, zero_flow=zero_flow)
-        assert torch.equal(got["logits"], want["logits"]) and torch.equal(got["labels"], want["labels"]), i
+        got = st.infer(model, i, h_state=h_b, zero_flow=zero_flow)
+        want = model.infer(feats[i][0], None if zero_flow else feats[i][1], h_state=h_a, precision=prec, zero_flow=zero_flow)
+        assert torch.equal(got["labels"], want["labels"]), i
     st.close()
     assert torch.equal(h_a, h_b)
