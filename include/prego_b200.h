@@ -255,6 +255,18 @@ int prego_perframe_ap(const float* scores, const float* targets, const int32_t* 
  * nothing of the model is computed on the CPU.  Blocking; thread-safe. */
 int prego_host_round_features(const float* src, void* dst, int64_t n, int32_t precision, int32_t num_threads);
 int prego_host_round_impl(void);
+/* Ring stager: rounds a large fp32 HOST tensor (same rule) and copies it to `dst_device` (16-bit, device) on `stream`
+ * through a small pinned ring (`ring_slots` x `slot_bytes`, a few MiB each: the copy engine loses ~30 % on sub-MiB
+ * copies): the rounded values are still in the CPU's last-level cache when the DMA engine reads them, so the host's
+ * DRAM -- the end-to-end bottleneck -- only sees the fp32 read.  A persistent pool of `num_threads` threads (the caller
+ * included) claims 128 KiB chunks from one atomic counter, no barrier (spins during a run, sleeps between runs).  The
+ * stager belongs to the device that is current at create time.  prego_host_stager_run returns when the last copy has
+ * been ENQUEUED on `stream` (the rounding itself is done).  One run at a time per stager. */
+typedef struct prego_host_stager prego_host_stager_t;
+int prego_host_stager_create(int32_t num_threads, int32_t ring_slots, int64_t slot_bytes, prego_host_stager_t** out);
+int prego_host_stager_destroy(prego_host_stager_t* stager);
+int prego_host_stager_run(prego_host_stager_t* stager, const float* src, void* dst_device, int64_t n, int32_t precision,
+                          void* stream);
 
 /* Building blocks exposed for parity tests and micro-benchmarks. */
 /* C[M,N] (fp32, ldc = N) = A[M,K] * W[N,K]^T + bias[N] with 16-bit operands (precision = PREGO_PREC_F16 or

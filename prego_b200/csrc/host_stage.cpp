@@ -6,11 +6,16 @@
 //
 // Rounding rule = Op16<FMT>::from_float of csrc/gemm_tc.cuh: fp16: clamp to +-65504 (NaN -> -65504, as fmaxf/fminf do on
 // the device), round to nearest even; bf16: round to nearest even, NaN -> 0x7FFF.
+#include <cuda_runtime_api.h>
 #include <immintrin.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -44,15 +49,20 @@ inline uint16_t f32_to_bf16_scalar(float f) {
     return static_cast<uint16_t>((x + 0x7FFFu + ((x >> 16) & 1u)) >> 16);
 }
 
+// fmt: bit 0 = 0 fp16 / 1 bf16; kCachedStores: plain stores (the destination is about to be read out of the cache by the
+// DMA engine) instead of streaming stores (the destination is a large staging buffer)
+constexpr int kCachedStores = 256;
+
 void round_scalar(const float* src, uint16_t* dst, int64_t n, int fmt) {
-    if (fmt == 0)
+    if ((fmt & 1) == 0)
         for (int64_t i = 0; i < n; ++i) dst[i] = f32_to_f16_scalar(src[i]);
     else
         for (int64_t i = 0; i < n; ++i) dst[i] = f32_to_bf16_scalar(src[i]);
 }
 
 __attribute__((target("avx2,f16c"))) void round_avx2(const float* src, uint16_t* dst, int64_t n, int fmt) {
-    const bool nt = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;  // streaming stores: the staging buffer is only read by the DMA engine
+    const bool nt = (fmt & kCachedStores) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    fmt &= 1;  // streaming stores: the staging buffer is only read by the DMA engine
     int64_t i = 0;
     if (fmt == 0) {
         const __m256 lo = _mm256_set1_ps(-65504.f), hi = _mm256_set1_ps(65504.f);
@@ -82,7 +92,8 @@ __attribute__((target("avx2,f16c"))) void round_avx2(const float* src, uint16_t*
 }
 
 __attribute__((target("avx512f,avx512bw"))) void round_avx512(const float* src, uint16_t* dst, int64_t n, int fmt) {
-    const bool nt = (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
+    const bool nt = (fmt & kCachedStores) == 0 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
+    fmt &= 1;
     int64_t i = 0;
     if (fmt == 0) {
         const __m512 lo = _mm512_set1_ps(-65504.f), hi = _mm512_set1_ps(65504.f);
@@ -148,4 +159,176 @@ extern "C" int prego_host_round_features(const float* src, void* dst, int64_t n,
 extern "C" int prego_host_round_impl(void) {
     static const RoundFn fn = pick_impl();
     return fn == round_avx512 ? 2 : (fn == round_avx2 ? 1 : 0);
+}
+
+
+// ---- Ring stager: round a large fp32 host tensor and copy it to the device through a SMALL pinned ring.
+// Rounding into a full-size staging buffer costs the host's memory system 4 B read + 2 B written + 2 B read again by
+// the DMA engine per value, and that memory system -- not the link, not the cores -- is what bounds the end-to-end
+// rate.  With a ring of a few slots of a few MiB the rounded values are written with plain stores and are still in the
+// last-level cache when the DMA engine reads them, so DRAM only sees the 4 B fp32 read; the slots are large because
+// the copy engine loses ~30 % on sub-MiB copies (measured).  A persistent pool works through the tensor in small
+// chunks claimed from one atomic counter (a descheduled thread just takes fewer chunks: no barrier, no fixed shares);
+// whoever rounds the last chunk of a slot hands the slot to cudaMemcpyAsync, whoever claims the first chunk of a slot
+// waits for the copy that last read it.  The pool spins while a run is in flight and sleeps between runs.
+struct prego_host_stager {
+    static constexpr int64_t kChunk = 32768;  // values per claim (128 KiB of fp32 in, 64 KiB out)
+    int threads = 0, slots = 0, device = 0;
+    int64_t slot_elems = 0, chunks_per_slot = 0;
+    uint16_t* ring = nullptr;                     // [slots][slot_elems]
+    std::vector<cudaEvent_t> ev;                  // [slots] recorded after the slot's copy
+    std::vector<std::atomic<int64_t>> issued;     // [slots] 1 + last slot instance whose copy was enqueued
+    std::vector<std::atomic<int>> filled;         // [slots] chunks rounded into the current instance
+    std::atomic<int64_t> free_upto{-1};           // slot instances <= this may be written
+    std::atomic<int64_t> next_chunk{0};
+    int64_t inst_base = 0;                        // slot instances used by earlier runs (ring position carries over)
+    RoundFn fn = nullptr;
+    std::vector<std::thread> pool;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<uint64_t> gen{0};
+    std::atomic<int> done{0}, sleepers{0}, failed{0};
+    std::atomic<bool> stop{false};
+    const float* job_src = nullptr;
+    uint16_t* job_dst = nullptr;
+    int64_t job_n = 0, job_chunks = 0;
+    int job_fmt = 0;
+    cudaStream_t job_stream = nullptr;
+    std::mutex call_mu;  // one run() at a time
+
+    prego_host_stager(int nslots) : issued(nslots), filled(nslots) {}
+
+    void work() {
+        for (;;) {
+            const int64_t c = next_chunk.fetch_add(1, std::memory_order_relaxed);
+            if (c >= job_chunks || failed.load(std::memory_order_relaxed)) return;
+            const int64_t li = c / chunks_per_slot;          // slot instance within this run
+            const int64_t gi = inst_base + li;               // ... and since the stager was created
+            const int slot = static_cast<int>(gi % slots);
+            if (c % chunks_per_slot == 0) {
+                // first claim of the instance: the copy out of this slot's previous instance must have been enqueued
+                // (by whoever finished it) and completed
+                if (gi >= slots) {
+                    while (issued[slot].load(std::memory_order_acquire) != gi - slots + 1 && !failed.load(std::memory_order_relaxed)) _mm_pause();
+                    if (cudaEventSynchronize(ev[slot]) != cudaSuccess) { (void)cudaGetLastError(); failed.store(1); }
+                }
+                filled[slot].store(0, std::memory_order_relaxed);
+                while (free_upto.load(std::memory_order_acquire) != gi - 1 && !failed.load(std::memory_order_relaxed)) _mm_pause();  // instances open in order
+                free_upto.store(gi, std::memory_order_release);
+            } else {
+                while (free_upto.load(std::memory_order_acquire) < gi && !failed.load(std::memory_order_relaxed)) _mm_pause();
+            }
+            const int64_t off = c * kChunk, m = std::min(kChunk, job_n - off);
+            const int64_t in_slot = off - li * slot_elems;
+            uint16_t* r = ring + static_cast<int64_t>(slot) * slot_elems;
+            fn(job_src + off, r + in_slot, m, job_fmt);
+            const int64_t slot_first = li * chunks_per_slot;
+            const int slot_chunks = static_cast<int>(std::min(chunks_per_slot, job_chunks - slot_first));
+            if (filled[slot].fetch_add(1, std::memory_order_acq_rel) + 1 == slot_chunks) {
+                // last chunk of the instance: hand the slot to the copy engine
+                const int64_t e0 = li * slot_elems, em = std::min(slot_elems, job_n - e0);
+                if (cudaMemcpyAsync(job_dst + e0, r, static_cast<size_t>(em) * 2, cudaMemcpyHostToDevice, job_stream) != cudaSuccess ||
+                    cudaEventRecord(ev[slot], job_stream) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    failed.store(1);
+                }
+                issued[slot].store(gi + 1, std::memory_order_release);
+            }
+        }
+    }
+
+    void worker() {
+        cudaSetDevice(device);
+        uint64_t seen = 0;
+        for (;;) {
+            int spins = 0;
+            while (gen.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_relaxed)) {
+                if (++spins < 20000) {
+                    _mm_pause();
+                } else {  // idle between batches: sleep instead of burning a core
+                    std::unique_lock<std::mutex> lk(mu);
+                    sleepers.fetch_add(1);
+                    cv.wait(lk, [&] { return gen.load(std::memory_order_acquire) != seen || stop.load(); });
+                    sleepers.fetch_sub(1);
+                }
+            }
+            if (stop.load()) return;
+            seen = gen.load(std::memory_order_acquire);
+            work();
+            done.fetch_add(1, std::memory_order_release);
+        }
+    }
+};
+
+extern "C" int prego_host_stager_create(int32_t num_threads, int32_t ring_slots, int64_t slot_bytes, prego_host_stager_t** out) {
+    if (out == nullptr || num_threads <= 0 || num_threads > 1024 || ring_slots < 2 || ring_slots > 64 || slot_bytes < 2 * prego_host_stager::kChunk)
+        return PREGO_ERR_INVALID;
+    prego_host_stager* s = new (std::nothrow) prego_host_stager(ring_slots);
+    if (s == nullptr) return PREGO_ERR_INVALID;
+    s->threads = num_threads;
+    s->slots = ring_slots;
+    s->chunks_per_slot = slot_bytes / 2 / prego_host_stager::kChunk;
+    s->slot_elems = s->chunks_per_slot * prego_host_stager::kChunk;
+    s->fn = pick_impl();
+    if (cudaGetDevice(&s->device) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void**>(&s->ring), static_cast<size_t>(ring_slots) * s->slot_elems * 2, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete s;
+        return PREGO_ERR_CUDA;
+    }
+    s->ev.resize(ring_slots);
+    for (int i = 0; i < ring_slots; ++i) {
+        s->issued[i].store(0);
+        s->filled[i].store(0);
+        if (cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return PREGO_ERR_CUDA;
+        }
+    }
+    for (int t = 0; t + 1 < num_threads; ++t) s->pool.emplace_back(&prego_host_stager::worker, s);  // + the caller = num_threads
+    *out = s;
+    return PREGO_OK;
+}
+
+extern "C" int prego_host_stager_destroy(prego_host_stager_t* s) {
+    if (s == nullptr) return PREGO_OK;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->stop.store(true);
+        s->cv.notify_all();
+    }
+    for (auto& th : s->pool) th.join();
+    for (size_t i = 0; i < s->ev.size(); ++i) {
+        if (s->issued[i].load() > 0) cudaEventSynchronize(s->ev[i]);
+        cudaEventDestroy(s->ev[i]);
+    }
+    cudaFreeHost(s->ring);
+    delete s;
+    return PREGO_OK;
+}
+
+extern "C" int prego_host_stager_run(prego_host_stager_t* s, const float* src, void* dst_device, int64_t n, int32_t precision, void* stream) {
+    if (s == nullptr || src == nullptr || dst_device == nullptr || n < 0) return PREGO_ERR_INVALID;
+    if (precision != PREGO_PREC_F16 && precision != PREGO_PREC_BF16) return PREGO_ERR_INVALID;
+    if (n == 0) return PREGO_OK;
+    std::lock_guard<std::mutex> call(s->call_mu);
+    s->job_src = src;
+    s->job_dst = static_cast<uint16_t*>(dst_device);
+    s->job_n = n;
+    s->job_chunks = (n + prego_host_stager::kChunk - 1) / prego_host_stager::kChunk;
+    s->job_fmt = (precision == PREGO_PREC_F16 ? 0 : 1) | kCachedStores;
+    s->job_stream = static_cast<cudaStream_t>(stream);
+    s->failed.store(0);
+    s->next_chunk.store(0);
+    s->free_upto.store(s->inst_base - 1);
+    s->done.store(0, std::memory_order_relaxed);
+    s->gen.fetch_add(1, std::memory_order_release);
+    if (s->sleepers.load() > 0) {
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->cv.notify_all();
+    }
+    s->work();  // the calling thread works too instead of spinning on a core the pool could use
+    while (s->done.load(std::memory_order_acquire) < s->threads - 1) _mm_pause();
+    s->inst_base += (s->job_chunks + s->chunks_per_slot - 1) / s->chunks_per_slot;
+    return s->failed.load() ? PREGO_ERR_CUDA : PREGO_OK;
 }

@@ -240,8 +240,10 @@ class HostRoundingStager:
     the path is bound by the host->device link, and the first thing the device does with a feature is round it to the
     projection GEMM's operand format.  Rounding on the host with the same rule (``prego_host_round_features``) halves
     the bytes on the link; ``MROAD.infer`` then reads the tensors in place (``PREGO_FEAT_16``) and returns bit-identical
-    results.  A batch is cut into ``slices`` along the stream axis: slice s is copied (copy stream) while slice s + 1 is
-    rounded (host threads), and the whole batch i + 1 is staged while the device computes batch i (two slots).
+    results.  The rounded values travel through a small pinned ring (``ring_slots`` x ``ring_slot_bytes``): a slot is
+    copied (copy stream) while the next one is rounded (persistent pool of host threads claiming 128 KiB chunks), and
+    it is still in the CPU's last-level cache when the DMA engine reads it, so the host's DRAM only sees the fp32 read.  The whole batch i + 1 is
+    staged while the device computes batch i (two device slots).
 
     Rounding costs host memory bandwidth (4 B read + 2 B written per value, then 2 B read by the DMA engine), and on a
     host whose memory system is the limit the link idles part of the time.  ``direct_streams`` > 0 sends that many
@@ -254,8 +256,8 @@ class HostRoundingStager:
         labels = stager.infer(model, 0, h_state=h)["labels"] # waits for the copies on the current stream, runs, releases
     """
 
-    def __init__(self, B: int, T: int, d_rgb: int, d_flow: int, precision: str, device, slices: int = 8,
-                 threads: Optional[int] = None, slots: int = 2, direct_streams: int = 0):
+    def __init__(self, B: int, T: int, d_rgb: int, d_flow: int, precision: str, device, threads: Optional[int] = None,
+                 slots: int = 2, direct_streams: int = 0, ring_slots: int = 3, ring_slot_bytes: int = 8 << 20):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("prego_b200 ingest streams to a CUDA device; there is no CPU path")
@@ -264,16 +266,21 @@ class HostRoundingStager:
         self.precision, self.dtype = precision, OPERAND_DTYPES[precision]
         self.B, self.T, self.dims = int(B), int(T), (int(d_rgb), int(d_flow))
         self.Bd = max(0, min(int(direct_streams), self.B))
-        self.threads = int(threads or os.cpu_count() or 1)
-        self.slices = max(1, min(int(slices), max(self.B - self.Bd, 1)))
+        cores = os.cpu_count() or 1
+        self.threads = int(threads or (cores - 2 if cores > 4 else cores))  # the rounding is memory-bound: leave two cores to Python / the driver
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.slots = []
         B16 = self.B - self.Bd
+        # the C ring stager: a persistent pool of rounding threads + a pinned ring small enough to stay in the CPU's
+        # last-level cache between the rounding stores and the DMA read (csrc/host_stage.cpp)
+        self._ring = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().prego_host_stager_create(self.threads, int(ring_slots), int(ring_slot_bytes), C.byref(self._ring)),
+                       "prego_host_stager_create")
         for _ in range(slots):
-            pin = [torch.empty(B16, self.T, d, dtype=self.dtype).pin_memory() if d and B16 else None for d in self.dims]
             dev = [torch.empty(B16, self.T, d, dtype=self.dtype, device=self.device) if d and B16 else None for d in self.dims]
             dev32 = [torch.empty(self.Bd, self.T, d, dtype=torch.float32, device=self.device) if d and self.Bd else None for d in self.dims]
-            self.slots.append({"pin": pin, "dev": dev, "dev32": dev32, "ready": torch.cuda.Event(), "free": torch.cuda.Event(),
+            self.slots.append({"dev": dev, "dev32": dev32, "ready": torch.cuda.Event(), "free": torch.cuda.Event(),
                                "issued": threading.Event(), "thread": None, "error": None})
         main = torch.cuda.current_stream(self.device)
         for s in self.slots:
@@ -284,22 +291,16 @@ class HostRoundingStager:
         try:
             lib = _lib.load()
             prec = _lib.PRECISIONS[self.precision]
-            slot["ready"].synchronize()  # the previous copies out of this slot's pinned staging have finished
-            B16 = self.B - self.Bd
-            bounds = [B16 * i // self.slices for i in range(self.slices + 1)]
             with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(slot["free"])  # the consumer is done with this slot's device tensors
                 for src, d32 in zip(srcs, slot["dev32"]):  # fp32 rows first: they keep the link busy while the host rounds
                     if src is not None and d32 is not None:
                         d32.copy_(src[:self.Bd], non_blocking=True)
-                for b0, b1 in zip(bounds[:-1], bounds[1:]):
-                    for src, pin, dev in zip(srcs, slot["pin"], slot["dev"]):
-                        if src is None or pin is None or b1 == b0:
-                            continue
-                        n = (b1 - b0) * src.shape[1] * src.shape[2]
-                        _lib.check(lib.prego_host_round_features(src[self.Bd + b0:self.Bd + b1].data_ptr(), pin[b0:b1].data_ptr(), n, prec,
-                                                                 self.threads), "prego_host_round_features")
-                        dev[b0:b1].copy_(pin[b0:b1], non_blocking=True)
+                for src, dev in zip(srcs, slot["dev"]):
+                    if src is None or dev is None:
+                        continue
+                    _lib.check(lib.prego_host_stager_run(self._ring, src[self.Bd:].data_ptr(), dev.data_ptr(), dev.numel(), prec,
+                                                         self.copy_stream.cuda_stream), "prego_host_stager_run")
                 slot["ready"].record(self.copy_stream)
         except Exception as e:  # surfaced by wait()
             slot["error"] = e
@@ -360,3 +361,13 @@ class HostRoundingStager:
             if s["thread"] is not None:
                 s["thread"].join()
                 s["thread"] = None
+        if self._ring is not None and self._ring.value:
+            torch.cuda.synchronize(self.device)
+            _lib.load().prego_host_stager_destroy(self._ring)
+            self._ring = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

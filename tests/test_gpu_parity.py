@@ -594,7 +594,7 @@ def test_host_rounded_ingest_bit_identical(dev, prec, zero_flow, direct):
     B, T, steps = 256, 8, 4
     feats = [synthetic.device_features(B, T, dev, seed=40 + i, zero_flow=zero_flow) for i in range(steps)]
     host = [(r.cpu().pin_memory(), None if zero_flow else f.cpu().pin_memory()) for r, f in feats]
-    st = HostRoundingStager(B, T, 2048, 0 if zero_flow else 2048, prec, dev, slices=5, threads=3, direct_streams=direct)
+    st = HostRoundingStager(B, T, 2048, 0 if zero_flow else 2048, prec, dev, threads=3, direct_streams=direct, ring_slots=2, ring_slot_bytes=64 << 10)
     h_a = torch.zeros(B, 1024, device=dev)
     h_b = torch.zeros(B, 1024, device=dev)
     st.submit(0, *host[0])

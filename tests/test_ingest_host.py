@@ -121,3 +121,16 @@ def test_host_rounding_is_the_device_rule_bit_for_bit(prec):
     assert lib.prego_host_round_impl() in (0, 1, 2)
     with pytest.raises(RuntimeError):
         ingest.round_features_host(t, torch.empty(x.size, dtype=torch.float32), "fp32")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_ring_stager_fails_cleanly_without_gpu():
+    import ctypes as C
+    from prego_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.prego_host_stager_create(2, 4, 1 << 20, C.byref(h)) == 2 and not h.value  # PREGO_ERR_CUDA: no pinned memory without a device
+    assert lib.prego_host_stager_create(0, 4, 1 << 20, C.byref(h)) == 1                  # PREGO_ERR_INVALID
+    assert lib.prego_host_stager_destroy(None) == 0
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ingest.HostRoundingStager(4, 4, 2048, 2048, "fp16", "cpu")
