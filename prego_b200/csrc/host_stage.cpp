@@ -282,6 +282,9 @@ extern "C" int prego_host_stager_create(int32_t num_threads, int32_t ring_slots,
         s->filled[i].store(0);
         if (cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming) != cudaSuccess) {
             (void)cudaGetLastError();
+            for (int j = 0; j < i; ++j) cudaEventDestroy(s->ev[j]);
+            cudaFreeHost(s->ring);
+            delete s;
             return PREGO_ERR_CUDA;
         }
     }

@@ -606,3 +606,26 @@ def test_host_rounded_ingest_bit_identical(dev, prec, zero_flow, direct):
         assert torch.equal(got["labels"], want["labels"]), i
     st.close()
     assert torch.equal(h_a, h_b)
+
+
+def test_evaluate_skips_the_zero_flow_dummy_bit_identically(dev, tmp_path, monkeypatch):
+    """Evaluate recognises the loader's all-zero flow tensor (dataset.py:63-69) on the host and neither copies nor
+    multiplies it: same JSON and same mAP as the plain call with the zeros."""
+    from prego_b200 import build_eval, synthetic
+    cfg = dict(synthetic.EPIC_TENT_O, precision="fp16")
+    model = synthetic.seeded_model(cfg, seed=20, device=dev)
+    loader = []
+    for i, T in enumerate([130, 77]):
+        rgb, flow = synthetic.feature_batch([400 + i], T, "cpu", zero_flow=True)
+        loader.append((rgb, flow, synthetic.targets(400 + i, T, 12).unsqueeze(0), (f"v{i}",), torch.tensor([0]), torch.tensor([T])))
+    monkeypatch.chdir(tmp_path)
+    ev = build_eval(cfg)
+    m1 = ev(model, loader, None, dev)
+    got = json.load(open(tmp_path / "output_miniRoad" / "output_miniROAD.json"))
+    want = {}
+    for rgb, flow, _t, vid, _s, _e in loader:
+        with torch.no_grad():
+            model(rgb.to(dev), flow.to(dev))
+        want[vid[0]] = model.last_labels[0].cpu().tolist()
+    assert {k: v["pred"] for k, v in got.items()} == want
+    assert 0.0 <= m1 <= 1.0
