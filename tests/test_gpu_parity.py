@@ -593,7 +593,9 @@ def test_host_rounded_ingest_bit_identical(dev, prec, zero_flow, direct):
     model = synthetic.seeded_model(cfg, seed=20, device=dev)
     B, T, steps = 256, 8, 4
     feats = [synthetic.device_features(B, T, dev, seed=40 + i, zero_flow=zero_flow) for i in range(steps)]
-    host = [(r.cpu().pin_memory(), None if zero_flow else f.cpu().pin_memory()) for r, f in feats]
+    # direct == 0: plain pageable host tensors, what the reference's DataLoader yields (dataset_builder.py:22 pin_memory=False)
+    pin = (lambda t: t.pin_memory()) if direct else (lambda t: t)
+    host = [(pin(r.cpu()), None if zero_flow else pin(f.cpu())) for r, f in feats]
     st = HostRoundingStager(B, T, 2048, 0 if zero_flow else 2048, prec, dev, threads=3, direct_streams=direct, ring_slots=2, ring_slot_bytes=64 << 10)
     h_a = torch.zeros(B, 1024, device=dev)
     h_b = torch.zeros(B, 1024, device=dev)
