@@ -123,8 +123,12 @@ class ANT_Evaluate(nn.Module):
         with torch.no_grad():
             for rgb_input, flow_input, target, ant_target in dataloader:
                 rgb_input = rgb_input.to(device, non_blocking=True)
-                flow_input = flow_input.to(device, non_blocking=True)
-                out_dict = model(rgb_input, flow_input)
+                if _is_zero_flow(model, flow_input) and getattr(model, "anticipation_length", 0) > 0:
+                    out = model.infer(rgb_input, None, want_probs=True, want_anticipation=True, zero_flow=True)  # as in Evaluate.eval
+                    out_dict = {"logits": out["probs"], "anticipation_logits": out["anticipation_probs"]}
+                else:
+                    flow_input = flow_input.to(device, non_blocking=True)
+                    out_dict = model(rgb_input, flow_input)
                 K = out_dict["logits"].shape[-1]
                 A = out_dict["anticipation_logits"].shape[-2]
                 pred_scores.append(out_dict["logits"].reshape(-1, K))                      # eval.py:119-124

@@ -92,6 +92,27 @@ class SyntheticFeatures(torch.utils.data.Dataset):
         return rgb, flow, synthetic.targets(i, T, self.cfg["num_classes"]), f"synthetic_{i}", 0, T
 
 
+class SyntheticAnticipation(torch.utils.data.Dataset):
+    """Test-mode items of the reference's anticipation dataset (datasets/dataset.py:207-216,219-227) on seeded synthetic
+    videos: ``(rgb[T-A], flow[T-A], target[T-A, K], ant_target[T-A, A, K])`` with ``ant_target[s] = target[s : s + A]``.
+    (The reference's own class reads THUMOS / TVSeries .npy files; those datasets are outside PREGO's hot path.)"""
+
+    def __init__(self, cfg, n):
+        self.cfg, self.n, self.A = cfg, n, int(cfg["anticipation_length"])
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        T = (1024, 538, 2011)[i % 3]
+        zero_flow = self.cfg["flow_type"] == "flow_anet_resnet50"
+        rgb, flow = synthetic.features(i, T, "cpu", zero_flow, FEATURE_SIZES[self.cfg["rgb_type"]], FEATURE_SIZES[self.cfg["flow_type"]])
+        target = synthetic.targets(i, T, self.cfg["num_classes"])
+        end = T - self.A
+        ant = torch.stack([target[s:s + self.A] for s in range(end)])
+        return rgb[:end], flow[:end], target[:end], ant
+
+
 def main(argv=None):
     import yaml
 
@@ -120,7 +141,14 @@ def main(argv=None):
     logger = logging.getLogger("prego_b200")
     logger.info(cfg)
 
-    dataset = SyntheticFeatures(cfg, args.synthetic) if args.synthetic > 0 else EvalFeatures(cfg)
+    if cfg.get("task") == "ANTICIPATION":
+        if args.synthetic <= 0:
+            raise RuntimeError("task ANTICIPATION (MiniROADA) runs on --synthetic N videos: the reference's anticipation dataset is THUMOS / TVSeries")
+        if args.eval is None:
+            raise RuntimeError("MiniROADA is inference-only here: pass --eval <ckpt.pth | synthetic>")
+        dataset = SyntheticAnticipation(cfg, args.synthetic)
+    else:
+        dataset = SyntheticFeatures(cfg, args.synthetic) if args.synthetic > 0 else EvalFeatures(cfg)
     testloader = torch.utils.data.DataLoader(dataset, batch_size=cfg.get("test_batch_size", 1), shuffle=False,
                                              num_workers=0, pin_memory=True)
     model = build_model(cfg, device)

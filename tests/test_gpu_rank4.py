@@ -205,3 +205,33 @@ def test_ant_evaluate_matches_oracle(dev, meta4):
     for a in range(A):
         assert abs(ev.last_result[f"anticipation_{a+1}"]["mean_AP"] - want_steps[a]) <= AP_TOL
     assert abs(got - np.mean(want_steps)) <= AP_TOL
+
+
+def test_main_entry_miniroada_synthetic(dev, tmp_path, monkeypatch):
+    """python -m prego_b200.main --config configs/miniroada_synthetic.yaml --eval synthetic --synthetic 3: registry ->
+    MROADA -> ANT_Evaluate end to end (zero-flow dummy recognised on the host), mean anticipation mAP == the oracle's on
+    the same outputs."""
+    from conftest import ROOT
+    from prego_b200 import main as pmain, synthetic
+    import yaml
+    monkeypatch.chdir(tmp_path)
+    cfg_path = os.path.join(ROOT, "configs", "miniroada_synthetic.yaml")
+    got = pmain.main(["--config", cfg_path, "--eval", "synthetic", "--synthetic", "3", "--device", "cuda:0", "--precision", "fp32"])
+    cfg = yaml.safe_load(open(cfg_path))
+    cfg.update(no_rgb=False, no_flow=False, precision="fp32")
+    pmain.set_seed(20)
+    model = __import__("prego_b200").build_model(cfg, dev).eval()
+    ds = pmain.SyntheticAnticipation(cfg, 3)
+    A, K = 4, 86
+    ps, ts = [], []
+    for i in range(3):
+        rgb, flow, _t, ant = ds[i]
+        out = model.infer(rgb.unsqueeze(0).to(dev), flow.unsqueeze(0).to(dev), precision="fp32", want_anticipation=True)
+        ps.append(out["anticipation_probs"][0].cpu().numpy())
+        ts.append(ant.numpy())
+    p, t = np.concatenate(ps), np.concatenate(ts)
+    names = [str(i) for i in range(K)]
+    want = np.mean([metrics_np.perframe_average_precision(p[:, a], t[:, a], names)["mean_AP"] for a in range(A)])
+    assert abs(got - want) <= 1e-9
+    with pytest.raises(RuntimeError, match="inference-only"):
+        pmain.main(["--config", cfg_path, "--synthetic", "2"])
