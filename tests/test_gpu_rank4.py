@@ -235,3 +235,25 @@ def test_main_entry_miniroada_synthetic(dev, tmp_path, monkeypatch):
     assert abs(got - want) <= 1e-9
     with pytest.raises(RuntimeError, match="inference-only"):
         pmain.main(["--config", cfg_path, "--synthetic", "2"])
+
+
+@pytest.mark.parametrize("N,K", [(1, 1), (1, 7), (31, 3), (4097, 2), (12289, 33)])
+def test_perframe_ap_multilabel_and_tiny_shapes_vs_oracle(dev, N, K):
+    """Multi-hot targets (several positive classes per frame, classes that are all-positive or empty), N = 1, K = 1,
+    tile and slice boundaries: the device result equals the oracle (sklearn restatement) class by class."""
+    from prego_b200.metrics import average_precision_per_class
+    rs = np.random.RandomState(N * 131 + K)
+    scores = (rs.randint(0, 1 << 12, (N, K)).astype(np.float32) / np.float32(1 << 12))
+    scores[rs.rand(N, K) < 0.05] = 1.0
+    scores[rs.rand(N, K) < 0.05] = 0.0
+    targets = (rs.rand(N, K) < 0.3).astype(np.float32)
+    if K > 2:
+        targets[:, 1] = 1.0   # every frame positive
+        targets[:, 2] = 0.0   # no positive: skipped by the reference (metrics.py:54)
+    ap, npos = average_precision_per_class(torch.from_numpy(scores).to(dev), torch.from_numpy(targets).to(dev))
+    assert np.array_equal(npos, targets.sum(0).astype(np.int64))
+    for k in range(K):
+        if targets[:, k].any():
+            assert abs(ap[k] - metrics_np.average_precision(targets[:, k], scores[:, k])) <= AP_TOL, (k, ap[k])
+        else:
+            assert np.isnan(ap[k])

@@ -95,3 +95,21 @@ def test_metrics_need_cuda():
         pytest.skip("no-GPU failure mode")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         prego_b200.perframe_average_precision(torch.rand(8, 3), torch.zeros(8, dtype=torch.int32), ["a", "b", "c"])
+
+
+def test_average_precision_restatement_matches_sklearn_live_on_multilabel():
+    """Beyond the committed golden cases: the restatement against the dependency itself (scikit-learn, the library the
+    reference calls at utils/metrics.py:43,55) on multi-hot targets, all-positive classes, N = 1."""
+    from sklearn.metrics import average_precision_score
+    for N, K in [(1, 1), (1, 7), (31, 3), (4097, 2), (12289, 33)]:
+        rs = np.random.RandomState(N * 131 + K)
+        scores = (rs.randint(0, 1 << 12, (N, K)).astype(np.float32) / np.float32(1 << 12))
+        scores[rs.rand(N, K) < 0.05] = 1.0
+        scores[rs.rand(N, K) < 0.05] = 0.0
+        targets = (rs.rand(N, K) < 0.3).astype(np.float32)
+        if K > 2:
+            targets[:, 1] = 1.0
+            targets[:, 2] = 0.0
+        for k in range(K):
+            if targets[:, k].any():
+                assert abs(metrics_np.average_precision(targets[:, k], scores[:, k]) - average_precision_score(targets[:, k], scores[:, k])) <= 1e-12
