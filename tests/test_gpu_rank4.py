@@ -257,3 +257,29 @@ def test_perframe_ap_multilabel_and_tiny_shapes_vs_oracle(dev, N, K):
             assert abs(ap[k] - metrics_np.average_precision(targets[:, k], scores[:, k])) <= AP_TOL, (k, ap[k])
         else:
             assert np.isnan(ap[k])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+@pytest.mark.parametrize("over", [{"num_classes": 100, "anticipation_length": 2}, {"no_flow": True, "anticipation_length": 3},
+                                  {"num_classes": 128, "anticipation_length": 5, "actionness": True}])
+def test_anticipation_non_shipped_shapes_vs_oracle(dev, prec, over):
+    """Shapes no golden case covers (the 128-column head tile, rgb-only input, odd A): CUDA path vs the numpy oracle,
+    which the golden cases pin on the shipped shapes."""
+    from prego_b200 import MROADA, synthetic
+    cfg = dict(synthetic.EPIC_TENT_O, model="MiniROADA", actionness=False)
+    cfg.update(over)
+    torch.manual_seed(7)
+    m = MROADA(cfg).to(dev).eval()
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    B, T = 18, 5  # B > 16: batched tcgen05 recurrence
+    rgb, flow = synthetic.feature_batch(list(range(900, 900 + B)), T, "cpu")
+    _, _, ref_l, ref_al = miniroad_np.forward_anticipation(sd, rgb.numpy(), flow.numpy(), cfg["anticipation_length"],
+                                                           use_flow=not cfg["no_flow"])
+    out = m.infer(rgb.to(dev), None if cfg["no_flow"] else flow.to(dev), want_logits=True, precision=prec,
+                  want_anticipation=True, want_anticipation_logits=True)
+    e0 = _check_logits(out["logits"].cpu().numpy(), ref_l, REL[prec], "trunk")
+    e1 = _check_logits(out["anticipation_logits"].cpu().numpy(), ref_al, REL[prec], "anticipation")
+    _check_labels(out["anticipation_labels"].cpu().numpy(), ref_al, e1, "anticipation")
+    ap = out["anticipation_probs"].cpu().numpy()
+    assert ap.shape == (B, T, cfg["anticipation_length"], cfg["num_classes"]) and np.abs(ap.sum(-1) - 1).max() < 1e-5
+    assert e0 >= 0
