@@ -191,8 +191,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) online_fused_kernel(const On
     const int upc = (H + G - 1) / G, rpc = (E + G - 1) / G;  // hidden units / W1 rows per CTA (<= 8 / <= 16: checked by the host)
     const int u0 = cta * upc, n0 = cta * rpc;
     const int nu = min(upc, max(H - u0, 0)), nr = min(rpc, max(E - n0, 0));
-    const bool uval = g < nu;
-    const int u = u0 + g;
     FUSED_STAMP(0);
 
     // ---- this warp's K slice of the activations is requested FIRST (the L2 -> SM path is served in order and the
