@@ -113,3 +113,26 @@ def test_average_precision_restatement_matches_sklearn_live_on_multilabel():
         for k in range(K):
             if targets[:, k].any():
                 assert abs(metrics_np.average_precision(targets[:, k], scores[:, k]) - average_precision_score(targets[:, k], scores[:, k])) <= 1e-12
+
+
+def test_c_restatement_of_average_precision_matches_golden_and_numpy():
+    """oracle/metrics_oracle.c (plain C, qsort) against the reference-made golden values and the numpy restatement."""
+    import ctypes as C
+    import subprocess
+    from conftest import ROOT
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libmetrics_oracle.so"))
+    lib.oracle_average_precision.restype = C.c_double
+    lib.oracle_average_precision.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    gold = np.load(os.path.join(GOLD, "map_cases.npz"))
+    for name, scores, labels in map_cases():
+        want = gold[f"{name}.ap"]
+        for k in range(scores.shape[1]):
+            col = np.ascontiguousarray(scores[:, k])
+            pos = np.ascontiguousarray((labels == k).astype(np.int32))
+            got = lib.oracle_average_precision(col.ctypes.data, pos.ctypes.data, col.size)
+            if k == 0:  # background: not in the golden dict, compare with the numpy restatement instead
+                ref = metrics_np.average_precision(pos, col) if pos.any() else float("nan")
+            else:
+                ref = want[k]
+            assert (np.isnan(got) and np.isnan(ref)) or abs(got - ref) <= 1e-12, (name, k, got, ref)
