@@ -8,7 +8,8 @@
 //      scores the order is irrelevant: only group ends contribute).  [N, K] -> [K, N] through a shared-memory tile.
 //   2. four stable 8-bit LSD radix passes, each class cut into S slices so that K * S CTAs fill the machine:
 //      ap_hist_kernel (digit counts per slice) -> ap_offsets_kernel (prefix over (digit, slice) per class) ->
-//      ap_scatter_kernel (tile-wise stable ranks: ballot-built peer masks + per-warp digit counters).
+//      ap_scatter_kernel (4096-key tiles: stable ranks from ballot-built peer masks + one shared atomic per digit
+//      group, the tile is ordered by digit in shared memory and leaves in runs, so the global stores coalesce).
 //   3. the precision-recall integral over the descending order, again per slice: ap_scan_local (positives and the tp
 //      at the last threshold of each slice) -> ap_scan_final (carries from the slices above, float64 partial sums)
 //      -> ap_reduce (fixed-order sum: deterministic).
