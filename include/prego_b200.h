@@ -255,6 +255,9 @@ int prego_perframe_ap(const float* scores, const float* targets, const int32_t* 
  * nothing of the model is computed on the CPU.  Blocking; thread-safe. */
 int prego_host_round_features(const float* src, void* dst, int64_t n, int32_t precision, int32_t num_threads);
 int prego_host_round_impl(void);
+/* 1 when all n values are +-0.0 -- the reference loader's all-zero flow dummy (datasets/dataset.py:63-69), which the
+ * caller may then declare with flow_is_zero instead of copying and multiplying it -- 0 otherwise, -1 on a bad argument. */
+int prego_host_all_zero(const float* src, int64_t n, int32_t num_threads);
 /* Ring stager: rounds a large fp32 HOST tensor (same rule) and copies it to `dst_device` (16-bit, device) on `stream`
  * through a small pinned ring (`ring_slots` x `slot_bytes`, a few MiB each: the copy engine loses ~30 % on sub-MiB
  * copies): the rounded values are still in the CPU's last-level cache when the DMA engine reads them, so the host's

@@ -87,6 +87,7 @@ SIGNATURES = {
                                     C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "prego_host_round_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
     "prego_host_round_impl": (C.c_int, []),
+    "prego_host_all_zero": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32]),
     "prego_host_stager_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]),
     "prego_host_stager_destroy": (C.c_int, [C.c_void_p]),
     "prego_host_stager_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),

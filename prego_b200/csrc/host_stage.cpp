@@ -156,6 +156,37 @@ extern "C" int prego_host_round_features(const float* src, void* dst, int64_t n,
     return PREGO_OK;
 }
 
+// 1 when every value is +-0.0 (the reference loader's flow dummy is np.zeros, datasets/dataset.py:63-69), else 0.
+// Threads stop early once any of them has seen a non-zero value.
+extern "C" int prego_host_all_zero(const float* src, int64_t n, int32_t num_threads) {
+    if (src == nullptr || n < 0) return -1;
+    std::atomic<int> nonzero{0};
+    auto scan = [&](int64_t b, int64_t e) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(src);
+        for (int64_t i = b; i < e && !nonzero.load(std::memory_order_relaxed);) {
+            const int64_t stop = std::min(e, i + 16384);
+            uint32_t acc = 0;
+            for (; i < stop; ++i) acc |= p[i];
+            if (acc & 0x7FFFFFFFu) nonzero.store(1, std::memory_order_relaxed);
+        }
+    };
+    int64_t nt = num_threads > 0 ? num_threads : 1;
+    const int64_t min_chunk = 1 << 18;
+    if (nt > (n + min_chunk - 1) / min_chunk) nt = (n + min_chunk - 1) / min_chunk;
+    if (nt <= 1) {
+        scan(0, n);
+    } else {
+        const int64_t chunk = (n + nt - 1) / nt;
+        std::vector<std::thread> pool;
+        for (int64_t t = 0; t < nt; ++t) {
+            const int64_t b = t * chunk, e = std::min(n, b + chunk);
+            if (b < e) pool.emplace_back(scan, b, e);
+        }
+        for (auto& th : pool) th.join();
+    }
+    return nonzero.load() ? 0 : 1;
+}
+
 extern "C" int prego_host_round_impl(void) {
     static const RoundFn fn = pick_impl();
     return fn == round_avx512 ? 2 : (fn == round_avx2 ? 1 : 0);

@@ -257,7 +257,8 @@ class HostRoundingStager:
     """
 
     def __init__(self, B: int, T: int, d_rgb: int, d_flow: int, precision: str, device, threads: Optional[int] = None,
-                 slots: int = 2, direct_streams: int = 0, ring_slots: int = 3, ring_slot_bytes: int = 8 << 20):
+                 slots: int = 2, direct_streams: int = 0, ring_slots: int = 3, ring_slot_bytes: int = 8 << 20,
+                 detect_zero_flow: bool = True):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("prego_b200 ingest streams to a CUDA device; there is no CPU path")
@@ -266,6 +267,7 @@ class HostRoundingStager:
         self.precision, self.dtype = precision, OPERAND_DTYPES[precision]
         self.B, self.T, self.dims = int(B), int(T), (int(d_rgb), int(d_flow))
         self.Bd = max(0, min(int(direct_streams), self.B))
+        self.detect_zero_flow = bool(detect_zero_flow) and self.dims[0] > 0
         cores = os.cpu_count() or 1
         self.threads = int(threads or (cores - 2 if cores > 4 else cores))  # the rounding is memory-bound: leave two cores to Python / the driver
         self.copy_stream = torch.cuda.Stream(device=self.device)
@@ -291,6 +293,11 @@ class HostRoundingStager:
         try:
             lib = _lib.load()
             prec = _lib.PRECISIONS[self.precision]
+            if self.detect_zero_flow and srcs[1] is not None and lib.prego_host_all_zero(srcs[1].data_ptr(), srcs[1].numel(), self.threads) == 1:
+                # the reference loader's flow dummy (np.zeros, datasets/dataset.py:63-69): neither rounded nor copied; infer()
+                # declares it (flow_is_zero: bit-identical to multiplying by the zeros)
+                srcs = [srcs[0], None]
+                slot["flow"], slot["zero_flow"] = False, True
             with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(slot["free"])  # the consumer is done with this slot's device tensors
                 for src, d32 in zip(srcs, slot["dev32"]):  # fp32 rows first: they keep the link busy while the host rounds
@@ -321,7 +328,7 @@ class HostRoundingStager:
             slot["thread"].join()
         slot["issued"].clear()
         slot["error"] = None
-        slot["flow"] = srcs[1] is not None
+        slot["flow"], slot["zero_flow"] = srcs[1] is not None, False
         slot["thread"] = threading.Thread(target=self._work, args=(slot, srcs), daemon=True)
         slot["thread"].start()
 
@@ -344,8 +351,11 @@ class HostRoundingStager:
 
     def infer(self, model, i: int, h_state: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None, **kw):
         """wait(i) + ``model.infer`` on the staged tensors + release(i).  Returns {'labels': int32 [B, T]} (``labels`` is
-        reused when given).  ``h_state`` [B, H] is carried in place.  kw: chunk_T, zero_flow."""
+        reused when given).  ``h_state`` [B, H] is carried in place.  kw: chunk_T, zero_flow (set automatically when the
+        submitted flow tensor was recognised as the all-zero dummy)."""
         g32, g16 = self.wait(i)
+        if self.slots[i % len(self.slots)].get("zero_flow"):
+            kw = dict(kw, zero_flow=True)
         if labels is None:
             labels = torch.empty(self.B, self.T, dtype=torch.int32, device=self.device)
         for grp, b0, b1 in ((g32, 0, self.Bd), (g16, self.Bd, self.B)):

@@ -631,3 +631,27 @@ def test_evaluate_skips_the_zero_flow_dummy_bit_identically(dev, tmp_path, monke
         want[vid[0]] = model.last_labels[0].cpu().tolist()
     assert {k: v["pred"] for k, v in got.items()} == want
     assert 0.0 <= m1 <= 1.0
+
+
+def test_stager_recognises_the_zero_flow_dummy(dev):
+    """A flow tensor that is the reference loader's np.zeros dummy (dataset.py:63-69) is found by the host scan, neither
+    rounded nor copied, and declared to the device: labels / state equal the run that multiplies by the zeros."""
+    from prego_b200 import synthetic
+    from prego_b200.ingest import HostRoundingStager
+    model = synthetic.seeded_model(dict(synthetic.ASSEMBLY101_O), seed=20, device=dev)
+    B, T = 128, 6
+    rgb, flow = synthetic.device_features(B, T, dev, seed=77, zero_flow=True)
+    st = HostRoundingStager(B, T, 2048, 2048, "fp16", dev, threads=2, ring_slots=2, ring_slot_bytes=256 << 10)
+    h_a, h_b = torch.zeros(B, 1024, device=dev), torch.zeros(B, 1024, device=dev)
+    st.submit(0, rgb.cpu(), flow.cpu())
+    got = st.infer(model, 0, h_state=h_b)
+    assert st.slots[0]["zero_flow"] and not st.slots[0]["flow"]
+    want = model.infer(rgb, flow, h_state=h_a, precision="fp16")
+    assert torch.equal(got["labels"], want["labels"]) and torch.equal(h_a, h_b)
+    flow[3, 2, 100] = 1e-3   # no longer the dummy: goes through the ordinary path
+    st.submit(1, rgb.cpu(), flow.cpu())
+    got = st.infer(model, 1, h_state=h_b)
+    assert not st.slots[1]["zero_flow"] and st.slots[1]["flow"]
+    want = model.infer(rgb, flow, h_state=h_a, precision="fp16")
+    assert torch.equal(got["labels"], want["labels"]) and torch.equal(h_a, h_b)
+    st.close()

@@ -134,3 +134,19 @@ def test_ring_stager_fails_cleanly_without_gpu():
     assert lib.prego_host_stager_destroy(None) == 0
     with pytest.raises(RuntimeError, match="no CPU path"):
         ingest.HostRoundingStager(4, 4, 2048, 2048, "fp16", "cpu")
+
+
+def test_host_all_zero_scan():
+    from prego_b200 import _lib
+    lib = _lib.load()
+    n = (1 << 20) + 13
+    x = np.zeros(n, np.float32)
+    x[5] = -0.0
+    for th in (1, 4):
+        assert lib.prego_host_all_zero(x.ctypes.data, n, th) == 1          # +-0.0 only
+    for pos in (0, 12345, n - 1):
+        y = x.copy()
+        y[pos] = 1e-45                                                     # smallest subnormal still counts
+        for th in (1, 4):
+            assert lib.prego_host_all_zero(y.ctypes.data, n, th) == 0, (pos, th)
+    assert lib.prego_host_all_zero(x.ctypes.data, 0, 2) == 1 and lib.prego_host_all_zero(None, 4, 1) == -1
