@@ -2,7 +2,7 @@
 
 The reference loader keeps every video's TSN features as float64/float32 ``.npy`` arrays, converts them to fp32 per
 item, and -- in both shipped configs -- replaces the flow stream by ``np.zeros`` (``dataset.py:63-69``).  End to end
-the B200 path is bound by the host->device link (16 KiB per frame as fp32), so the ingest side does three things:
+the B200 path is bound by the host->device link (16 KiB per frame as fp32), so the ingest side does four things:
 
 * **convert once**: each video is rounded to the 16-bit operand format of the model's precision when it is loaded
   (the CUDA path would apply exactly this rounding in its staging pass, so results are bit-identical) and kept in
@@ -11,6 +11,11 @@ the B200 path is bound by the host->device link (16 KiB per frame as fp32), so t
   model is told so (``zero_flow``) and skips that half of the projection;
 * **stream**: videos are bucketed by length (the GRU is causal, so end-padding cannot change earlier outputs), each
   bucket is assembled in a pinned staging buffer and copied on a side stream while the previous bucket computes.
+
+* **round on the host when the caller holds fp32 host tensors** (what the reference's ``DataLoader`` yields,
+  ``dataset_builder.py:17-23``): ``HostRoundingStager`` applies the device's operand rounding on host threads and copies
+  through a cache-resident pinned ring (``csrc/host_stage.cpp``), halving the bytes on the link with bit-identical
+  results; the loader's all-zero flow dummy is recognised by a host scan and never copied.
 
 Host code only; the compute stays behind ``MROAD.infer`` (there is no CPU fallback here either).
 """
