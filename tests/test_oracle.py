@@ -107,3 +107,42 @@ def test_aggregate_c_oracle(c_oracle):
         n, vals, chg = _c_collapse(c_oracle, kat["pred"], 200, max(kat["pred"]) + 1)
         assert vals == kat["expected"]["pred"] and chg == kat["expected"]["changes_pred"]
     assert _c_collapse(c_oracle, [])[0] == -1
+
+
+# ------------------------------------------------------------------ property tests (hypothesis)
+def _reference_aggregate_module():
+    """The reference's own utils/aggregate.py, imported live when the checkout is mounted (the build container);
+    None on machines without it (the GPU box never sees /root/reference)."""
+    import importlib.util
+    path = "/root/reference/utils/aggregate.py"
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("ref_aggregate_live", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_aggregate_restatements_agree_on_random_sequences(c_oracle, tmp_path):
+    """numpy restatement == plain-C restatement (== the reference's own functions, when the checkout is present) on
+    random label sequences: short and long runs, lengths around the 200-frame window, one-element sequences."""
+    from hypothesis import given, settings, strategies as st
+    ref = _reference_aggregate_module()
+    runs = st.lists(st.tuples(st.integers(0, 11), st.integers(1, 260)), min_size=1, max_size=12)
+
+    @settings(max_examples=120, deadline=None)
+    @given(runs, runs)
+    def check(pred_runs, gt_runs):
+        pred = [l for l, n in pred_runs for _ in range(n)]
+        gt = [l for l, n in gt_runs for _ in range(n)]
+        want = aggregate_np.aggregate_video(pred, gt)
+        n, vals, chg = _c_collapse(c_oracle, pred, 200, 12)
+        assert (vals, chg) == (want["pred"], want["changes_pred"])
+        n, vals, chg = _c_collapse(c_oracle, gt)
+        assert (vals, chg) == (want["gt"], want["changes_gt"])
+        if ref is not None:
+            out = tmp_path / "o.json"
+            ref.aggregate({"v": {"pred": pred, "gt": gt}}, str(out))
+            assert json.load(open(out))["v"] == want
+
+    check()
