@@ -136,3 +136,43 @@ def test_c_restatement_of_average_precision_matches_golden_and_numpy():
             else:
                 ref = want[k]
             assert (np.isnan(got) and np.isnan(ref)) or abs(got - ref) <= 1e-12, (name, k, got, ref)
+
+
+_LIVE_CHECK = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, "/root/reference/step_recognition")
+from model import build_model                      # the reference's registry (model/model_builder.py:7-9)
+from oracle import miniroad_np
+from prego_b200 import synthetic
+torch.set_num_threads(4)
+for seed, (B, T), A, K in ((1, (2, 9), 2, 12), (2, (1, 33), 5, 86), (3, (5, 4), 1, 30)):
+    cfg = dict(synthetic.EPIC_TENT_O, num_classes=K, model="MiniROADA", anticipation_length=A, actionness=bool(seed % 2))
+    torch.manual_seed(seed)
+    ref = build_model(cfg, "cpu").eval()
+    g = torch.Generator().manual_seed(seed)
+    rgb, flow = torch.randn(B, T, 2048, generator=g).abs(), torch.randn(B, T, 2048, generator=g).abs()
+    with torch.no_grad():
+        out = ref(rgb, flow)
+    p, ap, _, _ = miniroad_np.forward_anticipation(ref.state_dict(), rgb.numpy(), flow.numpy(), A)
+    assert np.abs(p - out["logits"].numpy()).max() <= 2e-6 and np.abs(ap - out["anticipation_logits"].numpy()).max() <= 2e-6
+    cfg = dict(synthetic.EPIC_TENT_O, num_classes=K, model="MiniROAD")
+    torch.manual_seed(seed)
+    ref = build_model(cfg, "cpu").eval()
+    with torch.no_grad():
+        want = ref(rgb, flow)["logits"].numpy()
+    assert np.abs(miniroad_np.forward(ref.state_dict(), rgb.numpy(), flow.numpy()) - want).max() <= 2e-6
+print("live reference == restatement")
+"""
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/step_recognition/model"), reason="reference checkout not mounted")
+def test_restatements_against_the_live_reference_modules(tmp_path):
+    """Beyond the committed golden vectors: MROAD and MROADA imported live from the reference checkout (build container
+    only; a subprocess so that the reference's top-level packages do not leak into this one), random seeds / shapes."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    script = tmp_path / "live_check.py"
+    script.write_text(_LIVE_CHECK)
+    out = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "live reference == restatement" in out.stdout, out.stderr[-2000:]
