@@ -341,6 +341,8 @@ class HostRoundingStager:
         """-> ((rgb32, flow32 | None) of the first ``direct_streams`` streams or None, (rgb16, flow16 | None) of the rest
         or None); the current stream waits for their copies."""
         slot = self.slots[i % len(self.slots)]
+        if slot["thread"] is None:
+            raise RuntimeError(f"wait({i}) without a matching submit({i})")
         slot["issued"].wait()
         if slot["error"] is not None:
             raise slot["error"]
