@@ -188,17 +188,23 @@ def build_trainer(cfg):
 
 
 class WindowDataset(torch.utils.data.Dataset):
-    """Train-mode view of the reference dataset (datasets/dataset.py:96-135): every video is cut into windows of
+    """Train-mode view of the reference dataset (datasets/dataset.py:45-135): every video gets ``window_size - 1``
+    all-zero dummy frames (features AND targets) in front (dataset.py:53-55,77-82), then is cut into windows of
     ``window_size`` frames every ``stride`` frames, starting at a random offset in [0, stride) that is re-drawn by
-    ``_init_features()`` (the reference calls it after every epoch, main.py:101).  Items:
-    ``(rgb[W, Dr], flow[W, Df], target[W, K], vid, start, end)`` fp32, like ``THUMOSDataset.__getitem__``.
+    ``_init_features()`` (the reference calls it after every epoch, main.py:101).  The loss reads the LAST frame of a
+    window (criterions/loss.py:15-34), so with the front pad every real frame from the very first one is a training
+    target, seen with a short (zero-padded) context, and a video shorter than ``window_size`` still yields windows.
+    Items: ``(rgb[W, Dr], flow[W, Df], target[W, K], vid, start, end)`` fp32 with ``start`` / ``end`` in the PADDED
+    frame numbering, like ``THUMOSDataset.__getitem__`` (dataset.py:125-132).  The pad is virtual: it is written into
+    the item, never concatenated to the stored arrays.
 
     ``videos``: ``{vid: (rgb[T, Dr], flow[T, Df] | None, target[T, K])}`` numpy / torch arrays; a ``None`` flow is the
-    all-zero dummy of dataset.py:63-69."""
+    all-zero dummy of dataset.py:63-69.  ``front_pad=False`` gives plain windows over the stored frames."""
 
-    def __init__(self, videos, window_size: int, stride: int, d_flow: int = 2048, rng=None):
+    def __init__(self, videos, window_size: int, stride: int, d_flow: int = 2048, rng=None, front_pad: bool = True):
         import numpy as np
         self.videos, self.window_size, self.stride, self.d_flow = videos, int(window_size), int(stride), d_flow
+        self.pad = self.window_size - 1 if front_pad else 0
         self.rng = rng if rng is not None else np.random
         self.inputs = []
         self._init_features()
@@ -206,7 +212,7 @@ class WindowDataset(torch.utils.data.Dataset):
     def _init_features(self):
         self.inputs = []
         for vid, (rgb, flow, target) in self.videos.items():
-            n = int(target.shape[0])
+            n = int(target.shape[0]) + self.pad
             seed = int(self.rng.randint(self.stride))
             for start, end in zip(range(seed, n, self.stride), range(seed + self.window_size, n + 1, self.stride)):
                 self.inputs.append((vid, start, end))
@@ -217,9 +223,17 @@ class WindowDataset(torch.utils.data.Dataset):
     def __getitem__(self, index):
         vid, start, end = self.inputs[index]
         rgb, flow, target = self.videos[vid]
-        f32 = lambda a: torch.as_tensor(a[start:end]).to(torch.float32)
-        fl = torch.zeros(end - start, self.d_flow, dtype=torch.float32) if flow is None else f32(flow)
-        return f32(rgb), fl, f32(target), vid, start, end
+        lo, hi = max(start - self.pad, 0), end - self.pad   # stored frames covered by the window
+        z = (end - start) - (hi - lo)                       # leading dummy frames
+
+        def cut(a, width):
+            out = torch.zeros(end - start, width, dtype=torch.float32)
+            if a is not None and hi > lo:
+                out[z:] = torch.as_tensor(a[lo:hi]).to(torch.float32)
+            return out
+
+        return cut(rgb, int(rgb.shape[1])), cut(flow, self.d_flow if flow is None else int(flow.shape[1])), \
+            cut(target, int(target.shape[1])), vid, start, end
 
 
 def train_one_step(model, criterion, optimizer, rgb, flow, target, group=None):

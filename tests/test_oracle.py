@@ -146,3 +146,27 @@ def test_aggregate_restatements_agree_on_random_sequences(c_oracle, tmp_path):
             assert json.load(open(out))["v"] == want
 
     check()
+
+
+# ------------------------------------------------------------------------------ long sequences (reference's own eval shape)
+@pytest.mark.parametrize("name", ["epic_b1_t12531", "asm_b1_t9507"])
+def test_numpy_restatement_matches_reference_on_whole_videos(name):
+    """Goldens made by the live reference at its real evaluation lengths (oracle/gen_golden_long.py): the fp32
+    restatement must still agree at the END of 10^4 recurrence steps."""
+    from prego_b200 import synthetic
+    meta = json.load(open(os.path.join(GOLD, "meta_long.json")))
+    c = meta["cases"][name]
+    z = np.load(os.path.join(GOLD, f"long_{name}.npz"))
+    cfg = dict(getattr(synthetic, c["cfg"]))
+    rgb, flow = synthetic.feature_batch([c["stream_id"]], c["T"], "cpu", False)
+    sha = lambda t: hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+    assert sha(rgb) == c["rgb_sha256"] and sha(flow) == c["flow_sha256"]
+    sd = synthetic.seeded_model(cfg, seed=meta["seed"]).state_dict()
+    probs, logits, h_last = miniroad_np.forward(sd, rgb.numpy(), flow.numpy(), return_all=True)
+    fr = z["frames"]
+    assert np.abs(logits[0][fr] - z["logits"]).max() <= 1e-4 * float(z["max_abs_logit"])
+    assert np.abs(probs[0][fr] - z["probs"]).max() <= 2e-6
+    assert np.abs(h_last[0] - z["h_last"]).max() <= 5e-5
+    bad = miniroad_np.labels_from_probs(probs[0]) != z["labels"]
+    assert bad.mean() <= 1e-3 and np.all(z["margin"][bad] < 1e-4)
+    assert hashlib.sha256(z["labels"].astype(np.int16).tobytes()).hexdigest() == c["labels_sha256"]

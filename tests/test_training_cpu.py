@@ -83,8 +83,9 @@ def test_allreduce_gradients_world2():
 
 
 def test_window_dataset_matches_reference_sampling():
-    """WindowDataset reproduces dataset.py:113-119: windows [seed + k * stride, seed + k * stride + W) while they fit,
-    one random offset per video per (re-)initialisation, items in the reference's tuple layout."""
+    """WindowDataset reproduces dataset.py:53-55,77-82,113-119: window_size - 1 zero dummy frames in front of every
+    video, windows [seed + k * stride, seed + k * stride + W) in the PADDED numbering while they fit, one random
+    offset per video per (re-)initialisation, items in the reference's tuple layout."""
     import numpy as np
     from prego_b200 import WindowDataset
 
@@ -93,20 +94,85 @@ def test_window_dataset_matches_reference_sampling():
         def randint(self, n): return self.vals.pop(0) % n
 
     T, W, S, K = 300, 128, 4, 7
+    P = W - 1
     vids = {"a": (np.arange(T * 8, dtype=np.float64).reshape(T, 8), None, np.eye(K)[np.arange(T) % K]),
-            "b": (np.ones((130, 8)), np.full((130, 8), 2.0), np.eye(K)[np.zeros(130, dtype=int)])}
-    ds = WindowDataset(vids, W, S, d_flow=8, rng=FixedRng([3, 1, 0, 2]))
-    exp_a = list(zip(range(3, T, S), range(3 + W, T + 1, S)))
-    exp_b = list(zip(range(1, 130, S), range(1 + W, 131, S)))
-    assert [(v, s, e) for v, s, e in ds.inputs] == [("a", s, e) for s, e in exp_a] + [("b", s, e) for s, e in exp_b]
-    assert len(exp_b) == 1 and exp_a[-1][1] <= T
+            "b": (np.ones((130, 8)), np.full((130, 8), 2.0), np.eye(K)[np.zeros(130, dtype=int)]),
+            "short": (np.full((5, 8), 3.0), None, np.eye(K)[np.ones(5, dtype=int)])}   # shorter than the window
+    ds = WindowDataset(vids, W, S, d_flow=8, rng=FixedRng([3, 1, 2, 0, 2, 1]))
+    exp_a = list(zip(range(3, T + P, S), range(3 + W, T + P + 1, S)))
+    exp_b = list(zip(range(1, 130 + P, S), range(1 + W, 130 + P + 1, S)))
+    exp_s = list(zip(range(2, 5 + P, S), range(2 + W, 5 + P + 1, S)))
+    assert [(v, s, e) for v, s, e in ds.inputs] == [("a", s, e) for s, e in exp_a] + [("b", s, e) for s, e in exp_b] + \
+        [("short", s, e) for s, e in exp_s]
+    assert len(exp_s) == 1 and exp_a[-1][1] <= T + P   # the front pad lets a 5-frame video yield a window
     rgb, flow, tgt, vid, start, end = ds[0]
     assert (vid, start, end) == ("a", 3, 131) and rgb.dtype == torch.float32 and tuple(rgb.shape) == (W, 8)
     assert float(flow.abs().sum()) == 0 and tuple(flow.shape) == (W, 8) and tuple(tgt.shape) == (W, K)
-    assert float(rgb[0, 0]) == 24.0
-    assert float(ds[len(exp_a)][1][0, 0]) == 2.0
-    ds._init_features()   # new offsets (0 and 2), as main.py:101 does after every epoch
-    assert ds.inputs[0] == ("a", 0, 128) and ds.inputs[-1][0] == "b" and ds.inputs[-1][1] == 2
+    # padded frames 3..126 are dummies (features and targets zero), padded frame 127 is the video's frame 0
+    assert float(rgb[:P - 3].abs().sum()) == 0 and float(tgt[:P - 3].abs().sum()) == 0
+    assert float(rgb[P - 3, 1]) == 1.0 and float(rgb[-1, 0]) == 24.0 and int(tgt[-1].argmax()) == 3
+    fb = ds[len(exp_a)][1]
+    assert float(fb[-1, 0]) == 2.0 and float(fb[0, 0]) == 0.0
+    ds._init_features()   # new offsets, as main.py:101 does after every epoch
+    assert ds.inputs[0] == ("a", 0, 128) and ds.inputs[-1][0] == "short" and ds.inputs[-1][1] == 1
+    plain = WindowDataset(vids, W, S, d_flow=8, rng=FixedRng([3, 1, 0]), front_pad=False)
+    assert plain.inputs[0] == ("a", 3, 131) and float(plain[0][0][0, 0]) == 24.0 and all(v != "short" for v, _, _ in plain.inputs)
+
+
+_REF_DATASET_SCRIPT = r"""
+import json, os, sys, types
+import numpy as np, torch
+sys.modules["ipdb"] = types.SimpleNamespace(set_trace=lambda *a, **k: None)   # the reference leaves breakpoints in (SURVEY 0.5)
+sys.path.insert(0, "/root/reference/step_recognition")
+sys.path.insert(0, sys.argv[2])
+from datasets import build_dataset  # noqa: E402  (datasets/dataset_builder.py:11-13)
+from prego_b200 import WindowDataset  # noqa: E402
+root = sys.argv[1]
+rs = np.random.RandomState(0)
+K, W, S = 5, 16, 4
+lengths = {"v0": 40, "v1": 9, "v2": 77}
+for sub in ("target", "rgb_anet_resnet50", "rgb_as_flow/rgb_anet_resnet50"):
+    os.makedirs(os.path.join(root, sub), exist_ok=True)
+videos = {}
+for vid, T in lengths.items():
+    tgt = np.eye(K)[rs.randint(0, K, T)]
+    rgb = rs.rand(T, 2048)
+    np.save(os.path.join(root, "target", vid + ".npy"), tgt)
+    np.save(os.path.join(root, "rgb_anet_resnet50", vid + ".npy"), rgb)
+    np.save(os.path.join(root, "rgb_as_flow/rgb_anet_resnet50", vid + ".npy"), rgb)
+    videos[vid] = (rgb, None, tgt)
+json.dump({"EPIC-TENT-O": {"train_session_set": list(lengths), "test_session_set": []}}, open(os.path.join(root, "vl.json"), "w"))
+cfg = dict(root_path=root, window_size=W, stride=S, data_name="EPIC-TENT-O", video_list_path=os.path.join(root, "vl.json"),
+           num_classes=K, annotation_type="target", rgb_type="rgb_anet_resnet50", flow_type="flow_anet_resnet50")
+np.random.seed(11)
+ref = build_dataset(cfg)(cfg, "train")
+np.random.seed(11)
+mine = WindowDataset(videos, W, S, d_flow=2048)
+assert len(ref) == len(mine) > 0, (len(ref), len(mine))
+assert [(v, s, e) for v, s, e, _ in ref.inputs] == list(mine.inputs)
+for i in range(len(ref)):
+    a, b = ref[i], mine[i]
+    for x, y in zip(a[:3], b[:3]):
+        assert x.dtype == y.dtype and torch.equal(x, y), i
+    assert tuple(a[3:]) == tuple(b[3:])
+np.random.seed(12); ref._init_features()      # main.py:101
+np.random.seed(12); mine._init_features()
+assert [(v, s, e) for v, s, e, _ in ref.inputs] == list(mine.inputs)
+print("OK", len(ref))
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/step_recognition"), reason="the reference checkout is only mounted in the build container")
+def test_window_dataset_against_the_live_reference_dataset(tmp_path):
+    """The reference's own THUMOSDataset (train mode) on .npy files written here vs WindowDataset on the same arrays:
+    same (vid, start, end) list under the same numpy seed, bit-identical items, also after _init_features()."""
+    import subprocess
+    import sys
+    script = tmp_path / "ref_ds.py"
+    script.write_text(_REF_DATASET_SCRIPT)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, str(script), str(tmp_path / "data"), root], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def test_trainer_registry_and_optimizer_builder():
