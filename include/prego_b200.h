@@ -131,6 +131,10 @@ int prego_online_trace(prego_online_t* session, int64_t* out, int32_t max_ctas, 
 /* Device-side watchdog: the persistent recurrence kernels bound every inter-CTA spin; if a peer never shows up
  * they set a flag instead of hanging the GPU.  Reads (and clears) it; synchronises the device.  0 = healthy. */
 int prego_device_error(prego_model_t* model, int32_t* out);
+/* How many times the batched recurrence had to be launched WITHOUT the cooperative attribute (driver refused it for
+ * the cluster launch; taken only when the occupancy calculator confirms every CTA pair is co-resident, otherwise
+ * prego_forward fails).  0 on a healthy B200 stack; no reference counterpart. */
+int prego_recurrence_fallbacks(prego_model_t* model, int64_t* out);
 
 /* ---- Training step (reference: rnn.py:51-71 in train mode, trainer/train.py:20-24) -------------------------
  * prego_train_forward computes the raw logits [B, T, K] (train-mode out['logits'], rnn.py:67) with dropout active

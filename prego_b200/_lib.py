@@ -98,6 +98,7 @@ SIGNATURES = {
     "prego_online_close": (C.c_int, [C.c_void_p]),
     "prego_online_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "prego_device_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "prego_recurrence_fallbacks": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "prego_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64]),
     "prego_train_forward": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
     "prego_train_backward": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),

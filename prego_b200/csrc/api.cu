@@ -9,7 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <tuple>
+#include <vector>
 
 #include "../../include/prego_b200.h"
 #include "aggregate.cuh"
@@ -137,6 +140,27 @@ inline int grid_for(int64_t work_items, int threads, int sm_count) {
     return static_cast<int>(blocks);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (function, DEVICE): a model created on a second GPU of
+// the same process needs its own opt-in.  Remembers the largest size set per (function, current device).
+int ensure_dyn_smem(const void* fn, int bytes) {
+    static std::mutex mu;
+    static std::vector<std::tuple<const void*, int, int>> done;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& e : done) {
+        if (std::get<0>(e) == fn && std::get<1>(e) == dev) {
+            if (std::get<2>(e) >= bytes) return PREGO_OK;
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            std::get<2>(e) = bytes;
+            return PREGO_OK;
+        }
+    }
+    if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.emplace_back(fn, dev, bytes > 48 * 1024 ? bytes : 48 * 1024);
+    return PREGO_OK;
+}
+
 constexpr int kProfMaxEvents = 8192;
 constexpr int kLatencyMaxB = 16;  // up to this many streams the recurrence runs on the persistent SIMT kernel
 
@@ -169,6 +193,7 @@ struct prego_model {
     uint4* xchg_bwd = nullptr;  // [2][4][H] exchange words of the persistent BPTT kernel
     int* err_flag = nullptr;
     uint32_t tag_base = 0;
+    int64_t coop_fallbacks = 0;  // persistent recurrence launched WITHOUT the cooperative attribute (occupancy-checked)
     // side stream: stages the features of the next time chunk (HBM-bound) under the current chunk's GEMMs
     cudaStream_t side = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -244,12 +269,8 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N,
                    int sm_count, cudaStream_t stream, const char* name) {
     using Cfg = GemmCfg<TILE_N>;
     auto kfn = gemm_tc_kernel<TILE_N, STAGES, FMT, Epi>;
-    static bool attr_set = false;  // per instantiation
     const int smem = Cfg::smem_bytes(STAGES);
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    RC_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kfn), smem));
     const int tiles = (N / TILE_N) * ((M + kTileM - 1) / kTileM);
     const int grid = tiles < sm_count ? tiles : sm_count;
     kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, M, N, K, a_c1, epi);
@@ -264,12 +285,8 @@ int launch_gemm_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N
                     int rows_per_c1 = 0) {
     using Cfg = Gemm2Cfg<TILE_N>;
     auto kfn = gemm_tc2_kernel<TILE_N, STAGES, FMT, Epi>;
-    static bool attr_set = false;
     const int smem = Cfg::smem_bytes(STAGES);
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    RC_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kfn), smem));
     const int tiles = (N / TILE_N) * ((M + 2 * kTileM - 1) / (2 * kTileM));
     int grid = 2 * tiles < sm_count ? 2 * tiles : (sm_count & ~1);
     {   // experiment knob: cap the number of CTA pairs (e.g. a multiple of N / TILE_N so tiles sharing an A block stay in one wave)
@@ -362,11 +379,7 @@ template <int NB, bool REGW>
 int launch_latency_impl(const GruLatencyArgs& a, int H, cudaStream_t stream) {
     auto kfn = gru_latency_kernel<NB, REGW>;
     const size_t smem = ((REGW ? 0 : 3 * kLatUnitsPerCta * H) + 2 * NB * H) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    RC_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kfn), (int)smem));
     GruLatencyArgs args = a;
     void* params[] = {&args};
     CUDA_TRY(cudaLaunchCooperativeKernel((void*)kfn, dim3(H / kLatUnitsPerCta), dim3(kLatThreads), params, smem, stream));
@@ -591,11 +604,7 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
         RC_TRY(make_tmap_tm(&tmGi, kF16, gi, 3 * H, B, tc, 2));
         RC_TRY(make_tmap_tm(&tmHrelu, dt, hrelu, H, B, tc, 2));
         auto kfn = gru_seq_kernel<FMT>;
-        static bool attr_set = false;
-        if (!attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmemBytes));
-            attr_set = true;
-        }
+        RC_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kfn), kGruSmemBytes));
         const int m_tiles = (int)((B + 2 * kTileM - 1) / (2 * kTileM));
         const int per_step = (3 * H / kGruTileN) * m_tiles;  // CTA-pair tiles per time step
         const int max_grid = m->sm_count & ~1;
@@ -619,9 +628,24 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
             cfg.numAttrs = 1;
             cudaError_t le = cudaLaunchKernelEx(&cfg, kfn, tmHseq, tmW, tmGi, tmHrelu, ga);
             if (le != cudaSuccess) {
+                // Cooperative attribute refused (cluster launches on some drivers).  The dependency spins need every pair
+                // resident: fall back to a plain launch ONLY when the occupancy calculator says the whole grid fits at
+                // once, otherwise fail loudly -- never spin on CTAs that may not be scheduled.
                 (void)cudaGetLastError();
-                cfg.numAttrs = 0;  // cooperative attribute rejected with clusters: plain launch, grid <= resident CTAs
+                cfg.numAttrs = 0;
+                int max_clusters = 0;
+                cudaLaunchAttribute cattr[1];
+                cattr[0].id = cudaLaunchAttributeClusterDimension;
+                cattr[0].val.clusterDim.x = 2; cattr[0].val.clusterDim.y = 1; cattr[0].val.clusterDim.z = 1;
+                cudaLaunchConfig_t occ = cfg;
+                occ.attrs = cattr;
+                occ.numAttrs = 1;
+                CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &occ));
+                if (2 * max_clusters < grid)
+                    return fail(PREGO_ERR_CUDA, "persistent recurrence: cooperative launch refused (%s) and only %d of %d CTA pairs can be co-resident",
+                                cudaGetErrorString(le), max_clusters, grid / 2);
                 CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, tmHseq, tmW, tmGi, tmHrelu, ga));
+                m->coop_fallbacks += 1;
             }
             launches = 2;
         } else {
@@ -663,12 +687,8 @@ int online_step_r(prego_model* m, const prego_forward_args_t* a, const Plan& p, 
     float* y = reinterpret_cast<float*>(ws + p.online);
     float* gi = y + kOnlineMaxRows * E;
     float* hrelu = gi + kOnlineMaxRows * 3 * H;
-    static int attr_max = 48 * 1024;  // opt-in limit set so far for this instantiation (models may differ in Din)
     const int smem1 = R * Din * 2;
-    if (smem1 > attr_max) {
-        CUDA_TRY(cudaFuncSetAttribute(online_proj1<FMT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-        attr_max = smem1;
-    }
+    RC_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(online_proj1<FMT, R>), smem1));  // models may differ in Din
     const int wpb = kOnlineThreads / 32;
     online_proj1<FMT, R><<<(E + wpb - 1) / wpb, kOnlineThreads, smem1, s>>>(static_cast<const float*>(a->rgb), static_cast<const float*>(a->flow), reinterpret_cast<const OpT*>(m->w1_16[FMT]), m->b1, y,
                                                                             rows, d.d_rgb, d.d_flow, E, a->T, 0);
@@ -1103,6 +1123,13 @@ int prego_device_error(prego_model_t* m, int32_t* out) {
     CUDA_TRY(cudaMemcpy(&v, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));  // synchronises with prior work
     *out = v;
     if (v != 0) CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
+    return PREGO_OK;
+}
+
+int prego_recurrence_fallbacks(prego_model_t* m, int64_t* out) {
+    RC_TRY(check_model(m, false));
+    if (out == nullptr) return fail(PREGO_ERR_INVALID, "out is NULL");
+    *out = m->coop_fallbacks;
     return PREGO_OK;
 }
 

@@ -58,11 +58,45 @@ class Evaluate(nn.Module):
         self.last_result = None
 
     def eval(self, model, dataloader, logger, device):
+        """eval.py:30-81.  ``cfg['eval_batch_streams']`` (default 64) > 1 selects the GPU-resident batched evaluator
+        (SURVEY 8f row 1): the loader's whole-video items are bucketed by length, end-padded (the GRU is causal, so
+        padding cannot change earlier frames) and run many videos per forward; labels stay on the device and come back
+        in ONE D2H copy for the JSON.  ``eval_batch_streams: 1`` keeps the reference's one-video-per-forward loop."""
         model.eval()
-        output = {}
-        pred_scores, gt_targets = [], []
-        num_frames = 0
+        batch_streams = int(self.cfg.get("eval_batch_streams", 64))
         t_start = time.perf_counter()
+        if batch_streams > 1 and hasattr(model, "infer"):
+            vids, pred_scores, gt_targets, pred_labels = self._eval_batched(model, dataloader, device, batch_streams)
+        else:
+            vids, pred_scores, gt_targets, pred_labels = self._eval_per_video(model, dataloader, device)
+        if hasattr(model, "check_device"):
+            model.check_device("Evaluate.eval")   # before anything is written: a watchdog trip means garbage labels
+        num_frames = int(sum(p.shape[0] for p in pred_scores))
+        if self.cfg["eval"] is not None:
+            # eval.py:51-65: {"pred": np.argmax(prob), "gt": np.argmax(target)} per video; ONE D2H copy for all videos
+            lens = [int(p.shape[0]) for p in pred_labels]
+            pred_h = torch.cat([p.reshape(-1) for p in pred_labels]).cpu()
+            gt_h = torch.cat([torch.argmax(t, dim=1) for t in gt_targets]).cpu()   # first max, as np.argmax (eval.py:54)
+            output, off = {}, 0
+            for vid, n in zip(vids, lens):
+                output[vid] = {"pred": pred_h[off:off + n].tolist(), "gt": gt_h[off:off + n].tolist()}
+                off += n
+            os.makedirs(self.OUTPUT_DIR, exist_ok=True)
+            with open(os.path.join(self.OUTPUT_DIR, self.OUTPUT_FILE), "w") as fp:
+                json.dump(output, fp)
+        elapsed = time.perf_counter() - t_start
+        self.last_fps = num_frames / max(elapsed, 1e-9)
+        result = perframe_average_precision(torch.cat(pred_scores), torch.cat(gt_targets),
+                                            self.all_class_names, None, self.metric)
+        self.last_result = result
+        if logger is not None:
+            logger.info(f"Processed {num_frames} frames in {elapsed:.1f} seconds ({self.last_fps:.1f} FPS)")
+        return result["mean_AP"]
+
+    @staticmethod
+    def _eval_per_video(model, dataloader, device):
+        """The reference's loop (eval.py:36-56): one whole video per forward; nothing leaves the device here."""
+        vids, pred_scores, gt_targets, pred_labels = [], [], [], []
         with torch.no_grad():
             for rgb_input, flow_input, target, vid, _start, _end in dataloader:
                 rgb_input = rgb_input.to(device, non_blocking=True)
@@ -76,27 +110,43 @@ class Evaluate(nn.Module):
                     flow_input = flow_input.to(device, non_blocking=True)
                     out_dict = model(rgb_input, flow_input)
                 prob_val = out_dict["logits"].squeeze(0)                       # eval.py:46, kept on the device
-                target_dev = target.squeeze(0).to(device, non_blocking=True)
+                labels = getattr(model, "last_labels", None)
+                vids.append(vid[0])
                 pred_scores.append(prob_val)
-                gt_targets.append(target_dev)
-                num_frames += prob_val.shape[0]
-                if self.cfg["eval"] is not None:
-                    labels = getattr(model, "last_labels", None)
-                    pred = labels.squeeze(0) if labels is not None else torch.argmax(prob_val, dim=1)
-                    gt = torch.argmax(target_dev, dim=1)                       # eval.py:54 (first max, as np.argmax)
-                    output[vid[0]] = {"pred": pred.cpu().tolist(), "gt": gt.cpu().tolist()}
-        if self.cfg["eval"] is not None:
-            os.makedirs(self.OUTPUT_DIR, exist_ok=True)
-            with open(os.path.join(self.OUTPUT_DIR, self.OUTPUT_FILE), "w") as fp:
-                json.dump(output, fp)
-        elapsed = time.perf_counter() - t_start
-        self.last_fps = num_frames / max(elapsed, 1e-9)
-        result = perframe_average_precision(torch.cat(pred_scores), torch.cat(gt_targets),
-                                            self.all_class_names, None, self.metric)
-        self.last_result = result
-        if logger is not None:
-            logger.info(f"Processed {num_frames} frames in {elapsed:.1f} seconds ({self.last_fps:.1f} FPS)")
-        return result["mean_AP"]
+                gt_targets.append(target.squeeze(0).to(device, non_blocking=True))
+                pred_labels.append(labels.squeeze(0) if labels is not None else torch.argmax(prob_val, dim=1))
+        return vids, pred_scores, gt_targets, pred_labels
+
+    @staticmethod
+    def _eval_batched(model, dataloader, device, batch_streams):
+        """Many videos per forward.  Items are drained from the loader (the reference loader already holds every video in
+        RAM, dataset.py:30-43), sorted by length, and each bucket is assembled end-padded in ONE pinned staging buffer
+        and copied with one H2D per stream; results are returned in the loader's order."""
+        items = [(rgb[0], flow[0], target[0], vid[0]) for rgb, flow, target, vid, _s, _e in dataloader]
+        n = len(items)
+        zero_flow = n > 0 and all(_is_zero_flow(model, it[1]) for it in items)
+        order = sorted(range(n), key=lambda i: -int(items[i][0].shape[0]))
+        probs_of, labels_of, gt_of = [None] * n, [None] * n, [None] * n
+        with torch.no_grad():
+            for s in range(0, n, batch_streams):
+                idx = order[s:s + batch_streams]
+                tmax = int(items[idx[0]][0].shape[0])
+
+                def staged(col, width):
+                    host = torch.zeros(len(idx), tmax, width, dtype=torch.float32, pin_memory=True)
+                    for j, i in enumerate(idx):
+                        t = int(items[i][col].shape[0])
+                        host[j, :t].copy_(items[i][col])
+                    return host.to(device, non_blocking=True)
+
+                rgb = staged(0, int(items[idx[0]][0].shape[1])) if getattr(model, "use_rgb", True) else None
+                flow = None if (zero_flow or not getattr(model, "use_flow", True)) else staged(1, int(items[idx[0]][1].shape[1]))
+                out = model.infer(rgb, flow, want_probs=True, want_labels=True, zero_flow=zero_flow)
+                for j, i in enumerate(idx):
+                    t = int(items[i][0].shape[0])
+                    probs_of[i], labels_of[i] = out["probs"][j, :t], out["labels"][j, :t]
+                    gt_of[i] = items[i][2].to(device, non_blocking=True)
+        return [it[3] for it in items], probs_of, gt_of, labels_of
 
     def forward(self, model, dataloader, logger, device):
         return self.eval(model, dataloader, logger, device)
@@ -135,6 +185,8 @@ class ANT_Evaluate(nn.Module):
                 gt_targets.append(target.to(device, non_blocking=True).reshape(-1, K))
                 ant_pred_scores.append(out_dict["anticipation_logits"].reshape(-1, A, K))
                 ant_gt_targets.append(ant_target.to(device, non_blocking=True).reshape(-1, A, K))
+        if hasattr(model, "check_device"):
+            model.check_device("ANT_Evaluate.eval")
         elapsed = time.perf_counter() - t_start
         pred, gt = torch.cat(pred_scores), torch.cat(gt_targets)
         ant_pred, ant_gt = torch.cat(ant_pred_scores), torch.cat(ant_gt_targets)

@@ -223,6 +223,8 @@ def predict_labels_streamed(model, store: FeatureStore, device, batch_streams: i
         for j, i in enumerate(idx):
             v = store.videos[i]
             out[v.vid] = labels[j, : v.T].clone()
+    if hasattr(model, "check_device"):
+        model.check_device("predict_labels_streamed")
     return {v.vid: out[v.vid] for v in store.videos}
 
 

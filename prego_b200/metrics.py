@@ -66,6 +66,7 @@ def perframe_average_precision(prediction, ground_truth, class_names, postproces
     if postprocessing is not None:
         raise RuntimeError("postprocessing (THUMOS) is outside the hot path")
     ap, num_pos = average_precision_per_class(prediction, ground_truth)
+    pred_mass = prediction.sum(dim=0, dtype=torch.float64).cpu().numpy()   # metrics.py:58 prints int(np.sum(prediction[:, idx]))
     result = OrderedDict()
     result["per_class_AP"] = OrderedDict()
     result["num"] = OrderedDict()
@@ -74,7 +75,8 @@ def perframe_average_precision(prediction, ground_truth, class_names, postproces
             continue
         if num_pos[idx] > 0:
             result["per_class_AP"][class_name] = float(ap[idx])
-            result["num"][class_name] = int(num_pos[idx])
+            # the reference's log string (metrics.py:58); 'true' = sum of the one-hot column = number of positive frames
+            result["num"][class_name] = f"[true: {int(num_pos[idx])}, pred:{int(pred_mass[idx])}, AP:{float(ap[idx]) * 100:.1f}]"
     vals = list(result["per_class_AP"].values())
     result["mean_AP"] = float(np.mean(vals)) if vals else float("nan")
     return result

@@ -83,7 +83,6 @@ class MROAD(nn.Module):
         self._handle_device = None
         self._packed_key = None
         self._workspace = None
-        self._train_ws = None
         self._ant_workspace = None
         self.last_labels = None  # int32 [B, T] labels of the last forward (fused argmax)
 
@@ -236,6 +235,23 @@ class MROAD(nn.Module):
         _lib.check(_lib.load().prego_device_error(self._handle, C.byref(v)), "prego_device_error")
         return int(v.value)
 
+    def recurrence_fallbacks(self) -> int:
+        """Launches of the batched recurrence that ran without the cooperative attribute (0 on a healthy stack)."""
+        if self._handle is None:
+            return 0
+        v = C.c_int64(0)
+        _lib.check(_lib.load().prego_recurrence_fallbacks(self._handle, C.byref(v)), "prego_recurrence_fallbacks")
+        return int(v.value)
+
+    def check_device(self, where: str = "") -> None:
+        """Raise if a persistent kernel's watchdog fired since the last check: its outputs (labels, mAP, gradients)
+        would be garbage.  Called at the end of every product-level loop (evaluation, epoch, batched prediction);
+        synchronises the device, so never per step."""
+        err = self.device_error()
+        if err != 0:
+            raise RuntimeError(f"prego_b200: a persistent recurrence kernel timed out waiting for a peer CTA (flag {err})"
+                               f"{' during ' + where if where else ''}; results of this run are invalid")
+
     def profile_begin(self):
         """Arm per-phase CUDA-event timing inside the library (used by bench.py's roofline)."""
         if self._handle is None:
@@ -316,7 +332,6 @@ class MROADA(MROAD):
         self._packed_key = None
         self._ant_key = None
         self._workspace = None
-        self._train_ws = None
         self._ant_workspace = None
         self.last_labels = None
         self.last_anticipation_labels = None  # int32 [B, T, A]

@@ -40,6 +40,8 @@ def predict_labels(model, videos: Sequence[Tuple[str, torch.Tensor, torch.Tensor
         labels = model.infer(rgb, flow, want_probs=False, want_labels=True, precision=precision)["labels"]
         for j, i in enumerate(idx):
             out[videos[i][0]] = labels[j, : int(videos[i][1].shape[0])]
+    if hasattr(model, "check_device"):
+        model.check_device("predict_labels")
     return {v[0]: out[v[0]] for v in videos}  # original order
 
 

@@ -55,10 +55,11 @@ class MiniROADTrainFn(torch.autograd.Function):
             module._ensure_handle(device)
             module._sync_weights(lib, device)
             need = lib.prego_train_workspace_bytes(module._handle, B, T)
-            ws = module._train_ws
-            if ws is None or ws.device != device or ws.numel() < need + 1024:
-                module._train_ws = None
-                ws = module._train_ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
+            # the saved activations (gates, h_t, e, y, masks) belong to THIS forward: one workspace per call, kept alive
+            # by ctx until its backward ran, so a second train-mode forward before the first backward (gradient
+            # accumulation, two views, a loss over several batches) cannot overwrite or free them; torch's caching
+            # allocator makes the steady-state cost of the per-call allocation nil
+            ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
             ws_ptr = ws.data_ptr() + (-ws.data_ptr()) % 1024
             rgb_c = rgb.contiguous() if module.use_rgb else None
             flow_c = flow.contiguous() if module.use_flow else None
@@ -71,7 +72,7 @@ class MiniROADTrainFn(torch.autograd.Function):
             _lib.check(lib.prego_train_forward(module._handle, C.byref(args), stream), "prego_train_forward")
         ctx.module, ctx.rgb, ctx.flow, ctx.seed = module, rgb_c, flow_c, int(seed)
         ctx.prec = args.precision
-        ctx.ws_ptr, ctx.need, ctx.B, ctx.T = ws_ptr, need, B, T
+        ctx.ws, ctx.ws_ptr, ctx.need, ctx.B, ctx.T = ws, ws_ptr, need, B, T
         ctx.shapes = [tuple(p.shape) for p in params]
         return logits
 
@@ -90,6 +91,7 @@ class MiniROADTrainFn(torch.autograd.Function):
                                   ctx.prec)
             stream = torch.cuda.current_stream(device).cuda_stream
             _lib.check(lib.prego_train_backward(module._handle, C.byref(args), stream), "prego_train_backward")
+            ctx.ws.record_stream(torch.cuda.current_stream(device))  # freed by autograd right after this returns
         return (None, None, None, None, *grads)
 
 
@@ -179,6 +181,8 @@ def train_one_epoch(trainloader, model, criterion, optimizer, scaler, epoch, dev
             scheduler.step()
         if writer is not None:
             writer.add_scalar("Train Loss", loss.item(), it + epoch * len(trainloader))
+    if hasattr(model, "check_device"):
+        model.check_device(f"training epoch {epoch}")   # a watchdog trip in the persistent recurrence / BPTT kernels = garbage gradients
     return float(epoch_loss)
 
 

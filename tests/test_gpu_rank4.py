@@ -128,7 +128,9 @@ def test_perframe_ap_matches_reference_golden(dev, meta4, fmt):
         for k, v in r["per_class_AP"].items():
             assert abs(v - want[int(k)]) <= AP_TOL, (name, k, v, want[int(k)])
         assert abs(r["mean_AP"] - float(gold[f"{name}.mean_ap"])) <= AP_TOL, name
-        assert r["num"] == {str(k): int((labels == k).sum()) for k in range(1, K) if (labels == k).any()}
+        # metrics.py:58: '[true: <positives>, pred:<int(sum of the class's scores)>, AP:<percent, 1 decimal>]'
+        assert r["num"] == {str(k): f"[true: {int((labels == k).sum())}, pred:{int(scores[:, k].astype(np.float64).sum())}, AP:{r['per_class_AP'][str(k)] * 100:.1f}]"
+                            for k in range(1, K) if (labels == k).any()}
 
 
 def test_perframe_ap_vs_oracle_on_model_probabilities(dev):

@@ -189,3 +189,25 @@ def test_main_training_entry_synthetic(dev, tmp_path):
     ref = synthetic.seeded_model(dict(synthetic.EPIC_TENT_O), seed=20, device="cpu").state_dict()
     assert set(sd) == set(ref) and all(not torch.equal(sd[k], ref[k]) for k in sd)
     assert all(torch.isfinite(v).all() for v in sd.values())
+
+
+def test_two_forwards_before_backward_keep_their_own_activations(dev):
+    """Gradient accumulation / a loss over several batches: a second train-mode forward -- larger, so it
+    would also have re-allocated a shared workspace -- before the first backward must not disturb the first one's
+    saved activations.  The accumulated gradients must equal the sum of the two separate runs."""
+    cfg = dict(synthetic.EPIC_TENT_O, dropout=0.0)
+    crit = OadLoss(cfg)
+    r1, f1 = synthetic.feature_batch([70, 71], 9, "cpu", False)
+    r2, f2 = synthetic.feature_batch([72, 73, 74, 75, 76], 23, "cpu", False)
+    t1 = torch.stack([synthetic.targets(s, 9, 12) for s in (70, 71)])
+    t2 = torch.stack([synthetic.targets(s, 23, 12) for s in (72, 73, 74, 75, 76)])
+    _, _, g1, _ = _grads_cuda(cfg, r1, f1, t1, dev)
+    _, _, g2, _ = _grads_cuda(cfg, r2, f2, t2, dev)
+    model = synthetic.seeded_model(cfg, seed=20, device=dev).train()
+    l1 = crit(model(r1.to(dev), f1.to(dev)), t1.to(dev))
+    l2 = crit(model(r2.to(dev), f2.to(dev)), t2.to(dev))   # second forward BEFORE the first backward
+    (l1 + l2).backward()
+    torch.cuda.synchronize()
+    for k, p in model.named_parameters():
+        want = g1[k] + g2[k]
+        assert (p.grad.cpu() - want).abs().max().item() <= 1e-5 * max(want.abs().max().item(), 1e-6), k
