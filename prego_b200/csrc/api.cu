@@ -603,7 +603,9 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
         RC_TRY(make_tmap_w(&tmW, dt, m->whh_16p[FMT], H, 3 * H, kGruTileN / 2));
         RC_TRY(make_tmap_tm(&tmGi, kF16, gi, 3 * H, B, tc, 2));
         RC_TRY(make_tmap_tm(&tmHrelu, dt, hrelu, H, B, tc, 2));
-        auto kfn = gru_seq_kernel<FMT>;
+        // PREGO_GRU_DBG / PREGO_GRU_STATS (diagnostics, scripts/diag_recurrence.py) select the instrumented instantiation
+        const bool diag = getenv("PREGO_GRU_DBG") != nullptr || getenv("PREGO_GRU_STATS") != nullptr;
+        auto kfn = diag ? gru_seq_kernel<FMT, true> : gru_seq_kernel<FMT, false>;
         RC_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kfn), kGruSmemBytes));
         const int m_tiles = (int)((B + 2 * kTileM - 1) / (2 * kTileM));
         const int per_step = (3 * H / kGruTileN) * m_tiles;  // CTA-pair tiles per time step
@@ -616,6 +618,8 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
             const int64_t items = (int64_t)per_step * tc;
             const int grid = 2 * items < max_grid ? (int)(2 * items) : max_grid;
             GruSeqArgs ga{m->bhh_p, h32t, done, m->err_flag, (int)B, H, 0, tc};
+            if (const char* e = getenv("PREGO_GRU_DBG")) ga.dbg = atoi(e);  // diagnostics: results are garbage with any bit set
+            if (const char* e = getenv("PREGO_GRU_STATS")) ga.stats = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));  // device pointer [grid][16]
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(grid);
             cfg.blockDim = dim3(kGruThreads);

@@ -112,11 +112,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // broadcast through a shuffle so the compiler KNOWS the address is warp-uniform (tcgen05 operands live in uniform registers)
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -138,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::make_idesc(FMT, kTileM, TILE_N);
             int stage = 0;
             uint32_t phase = 0;
@@ -263,10 +264,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ptx::tc_fence_before();
     ptx::cluster_sync();  // barriers of both CTAs initialised before any remote signal
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // broadcast through a shuffle so the compiler KNOWS the address is warp-uniform (tcgen05 operands live in uniform registers)
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
@@ -290,7 +292,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        if (leader && lane == 0) {
+        if (leader && ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::make_idesc(FMT, 2 * kTileM, TILE_N);
             int stage = 0, it = 0;
             uint32_t phase = 0;

@@ -32,7 +32,7 @@
 //         epilogue LSU-bound).  Converted from / to [B, H] once per chunk (simt_kernels.cuh).
 //   done  [Tc, m_tiles] uint32 dependency counters (zeroed by the host before the launch)
 //
-// Warp roles (608 threads): warp 0 = operand TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// Warp roles (640 threads): warps 0 and 19 = operand TMA producers (even / odd k-blocks), warp 1 = TMEM alloc + MMA issuer,
 // warps 2..17 = epilogue (TMEM lane quadrant = warp % 4, hidden-unit group of 16 = (warp - 2) / 4; the
 // epilogue is latency-bound -- MUFU chains, TMEM loads -- so it is spread over 16 warps), warp 18 = gi
 // loader + result storer + publisher.  Results are staged in their own two boxes so the gi boxes can be
@@ -49,8 +49,9 @@
 namespace prego {
 
 constexpr int kGruEpiWarps = 16;
-constexpr int kGruThreads = (kGruEpiWarps + 3) * 32;  // 608
+constexpr int kGruThreads = (kGruEpiWarps + 4) * 32;  // 640
 constexpr int kGruIoWarp = kGruEpiWarps + 2;          // 18
+constexpr int kGruProd2Warp = kGruEpiWarps + 3;       // 19: second operand producer (odd k-blocks)
 constexpr int kGruTileN = 192;
 constexpr int kGruStages = 5;
 constexpr int kGruABytes = kTileM * kTileK * 2;                               // 16384: own 128 rows of h
@@ -95,9 +96,13 @@ struct GruSeqArgs {
     int* err_flag;
     int B, H;
     int t_begin, t_end;
+    long long* stats = nullptr;  // diagnostics: per-CTA wait-cycle counters [grid][16] (PREGO_GRU_STATS)
+    int dbg = 0;        // diagnostics only (PREGO_GRU_DBG): 1 = no gate math, 2 = no dependency waits, 4 = no gi loads, 8 = no result stores / publish, 16 = epilogue handshakes only, 32 / 64 = no W / h operand loads
 };
 
-template <int FMT>
+// DIAG = true compiles the diagnostic knobs (a.dbg) and the per-role wait-cycle counters (a.stats) in; the product
+// instantiation (DIAG = false) carries neither.
+template <int FMT, bool DIAG = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGruThreads, 1)
 gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1) 16-bit, box (64, 128, 1)
                const __grid_constant__ CUtensorMap tmW,      // 2-D (H, 3H) 16-bit, box (64, 96): half a tile
@@ -135,6 +140,9 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
     const int item_begin = a.t_begin * per_step + cluster_id;
     const int item_end = a.t_end * per_step;
     const uint32_t dep_target = 2u * static_cast<uint32_t>(n_tiles);  // both CTAs of all n-tiles of a stream block
+    const int dbg = DIAG ? a.dbg : 0;
+    auto now = [] { return DIAG ? clock64() : 0ll; };
+    long long* const stats = DIAG ? a.stats : nullptr;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmHseq);
@@ -162,45 +170,68 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
     ptx::tc_fence_before();
     ptx::cluster_sync();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // broadcast through a shuffle so the compiler KNOWS the address is warp-uniform (tcgen05 operands live in uniform registers)
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    if (warp == 0) {
-        // ---------------------------------------------------------------- operand producer
-        if (lane == 0) {
-            int stage = 0;
+    if (warp == 0 || warp == kGruProd2Warp) {
+        // ---------------------------------------------------------------- operand producers
+        // One thread needs ~400 cycles per k-block (mbarrier try_wait ~90, expect_tx, two UTMALDG with their uniform-register
+        // set-up): more than the 384 cycles the tensor pipe takes for the k-block's four 256 x 192 x 16 MMAs, so a single
+        // producer can never run ahead and the MMA issuer waits on `full` (measured: 5 500 of 9 550 cycles per item,
+        // profiles/r02_recurrence_diag.txt).  Two producer threads take the even / odd k-blocks of the same stage ring.
+        if (ptx::elect_one()) {
+            const int par = warp == 0 ? 0 : 1;
+            int stage = par, g0 = 0;  // g0: k-blocks issued by both producers before this item (thread `par` takes the global k-blocks g = par mod 2)
             uint32_t phase = 0;
+            long long w_dep = 0, w_empty = 0, t_all = now();
             for (int item = item_begin; item < item_end; item += num_clusters) {
                 const int t = item / per_step, rem = item % per_step;
                 const int mt = rem / n_tiles;
                 const int m0 = mt * (2 * kTileM) + row_base;
                 const int n0 = (rem % n_tiles) * kGruTileN + static_cast<int>(rank) * (kGruTileN / 2);
-                if (a.done != nullptr && t > a.t_begin) dep_wait(a.done + (t - 1) * m_tiles + mt, dep_target, a.err_flag);
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                long long c0 = now();
+                if (a.done != nullptr && t > a.t_begin && !(dbg & 2)) dep_wait(a.done + (t - 1) * m_tiles + mt, dep_target, a.err_flag);
+                w_dep += now() - c0;
+                for (int kb = par ^ (g0 & 1); kb < k_blocks; kb += 2) {
+                    c0 = now();
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    w_empty += now() - c0;
                     uint8_t* sa = smem + stage * kGruStageBytes;
-                    if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * kGruStageBytes);
-                    ptx::tma_load_3d_2sm(&tmHseq, sa, &full_bar[stage], kb * kTileK, m0, t, ptx::kEvictNormal);
-                    ptx::tma_load_2d_2sm(&tmW, sa + kGruABytes, &full_bar[stage], kb * kTileK, n0, ptx::kEvictLast);
-                    if (++stage == kGruStages) {
-                        stage = 0;
+                    const uint32_t tx = ((dbg & 64) ? 0u : 2u * kGruABytes) + ((dbg & 32) ? 0u : 2u * (kGruStageBytes - kGruABytes));
+                    if (leader) { if (tx) ptx::mbar_expect_tx(&full_bar[stage], tx); else ptx::mbar_arrive(&full_bar[stage]); }
+                    if (!(dbg & 64)) ptx::tma_load_3d_2sm(&tmHseq, sa, &full_bar[stage], kb * kTileK, m0, t, ptx::kEvictNormal);
+                    if (!(dbg & 32)) ptx::tma_load_2d_2sm(&tmW, sa + kGruABytes, &full_bar[stage], kb * kTileK, n0, ptx::kEvictLast);
+                    stage += 2;  // this thread's k-blocks are every other slot of the ring
+                    if (stage >= kGruStages) {
+                        stage -= kGruStages;
                         phase ^= 1;
                     }
                 }
+                g0 += k_blocks;
+            }
+            if (stats != nullptr && par == 0) {
+                long long* st = stats + blockIdx.x * 16;
+                st[0] = now() - t_all; st[1] = w_dep; st[2] = w_empty;
             }
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------------- MMA issuer
-        if (leader && lane == 0) {
+        if (leader && ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::make_idesc(FMT, 2 * kTileM, kGruTileN);
             int stage = 0, it = 0;
             uint32_t phase = 0;
+            long long w_acc = 0, w_full = 0, t_all = now(), c0;
             for (int item = item_begin; item < item_end; item += num_clusters, ++it) {
                 const int buf = it & 1;
+                c0 = now();
                 ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                w_acc += now() - c0;
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * 256;
                 for (int kb = 0; kb < k_blocks; ++kb) {
+                    c0 = now();
                     ptx::mbar_wait(&full_bar[stage], phase);
+                    w_full += now() - c0;
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + stage * kGruStageBytes);
                     const uint64_t adesc = ptx::make_smem_desc_sw128(sa);
@@ -216,20 +247,26 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
                 }
                 ptx::mma_commit_2sm(&acc_full[buf], 3);
             }
+            if (stats != nullptr) {
+                long long* st = stats + blockIdx.x * 16;
+                st[3] = now() - t_all; st[4] = w_acc; st[5] = w_full; st[6] = it;
+            }
         }
     } else if (warp == kGruIoWarp) {
         // ------------------- gi loader + result storer + publisher (TMA both ways)
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int it = 0;
             int pm0 = 0, pnt = 0, pt = 0, pmt = 0;
             auto store_and_publish = [&](int i_prev) {
                 // results of item i_prev are staged (epi_done already observed): store, free the staging, publish
+                if (!(dbg & 8)) {
                 ptx::tma_store_3d(&tmHseq, out_smem, pnt * 64, pm0, pt + 1);
                 ptx::tma_store_3d(&tmHrelu, out_smem + kGruBoxBytes, pnt * 64, pm0, pt);
                 ptx::tma_store_commit();
                 ptx::tma_store_wait_read();
+                }
                 ptx::mbar_arrive(out_free);
-                if (a.done != nullptr) {
+                if (a.done != nullptr && !(dbg & 8)) {
                     ptx::tma_store_wait_all();
                     asm volatile("fence.proxy.async;" ::: "memory");
                     __threadfence();  // also carries the epilogue warps' fp32 state stores (observed through epi_done)
@@ -243,13 +280,17 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
                 const int m0 = mt * (2 * kTileM) + row_base;
                 if (it >= 1) ptx::mbar_wait(gi_free, (it - 1) & 1);  // the epilogue holds the previous gi in registers
                 // gi[t] itself has no dependency (GEMM2 finished before the launch): refill right away
+                if (dbg & 4) {
+                    ptx::mbar_arrive(gi_full);
+                } else {
                 ptx::mbar_expect_tx(gi_full, kGruGiBytes);
 #pragma unroll
                 for (int g = 0; g < 3; ++g)
                     ptx::tma_load_3d(&tmGi, gi_smem + g * kGruBoxBytes, gi_full, nt * kGruTileN + g * 64, m0, t, ptx::kEvictFirst);
+                }
                 {   // gi streams from HBM (GEMM2's 1.6 GB output): warm L2 for this pair's NEXT item now
                     const int nitem = item + num_clusters;
-                    if (nitem < item_end) {
+                    if (nitem < item_end && !(dbg & 4)) {
                         const int t2 = nitem / per_step, rem2 = nitem % per_step;
                         const int m2 = (rem2 / n_tiles) * (2 * kTileM) + row_base, nt2 = rem2 % n_tiles;
 #pragma unroll
@@ -278,6 +319,7 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
         const uint32_t s_box = ptx::smem_u32(gi_smem) + row_off;
         const uint32_t s_out = ptx::smem_u32(out_smem) + row_off;
         int it = 0;
+        long long w_gi = 0, w_accf = 0, w_outf = 0, t_all = now(), c0;
         for (int item = item_begin; item < item_end; item += num_clusters, ++it) {
             const int buf = it & 1;
             const int rem = item % per_step;
@@ -292,7 +334,23 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
             float4* hptr = reinterpret_cast<float4*>(a.h32t) +
                            ((static_cast<int64_t>(row >> 7) * (H / 64) + nt) * 16 + ugrp * 4) * 128 + (row & 127);
             float4 hcur[4];
+            c0 = now();
             ptx::mbar_wait(gi_full, it & 1);
+            w_gi += now() - c0;
+            if (dbg & 16) {  // handshakes only
+                ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+                ptx::tc_fence_after();
+                ptx::mbar_wait(out_free, (it & 1) ^ 1);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(gi_free);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::mbar_arrive_leader(&acc_empty[buf]);
+                    ptx::mbar_arrive(epi_done);
+                }
+                continue;
+            }
             bool early = true;
             if (a.done != nullptr) {
                 const int t = item / per_step;
@@ -306,13 +364,17 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) hcur[i] = __ldcg(hptr + i * 128);
             }
+            c0 = now();
             ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            w_accf += now() - c0;
             ptx::tc_fence_after();
             if (!early) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) hcur[i] = __ldcg(hptr + i * 128);
             }
+            c0 = now();
             ptx::mbar_wait(out_free, (it & 1) ^ 1);  // the previous item's staged results have left
+            w_outf += now() - c0;
             const uint32_t taddr = tmem_base + buf * 256 + (static_cast<uint32_t>(quad * 32) << 16);
             const float* bh = a.bhh + nt * kGruTileN;
             // gi of this thread's 16 units -> registers, then hand the boxes back so the next item's gi streams in
@@ -358,6 +420,7 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int u = 2 * j + e;
+                        if (dbg & 1) { hn[u] = hp[u] + gir[e] + giz[e] + gin[e] + __uint_as_float(vr[u]) + __uint_as_float(vz[u]) + __uint_as_float(vn[u]); continue; }
                         const float rr = fast_sigmoid(gir[e] + __uint_as_float(vr[u]));
                         const float zz = fast_sigmoid(giz[e] + __uint_as_float(vz[u]));
                         const float nn = fast_tanh(gin[e] + rr * (__uint_as_float(vn[u]) + bn[u]));
@@ -385,6 +448,10 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
                 ptx::mbar_arrive_leader(&acc_empty[buf]);
                 ptx::mbar_arrive(epi_done);  // release: the publisher's gpu-scope fence is cumulative over these stores
             }
+        }
+        if (stats != nullptr && warp == 2 && lane == 0) {
+            long long* st = stats + blockIdx.x * 16;
+            st[8] = now() - t_all; st[9] = w_gi; st[10] = w_accf; st[11] = w_outf;
         }
     }
 

@@ -13,6 +13,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One thread of a CONVERGED warp.  The single-thread roles (TMA producer, MMA issuer) must be entered through this, not
+// through `lane == 0`: ptxas recognises elect.sync and emits UTCHMMA / UTMALDG / UTCBAR straight-line, whereas a region
+// guarded by a lane comparison is "divergent code" to it and every tcgen05 / TMA instruction gets wrapped in an
+// ELECT ... BRA.U.ANY waterfall loop (~50 issue cycles each: the MMA issuer then needs ~490 cycles per 4-MMA k-block,
+// which caps 192-column tiles at 79 % of the tensor pipe; scripts/mma_rate.cu, profiles/r02_mma_issue_microbench.txt).
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
