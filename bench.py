@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     ap.add_argument("--no-rank4", action="store_true", help="skip the MiniROADA anticipation / device mAP leg (SURVEY 8f rank 4)")
     ap.add_argument("--no-variants", action="store_true", help="skip the feature-format variants (16-bit features, zero flow)")
+    ap.add_argument("--e2e-direct", type=int, default=0, help="e2e: send this many leading streams of every batch as plain fp32 next to the host-rounded rest")
+    ap.add_argument("--no-library", action="store_true", help="skip the stock-torch (cuBLAS + cuDNN) baseline on the same GPU")
     ap.add_argument("--subchunk", type=int, default=64,
                     help="internal time-chunk of prego_forward inside one step; < --chunk stages the features of chunk c+1 on a side "
                          "stream under chunk c (measured +2 %% at 32, but it blurs the per-kernel roofline timing, so off by default)")
@@ -107,6 +109,9 @@ def dist_env(n):
 
 
 # ----------------------------------------------------------------------------- CPU baseline (oracle port)
+CPU_SAMPLE_STREAMS = 256  # bounded sample of the 4 096-stream workload: large enough that the CPU GEMMs run at their own batch efficiency
+
+
 def cpu_baseline_run(streams, chunk, target_seconds=12.0, repeats=1):
     """Time the ATen-based CPU port of the reference path (oracle/miniroad_torch_cpu.py) on a bounded
     sample of the workload, all host threads.  Returns (frames/s, description, cores)."""
@@ -118,7 +123,7 @@ def cpu_baseline_run(streams, chunk, target_seconds=12.0, repeats=1):
     torch.set_num_threads(cores)
     model = synthetic.seeded_model(dict(synthetic.ASSEMBLY101_O), seed=20)
     port = CpuMiniROAD(model.state_dict())
-    bs = min(streams, 64)
+    bs = min(streams, CPU_SAMPLE_STREAMS)
     g = torch.Generator().manual_seed(1)
     rgb = torch.randn(bs, chunk, 2048, generator=g).abs_()
     flow = torch.randn(bs, chunk, 2048, generator=g).abs_()
@@ -138,6 +143,32 @@ def cpu_baseline_run(streams, chunk, target_seconds=12.0, repeats=1):
     return bs * chunk / dt, f"{bs} of {streams} streams x {chunk} frames per pass, {reps} passes, torch {torch.__version__} CPU (ATen/oneDNN), + aggregate", cores
 
 
+def cpu_whole_video_run(lengths=(2011, 9507)):
+    """BASELINE.md 4.3(a) / configs[0]: the reference's own evaluation shape on the CPU -- ONE whole video per forward
+    (test_batch_size: 1, configs/miniroad_assembly101-O.yaml:17; Assembly101-O median and maximum length), all host
+    threads, followed by aggregate().  Returns {T: {...}}."""
+    from oracle.miniroad_torch_cpu import CpuMiniROAD
+    from oracle import aggregate_np
+    from prego_b200 import synthetic
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = synthetic.seeded_model(dict(synthetic.ASSEMBLY101_O), seed=20)
+    port = CpuMiniROAD(model.state_dict())
+    out = {}
+    for T in lengths:
+        rgb, flow = synthetic.feature_batch([7], T, "cpu", False)
+        port.labels(rgb[:, :64], flow[:, :64])  # warm-up
+        ts = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            labels = port.labels(rgb, flow)
+            aggregate_np.aggregate_video(labels[0], labels[0])
+            ts.append(time.perf_counter() - t0)
+        out[f"T{T}"] = {"frames": T, "seconds": min(ts), "frames_per_s": T / min(ts)}
+    out["note"] = "B = 1 whole-video sequences (the reference's test_batch_size: 1), ATen CPU port + aggregate, best of 2"
+    return out
+
+
 def run_reference(args, world, rank):
     """--impl reference: the reference's CPU implementation of the path (oracle port: the reference's Python
     files cannot travel to the GPU box and it has no compiled sources), rank 0 only."""
@@ -151,7 +182,7 @@ def run_reference(args, world, rank):
     torch.set_num_threads(cores)
     model = synthetic.seeded_model(dict(synthetic.ASSEMBLY101_O), seed=20)
     port = CpuMiniROAD(model.state_dict())
-    bs = 64
+    bs = min(args.streams, CPU_SAMPLE_STREAMS)
     g = torch.Generator().manual_seed(1)
     rgb = torch.randn(bs, args.chunk, 2048, generator=g).abs_()
     flow = torch.randn(bs, args.chunk, 2048, generator=g).abs_()
@@ -173,7 +204,8 @@ def run_reference(args, world, rank):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"Assembly101-O-shaped, {args.streams} streams x {args.chunk}-frame chunks (K=86)", "sample": sample},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                             "whole_video": cpu_whole_video_run()},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -356,6 +388,85 @@ def rank4_leg(dev):
     return out
 
 
+# ----------------------------------------------------------------------------- library baseline (stock torch on the same GPU)
+def library_baseline_leg(dev, B, Tc, local):
+    """SURVEY 2a / BASELINE.md 4.6: the reference's own modules -- nn.Linear / LayerNorm / nn.GRU (cuBLAS + cuDNN persistent RNN) /
+    softmax / argmax, rnn.py:38-71 + eval.py:53 -- on the SAME B200, same step (B streams x Tc frames resident in HBM, K = 86), in
+    the three precisions a user of the reference could select.  Library code end to end: none of this repo's kernels run here."""
+    import torch.nn as nn
+
+    class Ref(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gru = nn.GRU(2048, 1024, 1, batch_first=True)
+            self.layer1 = nn.Sequential(nn.Linear(4096, 2048), nn.LayerNorm(2048), nn.ReLU(), nn.Dropout(0.2))
+            self.fc = nn.Linear(1024, 86)
+
+        def forward(self, rgb, flow):
+            x = self.layer1(torch.cat((rgb, flow), 2))
+            ht, _ = self.gru(x, torch.zeros(1, x.shape[0], 1024, device=x.device, dtype=x.dtype))
+            return torch.softmax(self.fc(torch.relu(ht)), -1).argmax(-1)
+
+    torch.manual_seed(20)
+    m = Ref().to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(1)
+    rgb = torch.randn(B, Tc, 2048, generator=g, device=dev).abs_()
+    flow = torch.randn(B, Tc, 2048, generator=g, device=dev).abs_()
+    out = {}
+    tf32_before = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    for mode, n in (("bf16_autocast", 8), ("tf32", 8), ("fp32", 3)):
+        torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
+        torch.backends.cudnn.allow_tf32 = mode != "fp32"
+        try:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode.startswith("bf16")):
+                for _ in range(3):
+                    m(rgb, flow)
+                sampler = ClockSampler(local)
+                sampler.start()
+                time.sleep(0.25)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                t0 = time.time()
+                e0.record()
+                for _ in range(n):
+                    m(rgb, flow)
+                e1.record()
+                torch.cuda.synchronize()
+                t1 = time.time()
+            ms = e0.elapsed_time(e1) / n
+            out[mode] = {"ms_per_step": ms, "frames_per_s": B * Tc / ms * 1e3, "steps": n, "clocks": sampler.stop(t0, t1)}
+        except Exception as e:  # noqa: BLE001
+            out[mode] = {"error": repr(e)[:200]}
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32_before
+    out["note"] = (f"torch {torch.__version__} (cuBLAS + cuDNN GRU), the reference's module structure, {B} streams x {Tc} frames per step resident in HBM, "
+                   "eval mode, softmax + device argmax; same GPU, same process, right after this repo's legs")
+    del m, rgb, flow
+    torch.cuda.empty_cache()
+    return out
+
+
+def ncu_record(B, Tc, args):
+    """`roofline.traffic` cannot be measured inside a timed run (ncu replays kernels): it is read from the committed capture
+    profiles/ncu_gemm1.json (written by scripts/ncu_extract.py from one `ncu --set full` of this kernel at this shape) and is
+    reported ONLY while the kernel sources still hash to what was captured -- a changed kernel yields null, never a stale number."""
+    import hashlib
+    rec_path = os.path.join(ROOT, "profiles", "ncu_gemm1.json")
+    out = {"traffic": None, "traffic_source": None}
+    if not os.path.exists(rec_path):
+        return out
+    rec = json.load(open(rec_path))
+    h = hashlib.sha256()
+    for f in rec.get("sources", []):
+        h.update(open(os.path.join(ROOT, f), "rb").read())
+    same_shape = (rec.get("streams"), rec.get("chunk"), rec.get("precision")) == (B, min(Tc, args.subchunk), args.precision)
+    if h.hexdigest() == rec.get("sources_sha256") and same_shape:
+        out.update({"traffic": rec["dram_bytes_read"] + rec["dram_bytes_write"], "tensor_pipe_active_pct_ncu": rec.get("tensor_pipe_active_pct"),
+                    "traffic_source": f"{rec['capture']} (kernel sources unchanged since: sha256 {rec['sources_sha256'][:12]})"})
+    else:
+        out["traffic_source"] = f"{rec.get('capture')} is stale for this build / shape: not reported"
+    return out
+
+
 # ----------------------------------------------------------------------------- main arm
 def run_ours(args, world, rank, local):
     import torch.distributed as dist
@@ -379,11 +490,28 @@ def run_ours(args, world, rank, local):
         out = model.infer(rgb, flow, h_state=h, want_probs=False, want_labels=True, precision=args.precision, chunk_T=min(Tc, args.subchunk))
         labels_all[i % K].copy_(out["labels"])
 
+    from prego_b200.sharding import gather_ragged
+    gathered = {"bytes": 0, "sequences": 0}
+
     def collapse():
+        """labels of all K steps -> step sequences per stream (window vote + RLE on the device); under torchrun the collapsed
+        sequences of every rank are gathered on rank 0 (BASELINE configs[3]: 'outputs gathered and collapsed'; SURVEY 8e: the ONE
+        exchange of the inference path, ~200x smaller than the labels)."""
         seq = labels_all.permute(1, 0, 2).reshape(B, K * Tc).contiguous()
         flat = seq.reshape(-1)
         r = aggregate_device(flat, [K * Tc] * B, flat, [K * Tc] * B, 200, 86)
-        return r["pred_counts"].sum() + r["gt_counts"].sum()
+        total = r["pred_counts"].sum() + r["gt_counts"].sum()
+        if world > 1:
+            counts = r["pred_counts"].to(torch.int64)
+            wl = (K * Tc + 199) // 200
+            vals = r["pred_vals"][: B * wl].to(torch.int64).reshape(B, wl)
+            keep = torch.arange(wl, device=dev).view(1, -1) < counts.view(-1, 1)
+            packed = torch.cat([torch.tensor([B], device=dev, dtype=torch.int64), counts, vals[keep]])
+            parts = gather_ragged(packed, 0)
+            if parts is not None:
+                gathered["bytes"] = int(sum(p.numel() for p in parts) * 8)
+                gathered["sequences"] = int(sum(int(p[0]) for p in parts))
+        return total
 
     def barrier():
         if world > 1:
@@ -531,10 +659,8 @@ def run_ours(args, world, rank, local):
             the bytes; the device reads them in place (PREGO_FEAT_16).  `direct` leading streams travel as plain fp32 so that
             the link and the host's memory system finish together.  Bit-identical labels (tests/test_gpu_parity.py)."""
             from prego_b200.ingest import HostRoundingStager
-            cores = os.cpu_count() or 1
-            share = max(1, cores // world)
             st = HostRoundingStager(B, Tc, 2048, 0 if hf is None else 2048, args.precision, dev,
-                                    threads=share - 2 if share > 4 else share, direct_streams=direct)  # two cores stay with Python / the driver
+                                    threads=len(my_cores), direct_streams=direct)  # this rank's core block (bound below); the pool inherits the mask
             hl = torch.empty(B, Tc, dtype=torch.int32).pin_memory()
             dl = torch.empty(B, Tc, dtype=torch.int32, device=dev)
             h2 = torch.zeros(B, 1024, device=dev)
@@ -561,13 +687,71 @@ def run_ours(args, world, rank, local):
             h2d = n_dir * 4 + (hr.numel() + (0 if hf is None else hf.numel()) - n_dir) * 2
             return B * Tc * n_e2e / float(dt) * world, h2d, st.threads
 
+        # one rank = one contiguous block of the host's cores: the rank's Python thread, its rounding pool and (first touch)
+        # its pinned buffers stay there instead of all ranks' threads migrating over all cores
+        all_cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(all_cores) // world)
+        my_cores = all_cores[local * per:(local + 1) * per] or all_cores
+        try:
+            os.sched_setaffinity(0, my_cores)
+        except OSError:
+            my_cores = all_cores
         hr, hf = rgb.cpu().pin_memory(), flow.cpu().pin_memory()
+
+        def host_bounds():
+            """What the HOST side can deliver with every rank active at once: pinned H2D copy rate per GPU and a plain
+            memcpy of the fp32 features by this rank's cores (the read the rounding pool has to do)."""
+            dst = torch.empty_like(rgb)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                dst.copy_(hr, non_blocking=True)
+            torch.cuda.synchronize()
+            h2d = torch.tensor([3 * hr.numel() * 4 / (time.perf_counter() - t0) / 1e9], device=dev)
+            del dst
+            tot_h2d = h2d.clone()
+            if world > 1:
+                dist.all_reduce(tot_h2d)
+                dist.all_reduce(h2d, op=dist.ReduceOp.MIN)
+            out = {"h2d_gbs_per_gpu_min": float(h2d), "h2d_gbs_all_gpus": float(tot_h2d), "cores_per_rank": len(my_cores),
+                   "frames_per_s_bound_fp32_over_link": float(tot_h2d) * 1e9 / BYTES_FEATURES}
+            if args.precision != "fp32":
+                # the rounding pipeline alone (submit + wait, no model call): what this host can stage per second, all ranks at once
+                from prego_b200.ingest import HostRoundingStager
+                st = HostRoundingStager(B, Tc, 2048, 2048, args.precision, dev, threads=len(my_cores))
+                n = 6
+
+                def stage_only(k):
+                    st.submit(0, hr, hf)
+                    for i in range(k):
+                        if i + 1 < k:
+                            st.submit(i + 1, hr, hf)
+                        st.wait(i)
+                        st.release(i)
+                    torch.cuda.synchronize()
+
+                stage_only(2)
+                barrier()
+                t0 = time.perf_counter()
+                stage_only(n)
+                dt = torch.tensor([time.perf_counter() - t0], device=dev)
+                st.close()
+                if world > 1:
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                out["frames_per_s_bound_host_rounded"] = world * B * Tc * n / float(dt)
+                out["host_rounding_fp32_read_gbs_all_ranks"] = out["frames_per_s_bound_host_rounded"] * BYTES_FEATURES / 1e9
+            out["note"] = ("measured with all ranks active at once, staging only (no model call); fp32 host features cost 16 KiB of host-memory reads "
+                           "per frame on either path (the DMA's read, or the rounding pool's), so one host feeding N GPUs is bound by its own memory system")
+            return out
+
+        bounds = host_bounds()
         v, h2d, d2h, n_e2e = e2e_measure(hr, hf, False)
         e2e = {"value": v, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
                "path": "fp32 over the link",
                "note": "pinned host fp32 features -> H2D (copy stream, double-buffered: step i+1 copies while step i computes) -> "
                        "prego_forward -> int32 labels D2H; PCIe-bound (16 KiB/frame); all ranks concurrently, max over ranks"}
         e2e["fp32_over_link"] = {"value": v, "h2d_bytes_per_step": h2d}
+        e2e["host_bounds"] = bounds
         if args.precision != "fp32":
             v2, h2d2, nthreads = e2e_host_round(hr, hf, False, 0)
             e2e["host_rounded"] = {"value": v2, "h2d_bytes_per_step": h2d2, "host_threads": nthreads,
@@ -577,6 +761,17 @@ def run_ours(args, world, rank, local):
             if v2 > v:
                 e2e.update({"value": v2, "h2d_bytes_per_step": h2d2,
                             "path": "fp32 host buffers, operand rounding on the host, 8 KiB/frame over the link"})
+            if args.e2e_direct > 0:
+                # split every batch: `direct` leading streams travel as plain fp32 while the pool rounds the rest.  Off by
+                # default: both paths read the same 16 KiB per frame out of host memory, which is what bounds this loop (measured
+                # r02: 1 152 direct streams 4.12 M frames/s vs 4.72 M without a split on the same lease)
+                direct = args.e2e_direct // 128 * 128
+                v3, h2d3, _ = e2e_host_round(hr, hf, False, direct)
+                e2e["host_rounded_split"] = {"value": v3, "h2d_bytes_per_step": h2d3, "direct_streams": direct,
+                                             "note": "the same loop with `direct_streams` leading streams sent as fp32 (bit-identical labels)"}
+                if v3 > e2e["value"]:
+                    e2e.update({"value": v3, "h2d_bytes_per_step": h2d3,
+                                "path": f"fp32 host buffers, {direct} streams as fp32 + {B - direct} rounded on the host"})
         if variants is not None:
             # the same loop fed in the declared ingest formats: the link carries 8 / 8 / 4 KiB per frame instead of 16
             del hf
@@ -622,12 +817,8 @@ def run_ours(args, world, rank, local):
     roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel<256,6,...> (Linear 4096->2048, tcgen05 cta_group::2 kind::f16)",
                 "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops_sustained"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one `ncu --set full` capture
-                # (profiles/r01_ncu_session2.txt): 3.462 GB + 1.062 GB per launch vs 3.238 GB algorithmic
-                "traffic": 4.523928e9 if (B, Tc, args.precision) == (4096, 64, "fp16") and min(Tc, args.subchunk) == 64 else None,
-                "traffic_note": "ncu capture at chunk 64; with internal_subchunk 32 a launch moves half of it",
+                **ncu_record(B, Tc, args),
                 "algorithmic_bytes_per_launch": (8192 + 4096) * rows_per_launch + 4096 * 2048 * 2,
-                "tensor_pipe_active_pct_ncu": 99.6,
                 "peak_source": f"{pk['source']} bf16 sustained (kernel timed inside a long step)",
                 "per_launch_ms": g1_ms, "flops_per_launch": FLOP_GEMM1 * rows_per_launch,
                 "phase_share": phase_share, "phase_tflops": phase_tflops,
@@ -645,10 +836,15 @@ def run_ours(args, world, rank, local):
         torch.cuda.empty_cache()
         rank4 = rank4_leg(dev)
 
+    library = None
+    if not args.no_library and world == 1:
+        torch.cuda.empty_cache()
+        library = library_baseline_leg(dev, B, Tc, local)
+
     cpu = None
     if not args.no_cpu and world == 1:
         v, sample, cores = cpu_baseline_run(B, Tc)
-        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample, "whole_video": cpu_whole_video_run()}
 
     line = {"metric": "frames/sec MiniROAD online inference", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
@@ -656,9 +852,11 @@ def run_ours(args, world, rank, local):
             "config": {"workload": f"Assembly101-O-shaped MiniROAD eval, {B} concurrent streams/GPU x {Tc}-frame chunks with carried GRU state (K=86), + window-vote/RLE collapse",
                        "streams_per_gpu": B, "chunk_frames": Tc, "internal_subchunk": min(Tc, args.subchunk), "frames_per_step_per_gpu": Mc, "precision": args.precision,
                        "l2_policy": "inputs larger than L2 (4 GiB of features per step vs 126 MB L2)",
+                       "gather": (f"collapsed step sequences of all ranks gathered on rank 0 inside the timed region ({gathered['sequences']} sequences, "
+                                  f"{gathered['bytes']} bytes over NCCL)") if world > 1 else "single GPU: nothing to gather",
                        "weights": "seed-20 default init (no checkpoint ships with the reference)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "sustained": sustained,
-            "single_stream": lat, "train_step": train, "feature_formats": variants, "rank4": rank4}
+            "single_stream": lat, "train_step": train, "feature_formats": variants, "rank4": rank4, "library_baseline": library}
     emit(line)
     if world > 1:
         dist.barrier()

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define PREGO_ABI_VERSION 3
+#define PREGO_ABI_VERSION 4
 
 #define PREGO_OK 0
 #define PREGO_ERR_INVALID 1     /* bad argument / unsupported shape */
@@ -174,6 +174,10 @@ typedef struct prego_train_args {
                                 reference's own GPU practice (cuDNN RNN allows TF32; main.py --amp trains in fp16).
                                 The recurrence, LayerNorm, loss and the classifier stay exact fp32 either way. */
     int32_t reserved;
+    void* gru_grads_event;   /* prego_train_backward only, may be NULL: a cudaEvent_t recorded on `stream` as soon as the gradients of
+                                the gru.* and f_classification.* tensors are final, i.e. before the layer1 backward (LayerNorm backward,
+                                dW1 = the largest GEMM of the step) is enqueued.  A data-parallel caller starts the all-reduce of that
+                                bucket on this event so it overlaps the rest of the backward. */
 } prego_train_args_t;
 
 size_t prego_train_workspace_bytes(const prego_model_t* model, int64_t B, int64_t T);

@@ -10,8 +10,8 @@ from .aggregate import aggregate, aggregate_labels  # noqa: F401
 from .evaluate import Evaluate, ANT_Evaluate  # noqa: F401
 from .metrics import perframe_average_precision  # noqa: F401
 from .pipeline import predict_labels, recognize_and_aggregate  # noqa: F401
-from .training import (OadLoss, build_criterion, train_one_step, allreduce_gradients, FusedAdamW, TRAINER, train_one_epoch,  # noqa: F401
-                       build_trainer, build_optimizer, WindowDataset)
+from .training import (OadLoss, build_criterion, train_one_step, allreduce_gradients, enable_overlapped_allreduce, FusedAdamW,  # noqa: F401
+                       TRAINER, train_one_epoch, build_trainer, build_optimizer, WindowDataset, gradient_buckets)
 from . import ingest  # noqa: F401
 
 __version__ = "0.1.0"

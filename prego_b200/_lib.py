@@ -56,7 +56,7 @@ class TrainArgs(C.Structure):
     _fields_ = [("rgb", C.c_void_p), ("flow", C.c_void_p), ("B", C.c_int64), ("T", C.c_int64),
                 ("logits", C.c_void_p), ("dlogits", C.c_void_p), ("grads", C.POINTER(Grads)),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("dropout_p", C.c_float),
-                ("seed", C.c_uint64), ("precision", C.c_int32), ("reserved", C.c_int32)]
+                ("seed", C.c_uint64), ("precision", C.c_int32), ("reserved", C.c_int32), ("gru_grads_event", C.c_void_p)]
 
 
 ADAMW_MAX_TENSORS = 16

@@ -82,17 +82,80 @@ class MiniROADTrainFn(torch.autograd.Function):
         module = ctx.module
         device = dlogits.device
         dlogits = dlogits.contiguous().float()
+        group = getattr(module, "_dp_group", None)
+        overlapped = group is not None
         with torch.cuda.device(device):
-            grads = [torch.empty(s, dtype=torch.float32, device=device) for s in ctx.shapes]
+            # ten gradients as views of ONE flat buffer laid out in the order the backward finishes them
+            # (gradient_buckets): a bucket is a contiguous slice, so its all-reduce needs no gather / scatter passes
+            buckets, offsets, total = gradient_buckets(ctx.shapes)
+            flat = torch.empty(total, dtype=torch.float32, device=device)
+            grads = [flat[o:o + _numel(s)].view(s) for o, s in zip(offsets, ctx.shapes)]
             g = _lib.Grads(*[t.data_ptr() for t in grads])
+            main = torch.cuda.current_stream(device)
+            ev = torch.cuda.Event() if overlapped else None
+            if ev is not None:
+                ev.record(main)  # materialises the cudaEvent_t; re-recorded by the library at the bucket boundary
             args = _lib.TrainArgs(ctx.rgb.data_ptr() if ctx.rgb is not None else None,
                                   ctx.flow.data_ptr() if ctx.flow is not None else None, ctx.B, ctx.T, None,
                                   dlogits.data_ptr(), C.pointer(g), ctx.ws_ptr, ctx.need, float(module.layer1[3].p), ctx.seed,
-                                  ctx.prec)
-            stream = torch.cuda.current_stream(device).cuda_stream
-            _lib.check(lib.prego_train_backward(module._handle, C.byref(args), stream), "prego_train_backward")
-            ctx.ws.record_stream(torch.cuda.current_stream(device))  # freed by autograd right after this returns
+                                  ctx.prec, 0, ev.cuda_event if ev is not None else None)
+            _lib.check(lib.prego_train_backward(module._handle, C.byref(args), main.cuda_stream), "prego_train_backward")
+            ctx.ws.record_stream(main)  # freed by autograd right after this returns
+            if overlapped:
+                import torch.distributed as dist
+                world = dist.get_world_size(group)
+                (a0, a1), (b0, b1) = buckets
+                comm = _comm_stream(device)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ev)  # gru.* / f_classification.* gradients final: reduce them under the layer1 backward
+                    w_a = dist.all_reduce(flat[a0:a1], op=dist.ReduceOp.SUM, group=group, async_op=True)
+                flat.record_stream(comm)
+                w_b = dist.all_reduce(flat[b0:b1], op=dist.ReduceOp.SUM, group=group, async_op=True)  # after the whole backward
+                w_a.wait()
+                w_b.wait()
+                flat.mul_(1.0 / world)
+                module._grads_reduced = True
         return (None, None, None, None, *grads)
+
+
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
+
+
+# _param_tensors() order: layer1.0.{weight, bias}, layer1.1.{weight, bias}, gru.{weight_ih, weight_hh, bias_ih, bias_hh},
+# f_classification.0.{weight, bias}.  The backward (csrc/train_api.inc) finishes the classifier and GRU gradients first and
+# the layer1 gradients (LayerNorm backward, dW1: the largest GEMM) last.
+_BUCKET_A = (4, 5, 6, 7, 8, 9)   # final when prego_train_args_t.gru_grads_event fires
+_BUCKET_B = (0, 1, 2, 3)          # final when prego_train_backward's last kernel is done
+
+
+def gradient_buckets(shapes):
+    """Layout of the flat gradient buffer: ((a0, a1), (b0, b1)) element ranges of the two all-reduce buckets, the offset of
+    each of the ten tensors (in ``_param_tensors()`` order), and the total length.  Offsets are 16-byte aligned so the
+    library's vectorised stores and NCCL see aligned slices."""
+    offsets = [0] * len(shapes)
+    pos = 0
+    bounds = []
+    for bucket in (_BUCKET_A, _BUCKET_B):
+        start = pos
+        for i in bucket:
+            offsets[i] = pos
+            pos += (_numel(shapes[i]) + 3) // 4 * 4
+        bounds.append((start, pos))
+    return tuple(bounds), offsets, pos
+
+
+_COMM_STREAMS = {}
+
+
+def _comm_stream(device):
+    key = torch.device(device).index
+    if key not in _COMM_STREAMS:
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COMM_STREAMS[key]
 
 
 def train_forward(module, rgb, flow):
@@ -104,12 +167,31 @@ def train_forward(module, rgb, flow):
     return MiniROADTrainFn.apply(module, rgb, flow, seed, *module._param_tensors())
 
 
-def allreduce_gradients(module, group=None):
-    """Data-parallel gradient averaging: ONE all-reduce of the flat gradient buffer (17.9 M floats for
-    K = 86) over NCCL / NVLink, then scatter back.  No-op for a single process."""
+def enable_overlapped_allreduce(module, group=None):
+    """Data-parallel training on the CUDA path: reduce the gradients INSIDE the backward, in two buckets over the flat
+    gradient buffer -- the gru.* / f_classification.* bucket (9.5 M floats for K = 86) starts on a side stream as soon as
+    the library signals it final (``gru_grads_event``) and overlaps the layer1 backward (LayerNorm backward, dW1), the
+    layer1 bucket (8.4 M floats) follows the last kernel.  ``allreduce_gradients`` becomes a no-op for
+    gradients reduced this way.  No-op itself for a single process."""
     import torch.distributed as dist
 
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        module._dp_group = None
+        return False
+    module._dp_group = group if group is not None else dist.group.WORLD
+    return True
+
+
+def allreduce_gradients(module, group=None):
+    """Data-parallel gradient averaging after the backward: ONE all-reduce of the flat gradient buffer (17.9 M floats
+    for K = 86), then scatter back.  Generic path (any module, gloo in the CPU tests); skipped when the CUDA backward
+    already reduced its gradients (``enable_overlapped_allreduce``).  No-op for a single process."""
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    if getattr(module, "_grads_reduced", False):
+        module._grads_reduced = False
         return
     grads = [p.grad for p in module.parameters() if p.grad is not None]
     flat = torch.cat([g.reshape(-1) for g in grads])
@@ -241,8 +323,11 @@ class WindowDataset(torch.utils.data.Dataset):
 
 
 def train_one_step(model, criterion, optimizer, rgb, flow, target, group=None):
-    """One iteration of trainer/train.py:8-24 (+ the gradient all-reduce when run data-parallel)."""
+    """One iteration of trainer/train.py:8-24 (+ the gradient all-reduce when run data-parallel: bucketed and overlapped
+    with the backward on the CUDA path, see ``enable_overlapped_allreduce``)."""
     model.train()
+    if hasattr(model, "_param_tensors") and not hasattr(model, "_dp_group"):
+        enable_overlapped_allreduce(model, group)
     out = model(rgb, flow)
     loss = criterion(out, target)
     optimizer.zero_grad(set_to_none=True)

@@ -31,7 +31,7 @@ def test_header_symbols_all_exported(lib):
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in include/prego_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes prototypes out of sync with the header"
-    assert lib.prego_abi_version() == 3
+    assert lib.prego_abi_version() == 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

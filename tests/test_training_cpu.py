@@ -186,3 +186,22 @@ def test_trainer_registry_and_optimizer_builder():
     lin.bias.grad = torch.zeros_like(lin.bias)
     with pytest.raises(RuntimeError):
         opt.step()   # CPU parameters: no fallback
+
+
+def test_gradient_bucket_layout():
+    """The flat gradient buffer of the overlapped all-reduce: bucket A (gru.*, f_classification.*: final first) and bucket B
+    (layer1.*) are disjoint contiguous ranges that tile the buffer, every tensor sits 16-byte aligned inside its bucket."""
+    from prego_b200 import gradient_buckets
+    m = synthetic.seeded_model(dict(synthetic.ASSEMBLY101_O), seed=20)
+    shapes = [tuple(t.shape) for t in m._param_tensors()]
+    (a0, a1), (b0, b1), = gradient_buckets(shapes)[0]
+    _, offsets, total = gradient_buckets(shapes)
+    assert a0 == 0 and a1 == b0 and b1 == total
+    numel = [int(np.prod(s)) for s in shapes]
+    assert total >= sum(numel) and total - sum(numel) < 4 * len(shapes)
+    spans = sorted((o, o + n) for o, n in zip(offsets, numel))
+    assert all(o % 4 == 0 for o, _ in spans) and all(e <= o2 for (_, e), (o2, _) in zip(spans, spans[1:]))
+    for i, (o, n) in enumerate(zip(offsets, numel)):
+        lo, hi = (a0, a1) if i >= 4 else (b0, b1)   # _param_tensors(): layer1 first, then gru, then the classifier
+        assert lo <= o and o + n <= hi
+    assert sum(numel[4:]) == 3072 * 2048 + 3072 * 1024 + 2 * 3072 + 86 * 1024 + 86
