@@ -294,7 +294,7 @@ def training_leg(dev, world):
             T = 128
             rgb, flow = synthetic.device_features(B, T, dev, seed=7, zero_flow=True)
             target = torch.nn.functional.one_hot(torch.randint(0, 86, (B, T), device=dev), 86).float()
-            for _ in range(2):
+            for _ in range(4 if world > 1 else 2):  # NCCL sets up its channels lazily over the first collectives of a size class
                 train_one_step(model, crit, opt, rgb, flow, target)
             torch.cuda.synchronize()
             n = 5 if B == 16 else 3
@@ -329,7 +329,9 @@ def training_leg(dev, world):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         nbytes = sum(p.numel() for p in model.parameters()) * 4
         out["grad_allreduce"] = {"ms": float(ms), "bytes": nbytes, "bus_gbs": 2 * (world - 1) / world * nbytes / (float(ms) * 1e-3) / 1e9,
-                                 "note": "flat-buffer gather + NCCL all-reduce (sum) + scatter back, per step; bus GB/s = 2 (N-1)/N x bytes / time"}
+                                 "note": "the exchange on its own, generic path: flat-buffer gather + NCCL all-reduce (sum) + scatter back; bus GB/s = 2 (N-1)/N x bytes / time. "
+                                         "Inside the timed training steps above the gradients are reduced IN the backward instead: two buckets of one flat buffer, the "
+                                         "gru / classifier bucket on a side stream under the layer1 backward (prego_b200.training.enable_overlapped_allreduce)"}
     out["note"] = ("fwd + BPTT + fused AdamW (one launch), dropout 0.2, flow = 0; recurrence (forward and BPTT) on the persistent exact-fp32 kernels "
                    "for B <= 64; plain keys: every GEMM exact fp32 on CUDA cores (parity mode); *_tf32: large projections and their "
                    "gradients on tcgen05 kind::tf32; grads all-reduced (NCCL) when n_gpus > 1")
