@@ -284,6 +284,17 @@ int prego_host_stager_run(prego_host_stager_t* stager, const float* src, void* d
  * PREGO_PREC_BF16) on the tcgen05 path; N % tile_n == 0, tile_n in {96, 128, 192, 256}, K % 64 == 0. */
 int prego_gemm16_nt(const void* A, const void* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
                     int32_t tile_n, int32_t precision, void* stream);
+/* Fused LayerNorm path (rnn.py:39-44 without a separate LayerNorm pass), building blocks:
+ * prego_gemm16_stats_nt: Y[M,N] fp16 = A W^T + bias (16-bit operands, CTA pairs) and, from the same epilogue, the LayerNorm
+ *   statistics of the rounded rows: stats [N/256][M] (sum, sum of squares) partials and rowstat [M] = (rstd, -mean * rstd)
+ *   (biased variance, eps inside the root).  N % 256 == 0, K % 64 == 0.
+ * prego_gemm16_ln_nt: C[M,N] fp32 = relu((Y * a_r + b_r) * gamma + beta) W^T + bias with Y fp16 [M,K] normalised on its way
+ *   into the tensor core (transform warps rewrite the TMA-staged A tile in place); rowstat = (a_r, b_r) per row.
+ *   rowstat == NULL: identity transform (Y in the operand format passes through the extra pipeline hop unchanged). */
+int prego_gemm16_stats_nt(const void* A, const void* W, const float* bias, void* Y, float* stats, float* rowstat, int64_t M,
+                          int64_t N, int64_t K, int32_t precision, float eps, void* stream);
+int prego_gemm16_ln_nt(const void* Y, const float* rowstat, const float* gamma, const float* beta, const void* W,
+                       const float* bias, float* C, int64_t M, int64_t N, int64_t K, int32_t precision, void* stream);
 /* Same contract with fp32 storage and TF32 tensor-core operands (CTA pairs); N % 256 == 0, K % 32 == 0;
  * accumulate != 0 adds into C.  Used by the PREGO_PREC_TF32 training step. */
 int prego_gemm_tf32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,

@@ -111,6 +111,10 @@ SIGNATURES = {
                             C.c_void_p, C.c_void_p, C.c_void_p]),
     "prego_gemm16_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                   C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "prego_gemm16_stats_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                        C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
+    "prego_gemm16_ln_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
     "prego_gemm_tf32_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                      C.c_int32, C.c_void_p]),
     "prego_gemm_f32_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,

@@ -17,6 +17,7 @@
 #include "../../include/prego_b200.h"
 #include "aggregate.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_xf.cuh"
 #include "gru_latency.cuh"
 #include "gru_step.cuh"
 #include "metrics.cuh"
@@ -233,8 +234,11 @@ struct Plan {
     int64_t sync;          // uint32 [Tc, ceil(B/256)] dependency counters  (batched 16-bit recurrence)
     int64_t online;        // fp32 scratch of the per-frame online path: 8 x (E + 3H + H)
     int64_t h32t;          // fp32 state in the recurrence's tiled order, rows padded to 128 (batched 16-bit recurrence)
+    int64_t lnstat;        // float2 [E / 256][Mc] partial (sum, sum of squares) + float2 [Mc] (rstd, -mean rstd): fused-LayerNorm path
     int64_t total;
 };
+
+bool use_ln_fused();
 
 Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec, bool double_xb = true) {
     Plan p{};
@@ -260,6 +264,7 @@ Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec, bool doub
     p.online = h16 ? take(kOnlineMaxRows * (E + 3 * H + H) * 4) : 0;
     p.sync = (h16 && batched) ? take(Tc * ((B + 255) / 256) * 4) : 0;
     p.h32t = (h16 && batched) ? take((B + 127) / 128 * 128 * H * 4) : 0;
+    p.lnstat = (h16 && use_ln_fused()) ? take(Mc * (E / 256 + 1) * 8) : 0;
     p.total = off;
     return p;
 }
@@ -303,6 +308,23 @@ int launch_gemm_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N
     return PREGO_OK;
 }
 
+
+// CTA-pair GEMM with the in-place A transform (gemm_xf.cuh); tmB encoded with box rows TILE_N / 2.
+template <int TILE_N, int STAGES, int FMT, class Epi, bool IDENTITY>
+int launch_gemm_xf(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const Epi& epi, const LnXf& xf, int sm_count,
+                   cudaStream_t stream, const char* name) {
+    using Cfg = GemmXfCfg<TILE_N, STAGES>;
+    auto kfn = gemm_tc2_xf_kernel<TILE_N, STAGES, FMT, Epi, IDENTITY>;
+    const int smem = Cfg::smem_bytes(K);
+    if (smem > 227 * 1024) return fail(PREGO_ERR_INVALID, "%s: K = %d needs %d bytes of shared memory", name, K, smem);
+    RC_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kfn), smem));
+    const int tiles = (N / TILE_N) * ((M + 2 * kTileM - 1) / (2 * kTileM));
+    const int grid = 2 * tiles < sm_count ? 2 * tiles : (sm_count & ~1);
+    kfn<<<grid, kXfThreads, smem, stream>>>(tmA, tmB, M, N, K, epi, xf);
+    LAUNCH_CHECK(name);
+    return PREGO_OK;
+}
+
 // C[M, N] (fp32, ldc) (+)= A[M, K] (lda) * W[N, K]^T (ldw) + bias, TF32 operands on CTA pairs.  N % 256 == 0, K % 32 == 0.
 int gemm_tf32_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M,
                  int N, int K, int accumulate, int sm_count, cudaStream_t s) {
@@ -334,6 +356,17 @@ int overlap_mode() {
     return v;
 }
 bool use_overlap() { return overlap_mode() != 0; }
+
+// PREGO_LN_FUSED=1: LayerNorm + ReLU folded into the input-gate GEMM's A operand (gemm_xf.cuh) instead of the separate
+// layernorm_relu_16 pass.  OFF by default: measured slower (profiles/r02_ln_fusion.txt); kept selectable so the comparison can be re-run.
+bool use_ln_fused() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PREGO_LN_FUSED");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 bool use_2cta() {
     static int v = -1;
@@ -521,6 +554,9 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
     OpT* hseq = reinterpret_cast<OpT*>(ws + p.hseq);
     OpT* hrelu = reinterpret_cast<OpT*>(ws + p.hrelu);
     CUtensorMap tmA, tmB;
+    const bool fused_ln = use_ln_fused() && use_2cta() && p.lnstat != 0 && E == 2048;
+    float2* ln_part = reinterpret_cast<float2*>(ws + p.lnstat);
+    float2* ln_row = ln_part + static_cast<int64_t>(E / 256) * Mc;
 
     // 1. stage features: concat + operand rounding (replaces torch.cat, rnn.py:53)
     if (direct) {
@@ -538,12 +574,17 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
         else RC_TRY(make_tmap_feat(&tmA, dt, a->flow, d.d_flow, T, B));
         if (both) RC_TRY(make_tmap_feat(&tmA2, dt, a->flow, d.d_flow, T, B));
         RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 128));
+        if (fused_ln)
+            RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, E, Dine, (int)t0, EpiStoreStats<256>{reinterpret_cast<__half*>(ye), m->b1, E, ln_part, Mi}, m->sm_count, s,
+                                                 "gemm1 (2cta, features in place, LN statistics)", both ? &tmA2 : &tmA, both ? d.d_rgb : Dine, (int)B)));
+        else
         RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, E, Dine, (int)t0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s,
                                              "gemm1 (2cta, features in place)", both ? &tmA2 : &tmA, both ? d.d_rgb : Dine, (int)B)));
     } else if (use_2cta()) {
         RC_TRY(make_tmap_a(&tmA, dt, xb, Dine, Mc));
         RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 128));
-        RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, E, Dine, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1 (2cta)")));
+        if (fused_ln) RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, E, Dine, 0, EpiStoreStats<256>{reinterpret_cast<__half*>(ye), m->b1, E, ln_part, Mi}, m->sm_count, s, "gemm1 (2cta, LN statistics)")));
+        else RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, E, Dine, 0, EpiStore<256, 0>{ye, m->b1, E, 0, 0}, m->sm_count, s, "gemm1 (2cta)")));
     } else {
         RC_TRY(make_tmap_a(&tmA, dt, xb, Dine, Mc));
         RC_TRY(make_tmap_w(&tmB, dt, m->w1_16[FMT], Din, E, 256));
@@ -565,14 +606,27 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
         }
     }
     prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
-    // 3. e = relu(LN(y))  (in place, operand format)
-    layernorm_relu_16<2048, FMT><<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(
-        reinterpret_cast<const __half*>(ye), reinterpret_cast<OpT*>(ye), m->ln_g, m->ln_b, Mc, 1e-5f);
-    LAUNCH_CHECK("layernorm_relu_16");
+    // 3. e = relu(LN(y))  (in place, operand format) -- or, fused: only the row statistics are finalised here and y is
+    //    normalised inside the input-gate GEMM's A operand
+    if (fused_ln) {
+        ln_finalize_kernel<<<(unsigned)((Mc + 255) / 256), 256, 0, s>>>(ln_part, ln_row, Mi, E / 256, E, 1e-5f);
+        LAUNCH_CHECK("ln_finalize_kernel");
+    } else {
+        layernorm_relu_16<2048, FMT><<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(
+            reinterpret_cast<const __half*>(ye), reinterpret_cast<OpT*>(ye), m->ln_g, m->ln_b, Mc, 1e-5f);
+        LAUNCH_CHECK("layernorm_relu_16");
+    }
     prof_mark(m, s, PREGO_PHASE_LAYERNORM, 1);
     // 4. gi = e W_ih'^T + b_ih'  (gate-interleaved columns, time-major rows)
-    RC_TRY(make_tmap_a(&tmA, dt, ye, E, Mc));
-    if (use_2cta()) {
+    RC_TRY(make_tmap_a(&tmA, fused_ln ? kF16 : dt, ye, E, Mc));
+    if (fused_ln) {
+        RC_TRY(make_tmap_w(&tmB, dt, m->wih_16p[FMT], E, 3 * H, 128));
+        const LnXf xf{ln_row, m->ln_g, m->ln_b};
+        if (batched)
+            RC_TRY((launch_gemm_xf<256, 6, FMT, EpiStore<256, 0>, false>(tmA, tmB, Mi, 3 * H, E, EpiStore<256, 0>{gi, m->bgi_p, 3 * H, 0, 0}, xf, m->sm_count, s, "gemm2 (LayerNorm fused)")));
+        else
+            RC_TRY((launch_gemm_xf<256, 6, FMT, EpiStore<256, -1>, false>(tmA, tmB, Mi, 3 * H, E, EpiStore<256, -1>{gi, m->bih_p, 3 * H, 0, 0}, xf, m->sm_count, s, "gemm2 (LayerNorm fused)")));
+    } else if (use_2cta()) {
         RC_TRY(make_tmap_w(&tmB, dt, m->wih_16p[FMT], E, 3 * H, 128));
         if (batched)
             RC_TRY((launch_gemm_tc2<256, 6, FMT>(tmA, tmB, Mi, 3 * H, E, 0, EpiStore<256, 0>{gi, m->bgi_p, 3 * H, 0, 0}, m->sm_count, s, "gemm2 (2cta)")));
@@ -1204,6 +1258,57 @@ int prego_gemm16_nt(const void* A, const void* W, const float* bias, float* C, i
     if (precision == PREGO_PREC_F16) return gemm16_test<0>(A, W, bias, C, M, N, K, tile_n, sms, s);
     if (precision == PREGO_PREC_BF16) return gemm16_test<1>(A, W, bias, C, M, N, K, tile_n, sms, s);
     return fail(PREGO_ERR_INVALID, "precision must be PREGO_PREC_F16 or PREGO_PREC_BF16");
+}
+
+// Test / diagnostic entry points of the fused LayerNorm path (gemm_xf.cuh), N % 256 == 0, K % 64 == 0:
+//  prego_gemm16_ln_nt:    C[M, N] fp32 = relu((Y * a_r + b_r) * gamma + beta) W^T + bias, Y fp16 [M, K], rowstat = (a_r, b_r) per row;
+//                         rowstat == NULL runs the IDENTITY transform (A passes through the extra pipeline hop unchanged).
+//  prego_gemm16_stats_nt: Y[M, N] fp16 = A W^T + bias plus the LayerNorm row statistics of the rounded Y (partials + finalised).
+int prego_gemm16_ln_nt(const void* Y, const float* rowstat, const float* gamma, const float* beta, const void* W, const float* bias,
+                       float* C, int64_t M, int64_t N, int64_t K, int32_t precision, void* stream) {
+    if (Y == nullptr || W == nullptr || bias == nullptr || C == nullptr) return fail(PREGO_ERR_INVALID, "NULL pointer argument");
+    if (rowstat != nullptr && (gamma == nullptr || beta == nullptr)) return fail(PREGO_ERR_INVALID, "gamma / beta is NULL");
+    if (M <= 0 || N <= 0 || K <= 0 || K % kTileK != 0 || N % 256 != 0) return fail(PREGO_ERR_INVALID, "need K %% 64 == 0 and N %% 256 == 0");
+    if (precision != PREGO_PREC_F16 && precision != PREGO_PREC_BF16) return fail(PREGO_ERR_INVALID, "precision must be PREGO_PREC_F16 or PREGO_PREC_BF16");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool f16 = precision == PREGO_PREC_F16;
+    CUtensorMap tmA, tmB;
+    // the raw A tile is fp16 for the LayerNorm transform (y is stored as fp16); the identity transform moves 16-bit words as they are
+    RC_TRY(make_tmap_a(&tmA, (rowstat != nullptr || f16) ? kF16 : kBF16, Y, K, M));
+    RC_TRY(make_tmap_w(&tmB, f16 ? kF16 : kBF16, W, K, N, 128));
+    LnXf xf{reinterpret_cast<const float2*>(rowstat), gamma, beta};
+    if (const char* e = getenv("PREGO_XF_DBG")) xf.dbg = atoi(e);
+    const EpiStore<256, -1> epi{C, bias, N, 0, 0};
+    if (rowstat == nullptr) {
+        if (f16) return launch_gemm_xf<256, 6, 0, EpiStore<256, -1>, true>(tmA, tmB, (int)M, (int)N, (int)K, epi, xf, sms, s, "gemm_xf identity");
+        return launch_gemm_xf<256, 6, 1, EpiStore<256, -1>, true>(tmA, tmB, (int)M, (int)N, (int)K, epi, xf, sms, s, "gemm_xf identity");
+    }
+    if (f16) return launch_gemm_xf<256, 6, 0, EpiStore<256, -1>, false>(tmA, tmB, (int)M, (int)N, (int)K, epi, xf, sms, s, "gemm_xf LayerNorm");
+    return launch_gemm_xf<256, 6, 1, EpiStore<256, -1>, false>(tmA, tmB, (int)M, (int)N, (int)K, epi, xf, sms, s, "gemm_xf LayerNorm");
+}
+
+int prego_gemm16_stats_nt(const void* A, const void* W, const float* bias, void* Y, float* stats, float* rowstat, int64_t M, int64_t N,
+                          int64_t K, int32_t precision, float eps, void* stream) {
+    if (A == nullptr || W == nullptr || bias == nullptr || Y == nullptr || stats == nullptr || rowstat == nullptr) return fail(PREGO_ERR_INVALID, "NULL pointer argument");
+    if (M <= 0 || N <= 0 || K <= 0 || K % kTileK != 0 || N % 256 != 0) return fail(PREGO_ERR_INVALID, "need K %% 64 == 0 and N %% 256 == 0");
+    if (precision != PREGO_PREC_F16 && precision != PREGO_PREC_BF16) return fail(PREGO_ERR_INVALID, "precision must be PREGO_PREC_F16 or PREGO_PREC_BF16");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const DType dt = precision == PREGO_PREC_F16 ? kF16 : kBF16;
+    CUtensorMap tmA, tmB;
+    RC_TRY(make_tmap_a(&tmA, dt, A, K, M));
+    RC_TRY(make_tmap_w(&tmB, dt, W, K, N, 128));
+    const EpiStoreStats<256> epi{static_cast<__half*>(Y), bias, N, reinterpret_cast<float2*>(stats), (int)M};
+    if (precision == PREGO_PREC_F16) RC_TRY((launch_gemm_tc2<256, 6, 0>(tmA, tmB, (int)M, (int)N, (int)K, 0, epi, sms, s, "gemm + LN statistics")));
+    else RC_TRY((launch_gemm_tc2<256, 6, 1>(tmA, tmB, (int)M, (int)N, (int)K, 0, epi, sms, s, "gemm + LN statistics")));
+    ln_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float2*>(stats), reinterpret_cast<float2*>(rowstat), (int)M, (int)(N / 256), (int)N, eps);
+    LAUNCH_CHECK("ln_finalize_kernel");
+    return PREGO_OK;
 }
 
 int prego_gemm_tf32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,

@@ -33,6 +33,16 @@ constexpr int kTileM = 128;
 constexpr int kTileK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kGemmThreads = 192;
 
+// 16-byte shared-memory accesses by shared-window address (epilogues / transform warps working on swizzled TMA boxes)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 template <int TILE_N>
 struct GemmCfg {
     static constexpr int kABytes = kTileM * kTileK * 2;

@@ -64,14 +64,6 @@ constexpr int kGruSmemBytes = kGruStages * kGruStageBytes + kGruGiBytes + kGruOu
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
 
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 
 // Dependency wait: spin (acquire) until done[idx] >= target, then order later async-proxy (TMA) reads after it.
 // Bounded: a missing peer sets the error flag instead of hanging the GPU.

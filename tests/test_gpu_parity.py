@@ -684,3 +684,72 @@ def test_stager_recognises_the_zero_flow_dummy(dev):
     want = model.infer(rgb, flow, h_state=h_a, precision="fp16")
     assert torch.equal(got["labels"], want["labels"]) and torch.equal(h_a, h_b)
     st.close()
+
+
+# ------------------------------------------------------------------ fused LayerNorm building blocks (gemm_xf.cuh)
+@pytest.mark.parametrize("M,N,K", [(300, 512, 256), (1000, 3072, 2048)])
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_layernorm_fused_gemm_blocks(dev, lib, M, N, K, prec):
+    """rnn.py:39-44 without a separate LayerNorm pass: (1) the projection GEMM's epilogue also emits the LayerNorm row
+    statistics of the rounded y, (2) the input-gate GEMM normalises y inside its A operand (transform warps rewrite the
+    TMA-staged tile in place).  Both against torch on the same numbers."""
+    from prego_b200 import _lib
+    P = _lib.PRECISIONS[prec]
+    dt = torch.float16 if prec == "fp16" else torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(M + N)
+    A = (torch.randn(M, 4096, generator=g, device=dev).abs() * 0.5).to(dt)
+    W1 = (torch.randn(K, 4096, generator=g, device=dev) * 0.02).to(dt)
+    b1 = torch.randn(K, generator=g, device=dev) * 0.1
+    Y = torch.empty(M, K, dtype=torch.float16, device=dev)
+    stats = torch.zeros(K // 256, M, 2, device=dev)
+    rowstat = torch.zeros(M, 2, device=dev)
+    _lib.check(lib.prego_gemm16_stats_nt(A.data_ptr(), W1.data_ptr(), b1.data_ptr(), Y.data_ptr(), stats.data_ptr(), rowstat.data_ptr(),
+                                         M, K, 4096, P, 1e-5, _stream()), "prego_gemm16_stats_nt")
+    torch.cuda.synchronize()
+    yref = A.float() @ W1.float().T + b1
+    assert (Y.float() - yref).abs().max().item() <= 2e-3 * yref.abs().max().item()
+    y32 = Y.float()
+    mu, var = y32.mean(-1), y32.var(-1, unbiased=False)
+    rstd = 1 / torch.sqrt(var + 1e-5)
+    assert ((rowstat[:, 0] - rstd).abs() / rstd).max().item() <= 1e-5 and (rowstat[:, 1] + mu * rstd).abs().max().item() <= 1e-5
+    gamma = 1 + 0.1 * torch.randn(K, generator=g, device=dev)
+    beta = 0.1 * torch.randn(K, generator=g, device=dev)
+    W2 = (torch.randn(N, K, generator=g, device=dev) * 0.03).to(dt)
+    b2 = torch.randn(N, generator=g, device=dev) * 0.1
+    C_ = torch.full((M, N), float("nan"), device=dev)
+    _lib.check(lib.prego_gemm16_ln_nt(Y.data_ptr(), rowstat.data_ptr(), gamma.data_ptr(), beta.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                                      C_.data_ptr(), M, N, K, P, _stream()), "prego_gemm16_ln_nt")
+    torch.cuda.synchronize()
+    e = torch.relu(torch.nn.functional.layer_norm(y32, (K,), gamma, beta, 1e-5)).to(dt).float()
+    ref = e @ W2.float().T + b2
+    assert torch.isfinite(C_).all()
+    assert (C_ - ref).abs().max().item() <= (2e-3 if prec == "fp16" else 1e-2) * ref.abs().max().item()
+
+
+def test_layernorm_fused_pipeline_matches_reference():
+    """The whole path with PREGO_LN_FUSED=1 (the knob is read once per process, hence the subprocess): golden cases
+    within the fp16 tolerance.  The fused variant is NOT the default (measured slower, profiles/r02_ln_fusion.txt)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os, json
+sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+import numpy as np, torch
+from conftest import case_inputs, load_model_case, seeded_weights_checked, GOLD
+meta = json.load(open(os.path.join(GOLD, "meta.json")))
+dev = torch.device("cuda:0")
+for name in ("asm_b40_t24", "asm_b2_t160", "epic_b1_t300"):
+    gold = load_model_case(name)
+    cfg, rgb, flow = case_inputs(meta, name, dev)
+    model = seeded_weights_checked(meta, name, dev)
+    out = model.infer(rgb, flow, want_logits=True, precision="fp16")
+    torch.cuda.synchronize()
+    d = np.abs(out["logits"].cpu().numpy() - gold["logits"]).max() / np.abs(gold["logits"]).max()
+    assert d <= 2e-3, (name, d)
+    assert model.device_error() == 0
+print("FUSED_OK")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", f"ROOT = {root!r}\n" + code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, PREGO_LN_FUSED="1"))
+    assert r.returncode == 0 and "FUSED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
