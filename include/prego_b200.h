@@ -31,6 +31,10 @@ extern "C" {
 #define PREGO_PREC_BF16 0       /* tcgen05 kind::f16, bf16 operands, fp32 accumulate (throughput path) */
 #define PREGO_PREC_FP32 1       /* exact fp32 FFMA path (1e-4 parity mode) */
 #define PREGO_PREC_TF32 3       /* training only: fp32 storage, tcgen05 kind::tf32 operands, fp32 accumulate */
+#define PREGO_PREC_F16X3 4      /* fp32-class accuracy ON the tensor cores: every fp32 operand travels as fp16 hi + fp16 lo (22 bits),
+                                   x.w = x_hi w_hi + x_lo w_hi + x_hi w_lo in one tcgen05 kind::f16 GEMM over 3 K, fp32 accumulate;
+                                   LayerNorm, gates, state, softmax in fp32.  Same 1e-4 logit bound as PREGO_PREC_FP32 at a
+                                   fraction of its cost; fp32 features only */
 #define PREGO_PREC_F16 2        /* tcgen05 kind::f16, fp16 operands (10-bit mantissa = TF32 accuracy at the bf16 rate),
                                    fp32 accumulate; inputs saturate at +-65504 (default throughput path) */
 

@@ -16,7 +16,8 @@ PREC_BF16 = 0
 PREC_FP32 = 1
 PREC_F16 = 2
 PREC_TF32 = 3  # training only
-PRECISIONS = {"bf16": PREC_BF16, "fp32": PREC_FP32, "fp16": PREC_F16}
+PREC_F16X3 = 4  # fp32-class accuracy on the tensor cores (split fp16 operands)
+PRECISIONS = {"bf16": PREC_BF16, "fp32": PREC_FP32, "fp16": PREC_F16, "fp16x3": PREC_F16X3}
 TRAIN_PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32}
 PHASES = ("stage", "gemm1", "layernorm", "gemm2", "recurrence", "head")
 

@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <new>
 #include <tuple>
@@ -189,6 +191,10 @@ struct prego_model {
     // 16-bit operands of the tcgen05 path, [0] = fp16, [1] = bf16
     void *w1_16[2] = {nullptr, nullptr}, *wih_16p[2] = {nullptr, nullptr}, *whh_16p[2] = {nullptr, nullptr},
          *wc_16p[2] = {nullptr, nullptr};
+    // split-fp16 (PREGO_PREC_F16X3) weights: rows [hi | hi | lo] of scale * W (fp16, [N, 3 K]), gate-interleaved like the 16-bit copies
+    __half *w1_x3 = nullptr, *wih_x3 = nullptr, *whh_x3 = nullptr;
+    float inv_scale_x3[3] = {1.f, 1.f, 1.f};  // 1 / scale of w1, wih, whh (powers of two)
+    unsigned* absmax = nullptr;               // [3] scratch of the scale search
     // latency-kernel exchange
     uint2* xchg = nullptr;
     uint4* xchg_bwd = nullptr;  // [2][4][H] exchange words of the persistent BPTT kernel
@@ -234,6 +240,7 @@ struct Plan {
     int64_t sync;          // uint32 [Tc, ceil(B/256)] dependency counters  (batched 16-bit recurrence)
     int64_t online;        // fp32 scratch of the per-frame online path: 8 x (E + 3H + H)
     int64_t h32t;          // fp32 state in the recurrence's tiled order, rows padded to 128 (batched 16-bit recurrence)
+    int64_t x3;            // fp16 [Mc, 3 max(Din, E)] | [B, 3 H]: split operands of the PREGO_PREC_F16X3 GEMMs
     int64_t lnstat;        // float2 [E / 256][Mc] partial (sum, sum of squares) + float2 [Mc] (rstd, -mean rstd): fused-LayerNorm path
     int64_t total;
 };
@@ -251,7 +258,7 @@ Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec, bool doub
     };
     p.h32_a = take(B * H * 4);
     p.h32_b = take(B * H * 4);
-    const bool h16 = prec != PREGO_PREC_FP32;
+    const bool h16 = prec != PREGO_PREC_FP32 && prec != PREGO_PREC_F16X3;
     const bool batched = B > kLatencyMaxB;
     p.xb = h16 ? take(Mc * Din * 2) : 0;
     p.xb2 = (h16 && double_xb && B > kLatencyMaxB) ? take(Mc * Din * 2) : 0;
@@ -263,8 +270,11 @@ Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec, bool doub
     p.logits = h16 ? 0 : take(Mc * K * 4);
     p.online = h16 ? take(kOnlineMaxRows * (E + 3 * H + H) * 4) : 0;
     p.sync = (h16 && batched) ? take(Tc * ((B + 255) / 256) * 4) : 0;
-    p.h32t = (h16 && batched) ? take((B + 127) / 128 * 128 * H * 4) : 0;
+    // a CTA pair owns 256 rows and reads / writes the state of all of them without a mask: pad to the PAIR tile (padding to 128 let
+    // the second CTA of the last pair run past the buffer whenever B % 256 is in (0, 128]; found by compute-sanitizer in round 2)
+    p.h32t = (h16 && batched) ? take((B + 255) / 256 * 256 * H * 4) : 0;
     p.lnstat = (h16 && use_ln_fused()) ? take(Mc * (E / 256 + 1) * 8) : 0;
+    p.x3 = prec == PREGO_PREC_F16X3 ? take(std::max(Mc * 3 * std::max(Din, E), B * 3 * H) * 2) : 0;
     p.total = off;
     return p;
 }
@@ -477,7 +487,7 @@ int make_tmap_feat(CUtensorMap* tm, DType dt, const void* base, uint64_t D, uint
 // [rows * A, H], then the SAME classifier + softmax / argmax.  Produced in row slabs that fit the caller's buffer.
 inline int64_t ant_row_bytes(const prego_model* m, int prec) {
     const int64_t A = m->ant_len, H = m->d.hidden_dim, K = m->d.num_classes;
-    return prec == PREGO_PREC_FP32 ? A * H * 4 + A * K * 4 : A * H * 2;
+    return (prec == PREGO_PREC_FP32 || prec == PREGO_PREC_F16X3) ? A * H * 4 + A * K * 4 : A * H * 2;
 }
 inline int64_t ant_slab_rows(const prego_model* m, const prego_anticipation_args_t* ant, int prec, int64_t Mc) {
     int64_t rows = static_cast<int64_t>(ant->workspace_bytes) / ant_row_bytes(m, prec);
@@ -855,6 +865,63 @@ int chunk_f32(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint
     return PREGO_OK;
 }
 
+// One time chunk of the split-fp16 mode (PREGO_PREC_F16X3): the exact-fp32 path's structure (stream-major rows, fp32 LayerNorm /
+// gates / state / softmax) with every large GEMM on tcgen05 over [hi | lo | hi] x [hi | hi | lo] operands (simt_kernels.cuh).
+int chunk_x3(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt, int64_t t0, int tc,
+             cudaStream_t s, const prego_anticipation_args_t* ant = nullptr) {
+    const prego_dims_t& d = m->d;
+    const int64_t B = a->B, T = a->T, Mc = B * tc;
+    const int Mi = static_cast<int>(Mc);
+    const int H = d.hidden_dim, E = d.embed_dim, K = d.num_classes, Din = m->din;
+    float* y32 = reinterpret_cast<float*>(ws + p.ye);
+    float* gi = reinterpret_cast<float*>(ws + p.gi);
+    float* hr32 = reinterpret_cast<float*>(ws + p.hrelu);
+    float* gh = reinterpret_cast<float*>(ws + p.gh);
+    float* logits_ws = reinterpret_cast<float*>(ws + p.logits);
+    __half* x3 = reinterpret_cast<__half*>(ws + p.x3);
+    CUtensorMap tmA, tmB;
+
+    stage_features_split3<<<grid_for(Mc * (Din / 4), 256, m->sm_count), 256, 0, s>>>(static_cast<const float*>(a->rgb), a->flow_is_zero ? nullptr : static_cast<const float*>(a->flow), x3, Mc,
+                                                                                    d.d_rgb, d.d_flow, tc, (int)T, (int)t0);
+    LAUNCH_CHECK("stage_features_split3");
+    prof_mark(m, s, PREGO_PHASE_STAGE, 1);
+    RC_TRY(make_tmap_a(&tmA, kF16, x3, 3 * (uint64_t)Din, Mc));
+    RC_TRY(make_tmap_w(&tmB, kF16, m->w1_x3, 3 * (uint64_t)Din, E, 128));
+    RC_TRY((launch_gemm_tc2<256, 6, 0>(tmA, tmB, Mi, E, 3 * Din, 0, EpiStore<256, -1>{y32, m->b1, E, 0, 0, 0, 0, m->inv_scale_x3[0]}, m->sm_count, s, "gemm1 (split fp16)")));
+    prof_mark(m, s, PREGO_PHASE_GEMM1, 1);
+    layernorm_relu_f32<<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(y32, y32, m->ln_g, m->ln_b, Mc, E, 1e-5f);
+    split3_rows_f32<<<grid_for(Mc * (E / 4), 256, m->sm_count), 256, 0, s>>>(y32, x3, Mc, E);
+    LAUNCH_CHECK("layernorm_relu_f32 / split3_rows_f32");
+    prof_mark(m, s, PREGO_PHASE_LAYERNORM, 2);
+    RC_TRY(make_tmap_a(&tmA, kF16, x3, 3 * (uint64_t)E, Mc));
+    RC_TRY(make_tmap_w(&tmB, kF16, m->wih_x3, 3 * (uint64_t)E, 3 * H, 128));
+    RC_TRY((launch_gemm_tc2<256, 6, 0>(tmA, tmB, Mi, 3 * H, 3 * E, 0, EpiStore<256, -1>{gi, m->bih_p, 3 * H, 0, 0, 0, 0, m->inv_scale_x3[1]}, m->sm_count, s, "gemm2 (split fp16)")));
+    prof_mark(m, s, PREGO_PHASE_GEMM2, 1);
+
+    if (B <= kLatencyMaxB) {
+        RC_TRY(run_latency_recurrence(m, gi, h_cur, h_alt, hr32, B, tc, -1, tc, 1, s));
+        prof_mark(m, s, PREGO_PHASE_RECURRENCE, (int)((B + 3) / 4));
+    } else {
+        RC_TRY(make_tmap_a(&tmA, kF16, x3, 3 * (uint64_t)H, B));
+        RC_TRY(make_tmap_w(&tmB, kF16, m->whh_x3, 3 * (uint64_t)H, 3 * H, 128));
+        for (int t = 0; t < tc; ++t) {
+            split3_rows_f32<<<grid_for(B * (H / 4), 256, m->sm_count), 256, 0, s>>>(h_cur, x3, B, H);
+            RC_TRY((launch_gemm_tc2<256, 6, 0>(tmA, tmB, (int)B, 3 * H, 3 * H, 0, EpiStore<256, -1>{gh, m->bhh_p, 3 * H, 0, 0, 0, 0, m->inv_scale_x3[2]}, m->sm_count, s, "recurrent gemm (split fp16)")));
+            gru_gates_f32<<<grid_for(B * H, 256, m->sm_count), 256, 0, s>>>(gi, gh, h_cur, hr32, (int)B, H, tc, t);
+        }
+        LAUNCH_CHECK("split fp16 recurrence");
+        prof_mark(m, s, PREGO_PHASE_RECURRENCE, 3 * tc);
+    }
+
+    SgemmA Ah{hr32, nullptr, H, H, 0, 0, tc, (int)T, (int)t0};
+    sgemm_nt_f32<<<dim3((K + 127) / 128, (Mi + 127) / 128), 256, 0, s>>>(Ah, m->wc_f32, m->bc, logits_ws, Mi, K, H, K);
+    softmax_argmax_f32<<<grid_for(Mc * 32, 256, m->sm_count), 256, 0, s>>>(logits_ws, a->probs, a->logits, a->labels, Mc, K, tc, (int)T, (int)t0, 1, 0);
+    LAUNCH_CHECK("fp32 head");
+    if (ant != nullptr) RC_TRY(anticipation_f32(m, a, ant, hr32, Mc, tc, t0, s));
+    prof_mark(m, s, PREGO_PHASE_HEAD, 2);
+    return PREGO_OK;
+}
+
 template <int FMT>
 int pack16(prego_model* m, const prego_weights_t* w, cudaStream_t s) {
     using OpT = typename Op16<FMT>::T;
@@ -934,6 +1001,7 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
         ALLOC(m->w1_16[f], E * din * 2); ALLOC(m->wih_16p[f], 3 * H * E * 2); ALLOC(m->whh_16p[f], 3 * H * H * 2);
         if (m->kpad) ALLOC(m->wc_16p[f], (int64_t)m->kpad * H * 2);
     }
+    ALLOC(m->w1_x3, E * 3 * din * 2); ALLOC(m->wih_x3, 3 * H * 3 * E * 2); ALLOC(m->whh_x3, 3 * H * 3 * H * 2); ALLOC(m->absmax, 3 * sizeof(unsigned));
     ALLOC(m->xchg, 2 * 4 * H * sizeof(uint2)); ALLOC(m->err_flag, sizeof(int)); ALLOC(m->wct_f32, K * H * 4);
     ALLOC(m->online_scratch, online_fused_scratch_floats((int)E, (int)K) * 4);
 #undef ALLOC
@@ -960,7 +1028,7 @@ int prego_model_destroy(prego_model_t* m) {
     void* ptrs[] = {m->w1_f32, m->b1, m->ln_g, m->ln_b, m->wih_f32p, m->whh_f32p, m->bih_p, m->bhh_p, m->bgi_p, m->wc_f32, m->bc,
                     m->w1_16[0], m->w1_16[1], m->wih_16p[0], m->wih_16p[1], m->whh_16p[0], m->whh_16p[1], m->wc_16p[0],
                     m->wc_16p[1], m->xchg, m->xchg_bwd, m->err_flag, m->wct_f32, m->online_scratch, m->online_stream[0], m->online_stream[1],
-                    m->wa_f32, m->ba, m->wa_16[0], m->wa_16[1]};
+                    m->wa_f32, m->ba, m->wa_16[0], m->wa_16[1], m->w1_x3, m->wih_x3, m->whh_x3, m->absmax};
     for (void* p : ptrs)
         if (p != nullptr) cudaFree(p);
     for (cudaEvent_t e : m->prof_ev)
@@ -1000,6 +1068,29 @@ int prego_model_load_weights(prego_model_t* m, const prego_weights_t* w, void* s
     LAUNCH_CHECK("fp32 weight packing");
     RC_TRY(pack16<0>(m, w, s));
     RC_TRY(pack16<1>(m, w, s));
+    {   // split-fp16 copies: power-of-two scale per matrix so that max |scale * w| sits near 2^14 (hi far from fp16's overflow, lo in
+        // its normal range); one small synchronisation per load_state_dict
+        const float* srcs[3] = {w->layer1_0_weight, w->gru_weight_ih_l0, w->gru_weight_hh_l0};
+        const int64_t ns[3] = {(int64_t)E * din, (int64_t)3 * H * E, (int64_t)3 * H * H};
+        CUDA_TRY(cudaMemsetAsync(m->absmax, 0, 3 * sizeof(unsigned), s));
+        for (int i = 0; i < 3; ++i) absmax_f32<<<g(ns[i]), T, 0, s>>>(srcs[i], ns[i], m->absmax + i);
+        unsigned bits[3];
+        CUDA_TRY(cudaMemcpyAsync(bits, m->absmax, sizeof(bits), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        float scale[3];
+        for (int i = 0; i < 3; ++i) {
+            float mx;
+            memcpy(&mx, &bits[i], 4);
+            int e = (mx > 0.f && std::isfinite(mx)) ? static_cast<int>(std::floor(std::log2(16384.0f / mx))) : 0;
+            e = std::max(-24, std::min(24, e));
+            scale[i] = std::ldexp(1.0f, e);
+            m->inv_scale_x3[i] = std::ldexp(1.0f, -e);
+        }
+        pack_rows_split3<<<g(ns[0]), T, 0, s>>>(w->layer1_0_weight, m->w1_x3, E, din, H, 0, scale[0]);
+        pack_rows_split3<<<g(ns[1]), T, 0, s>>>(w->gru_weight_ih_l0, m->wih_x3, 3 * H, E, H, 1, scale[1]);
+        pack_rows_split3<<<g(ns[2]), T, 0, s>>>(w->gru_weight_hh_l0, m->whh_x3, 3 * H, H, H, 1, scale[2]);
+        LAUNCH_CHECK("split-fp16 weight packing");
+    }
     m->loaded = true;
     return PREGO_OK;
 }
@@ -1018,11 +1109,14 @@ static int forward_impl(prego_model_t* m, const prego_forward_args_t* a, const p
     if (a->feature_dtype != PREGO_FEAT_F32 && a->feature_dtype != PREGO_FEAT_16) return fail(PREGO_ERR_INVALID, "unknown feature_dtype %d", a->feature_dtype);
     if (a->flow_is_zero && d.d_rgb == 0) return fail(PREGO_ERR_INVALID, "flow_is_zero on a flow-only model leaves no input");
     if ((d.d_rgb > 0 && a->rgb == nullptr) || (d.d_flow > 0 && !a->flow_is_zero && a->flow == nullptr)) return fail(PREGO_ERR_INVALID, "rgb / flow pointer is NULL");
-    if (a->feature_dtype == PREGO_FEAT_16 && a->precision == PREGO_PREC_FP32)
-        return fail(PREGO_ERR_INVALID, "16-bit features (PREGO_FEAT_16) need PREGO_PREC_F16 or PREGO_PREC_BF16; the exact path reads fp32 features");
-    if (a->precision != PREGO_PREC_BF16 && a->precision != PREGO_PREC_FP32 && a->precision != PREGO_PREC_F16)
+    const bool exact = a->precision == PREGO_PREC_FP32 || a->precision == PREGO_PREC_F16X3;
+    if (a->feature_dtype == PREGO_FEAT_16 && exact)
+        return fail(PREGO_ERR_INVALID, "16-bit features (PREGO_FEAT_16) need PREGO_PREC_F16 or PREGO_PREC_BF16; the fp32-class paths read fp32 features");
+    if (a->precision != PREGO_PREC_BF16 && a->precision != PREGO_PREC_FP32 && a->precision != PREGO_PREC_F16 && a->precision != PREGO_PREC_F16X3)
         return fail(PREGO_ERR_INVALID, "unknown precision %d", a->precision);
-    const bool h16 = a->precision != PREGO_PREC_FP32;
+    if (a->precision == PREGO_PREC_F16X3 && ((3 * d.hidden_dim) % 256 != 0 || m->din % 64 != 0))
+        return fail(PREGO_ERR_INVALID, "PREGO_PREC_F16X3 needs 3 * hidden_dim %% 256 == 0 (got hidden_dim %d); use PREGO_PREC_FP32", d.hidden_dim);
+    const bool h16 = !exact;
     if (h16 && m->kpad == 0) return fail(PREGO_ERR_INVALID, "16-bit paths support num_classes <= 128 (got %d); use PREGO_PREC_FP32", d.num_classes);
     const int64_t Tc = (a->chunk_T > 0 && a->chunk_T < T) ? a->chunk_T : T;
     if (B * Tc >= (int64_t(1) << 31) / 4) return fail(PREGO_ERR_INVALID, "B * chunk_T = %lld is too large for one pass; lower chunk_T", (long long)(B * Tc));
@@ -1084,6 +1178,7 @@ static int forward_impl(prego_model_t* m, const prego_forward_args_t* a, const p
         }
         if (a->precision == PREGO_PREC_F16) RC_TRY(chunk_16<0>(m, a, p, ws, h_cur, h_alt, t0, tc, s, ci, overlap, t_next, tc_next, ant));
         else if (a->precision == PREGO_PREC_BF16) RC_TRY(chunk_16<1>(m, a, p, ws, h_cur, h_alt, t0, tc, s, ci, overlap, t_next, tc_next, ant));
+        else if (a->precision == PREGO_PREC_F16X3) RC_TRY(chunk_x3(m, a, p, ws, h_cur, h_alt, t0, tc, s, ant));
         else RC_TRY(chunk_f32(m, a, p, ws, h_cur, h_alt, t0, tc, s, ant));
     }
     if (a->h_state != nullptr && h_cur != a->h_state)

@@ -372,6 +372,7 @@ struct EpiStore {
     int Tc, B;          // Tc == 0: no re-ordering
     int accumulate = 0; // fp32 output only: out += acc (+ bias)
     int relu = 0;       // out = max(acc + bias, 0)  (anticipation layer of MROADA, rnn.py:125-126)
+    float scale = 1.0f; // out = acc * scale + bias  (split-fp16 mode: the weights travel pre-scaled by a power of two)
 
     __device__ __forceinline__ void operator()(uint32_t taddr, int row, int n0, bool valid) const {
         const int64_t orow = Tc > 0 ? static_cast<int64_t>(row % Tc) * B + row / Tc : row;
@@ -386,10 +387,10 @@ struct EpiStore {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float4 bb = bias != nullptr ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
-                f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
-                f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
-                f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+                f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), scale, bb.x);
+                f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), scale, bb.y);
+                f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), scale, bb.z);
+                f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), scale, bb.w);
             }
             if (relu) {
 #pragma unroll

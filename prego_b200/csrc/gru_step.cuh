@@ -83,7 +83,7 @@ __device__ __forceinline__ void dep_wait(const uint32_t* ctr, uint32_t target, i
 
 struct GruSeqArgs {
     const float* bhh;   // [3H] packed order
-    float* h32t;        // fp32 master state, tiled order (in/out), rows padded to a multiple of 128
+    float* h32t;        // fp32 master state, tiled order (in/out), rows padded to a multiple of 256 (the pair tile: no row mask in the epilogue)
     uint32_t* done;     // [Tc][m_tiles] dependency counters, or nullptr (single step, no protocol)
     int* err_flag;
     int B, H;

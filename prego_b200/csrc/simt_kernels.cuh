@@ -423,4 +423,83 @@ __global__ void f32_to_16(const float* __restrict__ src, typename Op16<FMT>::T* 
         dst[i] = Op16<FMT>::from_float(src[i]);
 }
 
+// ---------------------------------------------------------------------------------------
+// Split-fp16 operands ("fp16x3", the fp32-class tensor-core mode): an fp32 value v is carried as hi = fp16(v) and
+// lo = fp16(v - hi) (22 significant bits together), and a product x . w is evaluated as
+//     x_hi w_hi + x_lo w_hi + x_hi w_lo                 (the lo . lo term, 2^-22 relative, is dropped)
+// by ONE tcgen05 GEMM over a three times longer K: activation rows [hi | lo | hi], weight rows [hi | hi | lo].
+// fp16 x fp16 products are exact in the fp32 accumulator.  Weights are pre-scaled by a power of two so that their lo
+// parts stay in fp16's normal range; the epilogue multiplies the accumulator by the inverse (exact).
+__device__ __forceinline__ void split_hi_lo(float v, __half& hi, __half& lo) {
+    const float c = fminf(fmaxf(v, -65504.f), 65504.f);
+    hi = __float2half_rn(c);
+    lo = __float2half_rn(c - __half2float(hi));
+}
+
+// dst[m, 0:K] = hi, dst[m, K:2K] = lo, dst[m, 2K:3K] = hi of src[m, :] (row-major fp32 [M, K]); 4 elements per thread.
+__global__ void __launch_bounds__(256)
+split3_rows_f32(const float* __restrict__ src, __half* __restrict__ dst, int64_t M, int K) {
+    const int vec = K / 4;
+    const int64_t total = M * vec;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t m = i / vec;
+        const int c = static_cast<int>(i % vec) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + m * K + c);
+        __half h[4], l[4];
+        split_hi_lo(v.x, h[0], l[0]); split_hi_lo(v.y, h[1], l[1]); split_hi_lo(v.z, h[2], l[2]); split_hi_lo(v.w, h[3], l[3]);
+        __half* d = dst + m * 3 * static_cast<int64_t>(K) + c;
+        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(d + K) = *reinterpret_cast<const uint2*>(l);
+        *reinterpret_cast<uint2*>(d + 2 * K) = *reinterpret_cast<const uint2*>(h);
+    }
+}
+
+// Feature staging of the split mode: chunk row m (STREAM-major, m = b * Tc + t, as in the exact-fp32 path) of [rgb | flow]
+// -> [hi | lo | hi] of width 3 D.
+__global__ void __launch_bounds__(256)
+stage_features_split3(const float* __restrict__ rgb, const float* __restrict__ flow, __half* __restrict__ dst, int64_t Mc, int Dr,
+                      int Df, int Tc, int T, int t0) {
+    const int D = Dr + Df, vec = D / 4;
+    const int64_t total = Mc * vec;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t m = i / vec;
+        const int c = static_cast<int>(i % vec) * 4;
+        const int64_t g = chunk_row_to_global(m, Tc, T, t0);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // flow == nullptr: the caller declared the flow stream all-zero
+        if (c < Dr) v = __ldcs(reinterpret_cast<const float4*>(rgb + g * Dr + c));
+        else if (flow != nullptr) v = __ldcs(reinterpret_cast<const float4*>(flow + g * Df + (c - Dr)));
+        __half h[4], l[4];
+        split_hi_lo(v.x, h[0], l[0]); split_hi_lo(v.y, h[1], l[1]); split_hi_lo(v.z, h[2], l[2]); split_hi_lo(v.w, h[3], l[3]);
+        __half* d = dst + m * 3 * static_cast<int64_t>(D) + c;
+        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(d + D) = *reinterpret_cast<const uint2*>(l);
+        *reinterpret_cast<uint2*>(d + 2 * D) = *reinterpret_cast<const uint2*>(h);
+    }
+}
+
+// Weights of the split mode: dst[p, 0:K] = hi, [K:2K] = hi, [2K:3K] = lo of scale * src[row(p), :]; rows optionally in the
+// packed gate-interleaved order; columns [0, col_limit) of src only (zero-flow elision is not offered in this mode: col_limit = cols).
+__global__ void pack_rows_split3(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols, int H, int permute, float scale) {
+    const int64_t total = static_cast<int64_t>(rows) * cols;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+        const int r = permute ? packed_to_orig_row(p, H) : p;
+        __half hi, lo;
+        split_hi_lo(src[static_cast<int64_t>(r) * cols + c] * scale, hi, lo);
+        __half* d = dst + static_cast<int64_t>(p) * 3 * cols + c;
+        d[0] = hi;
+        d[cols] = hi;
+        d[2 * cols] = lo;
+    }
+}
+
+// max |src[i]| as the bit pattern of a non-negative float (atomicMax on the unsigned view is order-preserving)
+__global__ void absmax_f32(const float* __restrict__ src, int64_t n, unsigned* __restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) m = fmaxf(m, fabsf(src[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
 }  // namespace prego

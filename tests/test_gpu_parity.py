@@ -161,6 +161,19 @@ def test_forward_fp32_matches_reference(dev, golden_meta, name):
 
 
 @pytest.mark.parametrize("name", ALL_CASES)
+def test_forward_split_fp16_matches_reference_at_the_fp32_bound(dev, golden_meta, name):
+    """PREGO_PREC_F16X3: every fp32 operand as fp16 hi + lo on the tensor cores -- the SAME 1e-4 bound as the exact path."""
+    gold = load_model_case(name)
+    cfg, rgb, flow = case_inputs(golden_meta, name, dev)
+    model = seeded_weights_checked(golden_meta, name, dev)
+    out = model.infer(rgb, flow, want_logits=True, precision="fp16x3")
+    torch.cuda.synchronize()
+    rel, agree = _check_against_reference(out, gold, FP32_REL, near_tie_floor=1e-5)
+    print(f"[fp16x3 {name}] rel logit err {rel:.2e}, label agreement {agree:.5f}")
+    assert agree >= 0.999 and rel <= 2e-5
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_forward_fp16_matches_reference(dev, golden_meta, name):
     gold = load_model_case(name)
     cfg, rgb, flow = case_inputs(golden_meta, name, dev)
@@ -199,14 +212,14 @@ def test_forward_bf16_matches_reference(dev, golden_meta, name):
 
 
 @pytest.mark.parametrize("name,chunk", [("epic_b1_t300", 37), ("asm_b40_t24", 7), ("asm_b2_t160", 64)])
-@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16", "fp16x3"])
 def test_time_chunking_matches_whole_sequence(dev, golden_meta, name, chunk, prec):
     cfg, rgb, flow = case_inputs(golden_meta, name, dev)
     model = seeded_weights_checked(golden_meta, name, dev)
     whole = model.infer(rgb, flow, want_logits=True, precision=prec, chunk_T=rgb.shape[1])
     parts = model.infer(rgb, flow, want_logits=True, precision=prec, chunk_T=chunk)
     torch.cuda.synchronize()
-    tol = 1e-5 if prec == "fp32" else 1e-4  # 16-bit: the carried fp32 state is re-rounded per chunk identically
+    tol = 1e-5 if prec in ("fp32", "fp16x3") else 1e-4  # 16-bit: the carried fp32 state is re-rounded per chunk identically
     d = (whole["logits"] - parts["logits"]).abs().max().item()
     assert d <= tol, d
 
@@ -309,11 +322,13 @@ def test_big_batch_tensor_recurrence_vs_oracle(dev):
         assert np.abs(h.cpu().numpy() - ref_h).max() <= 2 * REL[prec]
         assert model.device_error() == 0
         print(f"[{prec} B=256] rel {rel:.2e} agree {agree:.4f}")
-    h32 = torch.zeros(256, 1024, device=dev)
-    out32 = model.infer(rgb, flow, h_state=h32, want_logits=True, precision="fp32")
-    torch.cuda.synchronize()
-    _check_against_reference(out32, gold, FP32_REL, near_tie_floor=1e-5)
-    assert np.abs(h32.cpu().numpy() - ref_h).max() <= 1e-4
+    for prec in ("fp32", "fp16x3"):   # exact FFMA path, and the split-fp16 tensor-core path (batched: per-step recurrent GEMM)
+        h32 = torch.zeros(256, 1024, device=dev)
+        out32 = model.infer(rgb, flow, h_state=h32, want_logits=True, precision=prec)
+        torch.cuda.synchronize()
+        rel, _ = _check_against_reference(out32, gold, FP32_REL, near_tie_floor=1e-5)
+        assert np.abs(h32.cpu().numpy() - ref_h).max() <= 1e-4
+        print(f"[{prec} B=256] rel {rel:.2e}")
 
 
 def test_module_forward_contract(dev, golden_meta):
