@@ -7,7 +7,8 @@ Same flow as the reference's eval branch -- flat YAML merged with argparse (main
 ``set_seed(20)`` (main.py:32), ``build_model`` -> ``load_state_dict`` (main.py:44-48), ``build_eval`` ->
 ``evaluate(model, testloader, logger, device)`` (main.py:49-55), which writes
 ``output_miniRoad/output_miniROAD.json`` -- without the reference's landmines (hard-coded ``cuda:1``,
-``ipdb`` breakpoints).  ``--synthetic N`` replaces the ``.npy`` feature files by N seeded
+``ipdb`` breakpoints).  ``--eval`` runs in ``precision: fp16x3`` unless the config or ``--precision`` says otherwise (fp32-class logits on the
+tensor cores, so the labels in the JSON are the reference's; ``fp16`` is the throughput mode).  ``--synthetic N`` replaces the ``.npy`` feature files by N seeded
 synthetic videos (no dataset ships with the repo); ``--eval synthetic`` keeps the seeded default weights.
 Without ``--eval`` the reference's training loop runs (main.py:59-115): sliding-window train loader
 (dataset.py:96-135), ``OadLoss``, AdamW (fused), ``train_one_epoch`` + evaluation every epoch, ``best.pth`` kept and
@@ -123,7 +124,9 @@ def main(argv=None):
     parser.add_argument("--no_flow", action="store_true")
     parser.add_argument("--synthetic", type=int, default=0, help="evaluate on N synthetic videos instead of .npy features")
     parser.add_argument("--device", type=str, default="cuda:0")
-    parser.add_argument("--precision", type=str, default=None, choices=["fp16", "bf16", "fp32"])
+    parser.add_argument("--precision", type=str, default=None, choices=["fp16", "bf16", "fp32", "fp16x3"],
+                        help="default: 'fp16x3' for --eval (fp32-class accuracy on the tensor cores: the labels written to "
+                             "output_miniROAD.json are the reference's), the config's / 'fp16' otherwise")
     parser.add_argument("--amp", action="store_true")
     parser.add_argument("--tensorboard", action="store_true")
     parser.add_argument("--lr_scheduler", action="store_true")
@@ -135,6 +138,10 @@ def main(argv=None):
     cfg.update({k: v for k, v in vars(args).items() if k not in ("precision", "num_epoch", "output_path") or v is not None})
     if args.amp:
         cfg["train_precision"] = "tf32"
+    if args.eval is not None and "precision" not in cfg:
+        # the JSON feeds the 200-frame mode vote and the anticipation branch: pay ~3x the fp16 path for fp32-class logits
+        # (1e-4 bound, 0 label flips in 131 072 frames vs the reference; tests/test_gpu_long.py) instead of 99.95 % agreement
+        cfg["precision"] = "fp16x3"
     set_seed(20)
     device = torch.device(args.device)
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(message)s")

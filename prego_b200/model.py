@@ -47,7 +47,8 @@ _STATE_KEYS = (
 
 @META_ARCHITECTURES.register("MiniROAD")
 class MROAD(nn.Module):
-    """B200-native MiniROAD.  Extra (optional) cfg keys: ``precision`` ('fp16' default | 'bf16' | 'fp32'),
+    """B200-native MiniROAD.  Extra (optional) cfg keys: ``precision`` ('fp16' default: throughput | 'bf16' | 'fp16x3': fp32-class
+    accuracy on the tensor cores (fp16 hi + lo operands) | 'fp32': exact CUDA-core FFMA),
     ``chunk_frames`` (frames per pass over all streams; bounds the workspace), ``train_precision`` ('fp32' default:
     exact CUDA-core GEMMs | 'tf32': the large projections and their gradients on tcgen05 kind::tf32)."""
 
