@@ -681,7 +681,7 @@ def run_ours(args, world, rank, local):
             the link and the host's memory system finish together.  Bit-identical labels (tests/test_gpu_parity.py)."""
             from prego_b200.ingest import HostRoundingStager
             st = HostRoundingStager(B, Tc, 2048, 0 if hf is None else 2048, args.precision, dev,
-                                    threads=len(my_cores), direct_streams=direct)  # this rank's core block (bound below); the pool inherits the mask
+                                    threads=pool_threads, direct_streams=direct)  # this rank's core block (bound below); the pool inherits the mask
             hl = torch.empty(B, Tc, dtype=torch.int32).pin_memory()
             dl = torch.empty(B, Tc, dtype=torch.int32, device=dev)
             h2 = torch.zeros(B, 1024, device=dev)
@@ -717,6 +717,9 @@ def run_ours(args, world, rank, local):
             os.sched_setaffinity(0, my_cores)
         except OSError:
             my_cores = all_cores
+        # two cores of the block stay with the Python thread / the CUDA driver / the submit worker: with the pool on ALL cores the
+        # launch path timeshares with the rounding threads and the loop loses ~10 % (measured r02: 4.5-4.7 M vs 4.9-5.7 M frames/s)
+        pool_threads = len(my_cores) - 2 if len(my_cores) > 4 else len(my_cores)
         hr, hf = rgb.cpu().pin_memory(), flow.cpu().pin_memory()
 
         def host_bounds():
@@ -739,7 +742,7 @@ def run_ours(args, world, rank, local):
             if args.precision != "fp32":
                 # the rounding pipeline alone (submit + wait, no model call): what this host can stage per second, all ranks at once
                 from prego_b200.ingest import HostRoundingStager
-                st = HostRoundingStager(B, Tc, 2048, 2048, args.precision, dev, threads=len(my_cores))
+                st = HostRoundingStager(B, Tc, 2048, 2048, args.precision, dev, threads=pool_threads)
                 n = 6
 
                 def stage_only(k):

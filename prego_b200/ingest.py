@@ -278,6 +278,9 @@ class HostRoundingStager:
         cores = os.cpu_count() or 1
         self.threads = int(threads or (cores - 2 if cores > 4 else cores))  # the rounding is memory-bound: leave two cores to Python / the driver
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        # the plain-fp32 rows of a split batch travel on their OWN stream: behind the ring's small copies on one stream they would
+        # serialise with them and stall the rounding ring until the large copy is through
+        self.direct_stream = torch.cuda.Stream(device=self.device) if self.Bd else None
         self.slots = []
         B16 = self.B - self.Bd
         # the C ring stager: a persistent pool of rounding threads + a pinned ring small enough to stay in the CPU's
@@ -289,7 +292,7 @@ class HostRoundingStager:
         for _ in range(slots):
             dev = [torch.empty(B16, self.T, d, dtype=self.dtype, device=self.device) if d and B16 else None for d in self.dims]
             dev32 = [torch.empty(self.Bd, self.T, d, dtype=torch.float32, device=self.device) if d and self.Bd else None for d in self.dims]
-            self.slots.append({"dev": dev, "dev32": dev32, "ready": torch.cuda.Event(), "free": torch.cuda.Event(),
+            self.slots.append({"dev": dev, "dev32": dev32, "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "direct_done": torch.cuda.Event(),
                                "issued": threading.Event(), "thread": None, "error": None})
         main = torch.cuda.current_stream(self.device)
         for s in self.slots:
@@ -307,14 +310,20 @@ class HostRoundingStager:
                 slot["flow"], slot["zero_flow"] = False, True
             with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(slot["free"])  # the consumer is done with this slot's device tensors
-                for src, d32 in zip(srcs, slot["dev32"]):  # fp32 rows first: they keep the link busy while the host rounds
-                    if src is not None and d32 is not None:
-                        d32.copy_(src[:self.Bd], non_blocking=True)
+                if self.direct_stream is not None:
+                    self.direct_stream.wait_event(slot["free"])
+                    with torch.cuda.stream(self.direct_stream):  # fp32 rows: a second DMA queue next to the ring's copies
+                        for src, d32 in zip(srcs, slot["dev32"]):
+                            if src is not None and d32 is not None:
+                                d32.copy_(src[:self.Bd], non_blocking=True)
+                        slot["direct_done"].record(self.direct_stream)
                 for src, dev in zip(srcs, slot["dev"]):
                     if src is None or dev is None:
                         continue
                     _lib.check(lib.prego_host_stager_run(self._ring, src[self.Bd:].data_ptr(), dev.data_ptr(), dev.numel(), prec,
                                                          self.copy_stream.cuda_stream), "prego_host_stager_run")
+                if self.direct_stream is not None:
+                    self.copy_stream.wait_event(slot["direct_done"])
                 slot["ready"].record(self.copy_stream)
         except Exception as e:  # surfaced by wait()
             slot["error"] = e
