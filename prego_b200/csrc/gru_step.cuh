@@ -89,7 +89,7 @@ struct GruSeqArgs {
     int B, H;
     int t_begin, t_end;
     long long* stats = nullptr;  // diagnostics: per-CTA wait-cycle counters [grid][16] (PREGO_GRU_STATS)
-    int dbg = 0;        // diagnostics only (PREGO_GRU_DBG): 1 = no gate math, 2 = no dependency waits, 4 = no gi loads, 8 = no result stores / publish, 16 = epilogue handshakes only, 32 / 64 = no W / h operand loads
+    int dbg = 0;        // diagnostics only (PREGO_GRU_DBG): 1 = no gate math, 2 = no dependency waits, 4 = no gi loads, 8 = no result stores / publish, 16 = epilogue handshakes only, 32 / 64 = no W / h operand loads, 256 = no result stores (publish kept), 512 = no publish (stores kept; combine with 2), 1024 / 2048 / 4096 = publish without its __threadfence / proxy fence / bulk-store wait
 };
 
 // DIAG = true compiles the diagnostic knobs (a.dbg) and the per-role wait-cycle counters (a.stats) in; the product
@@ -251,17 +251,17 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
             int pm0 = 0, pnt = 0, pt = 0, pmt = 0;
             auto store_and_publish = [&](int i_prev) {
                 // results of item i_prev are staged (epi_done already observed): store, free the staging, publish
-                if (!(dbg & 8)) {
+                if (!(dbg & (8 | 256))) {
                 ptx::tma_store_3d(&tmHseq, out_smem, pnt * 64, pm0, pt + 1);
                 ptx::tma_store_3d(&tmHrelu, out_smem + kGruBoxBytes, pnt * 64, pm0, pt);
                 ptx::tma_store_commit();
                 ptx::tma_store_wait_read();
                 }
                 ptx::mbar_arrive(out_free);
-                if (a.done != nullptr && !(dbg & 8)) {
-                    ptx::tma_store_wait_all();
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    __threadfence();  // also carries the epilogue warps' fp32 state stores (observed through epi_done)
+                if (a.done != nullptr && !(dbg & (8 | 512))) {
+                    if (!(dbg & 4096)) ptx::tma_store_wait_all();
+                    if (!(dbg & 2048)) asm volatile("fence.proxy.async;" ::: "memory");
+                    if (!(dbg & 1024)) __threadfence();  // also carries the epilogue warps' fp32 state stores (observed through epi_done)
                     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.done + pt * m_tiles + pmt) : "memory");
                 }
                 (void)i_prev;
