@@ -102,7 +102,8 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
 int prego_model_destroy(prego_model_t* model);
 
 /* Replaces model.load_state_dict(torch.load(path)) (main.py:48): packs the ten fp32 tensors into the
- * library-owned operand formats (bf16 copies, gate-interleaved GRU rows, padded head). */
+ * library-owned operand formats (fp16 / bf16 copies, split-fp16 copies with a per-matrix power-of-two scale, gate-interleaved GRU
+ * rows, padded head).  Synchronises `stream` once (the scale search reads three maxima back): not capturable into a CUDA graph. */
 int prego_model_load_weights(prego_model_t* model, const prego_weights_t* w, void* stream);
 
 size_t prego_workspace_bytes(const prego_model_t* model, int64_t B, int64_t chunk_T, int32_t precision);

@@ -132,10 +132,12 @@ def main(argv=None):
     parser.add_argument("--lr_scheduler", action="store_true")
     parser.add_argument("--num_epoch", type=int, default=None)
     parser.add_argument("--output_path", type=str, default=None)
+    parser.add_argument("--aggregate_out", type=str, default=None,
+                        help="with --eval: also collapse output_miniRoad/output_miniROAD.json to step sequences (utils/aggregate.py) into this file")
     args = parser.parse_args(argv)
 
     cfg = yaml.load(open(args.config), Loader=yaml.FullLoader)
-    cfg.update({k: v for k, v in vars(args).items() if k not in ("precision", "num_epoch", "output_path") or v is not None})
+    cfg.update({k: v for k, v in vars(args).items() if k not in ("precision", "num_epoch", "output_path", "aggregate_out") or v is not None})
     if args.amp:
         cfg["train_precision"] = "tf32"
     if args.eval is not None and "precision" not in cfg:
@@ -165,6 +167,12 @@ def main(argv=None):
             model.load_state_dict(torch.load(args.eval, map_location=device))
         mAP = evaluate(model, testloader, logger, device)
         logger.info(f'{cfg["task"]} result: {mAP * 100:.2f} m{cfg["metric"]}')
+        if args.aggregate_out is not None and cfg.get("task") != "ANTICIPATION":
+            # the next stage of the reference pipeline (python utils/aggregate.py <in> <out>, aggregate.py:93-109) on the JSON just written
+            from .aggregate import aggregate
+            from .evaluate import Evaluate
+            aggregate(json.load(open(osp.join(Evaluate.OUTPUT_DIR, Evaluate.OUTPUT_FILE))), args.aggregate_out)
+            logger.info(f"aggregated step sequences -> {args.aggregate_out}")
         return mAP
     return train(cfg, args, model, evaluate, testloader, dataset, logger, device)
 

@@ -768,3 +768,37 @@ print("FUSED_OK")
     r = subprocess.run([sys.executable, "-c", f"ROOT = {root!r}\n" + code], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, PREGO_LN_FUSED="1"))
     assert r.returncode == 0 and "FUSED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_main_eval_cli_writes_frame_and_aggregated_json(dev, tmp_path, monkeypatch):
+    """python -m prego_b200.main --config <yaml> --eval synthetic --synthetic N --aggregate_out <json>: registry -> MROAD ->
+    batched Evaluate (fp32-class default precision) -> output_miniRoad/output_miniROAD.json -> aggregated step sequences, the
+    two files the anticipation branch reads.  Frame labels against the fp32 oracle, aggregation against the oracle on them."""
+    import yaml
+    from prego_b200 import main as pmain, synthetic
+    cfg = dict(synthetic.EPIC_TENT_O)
+    cfg.pop("eval")
+    cfg.update(root_path="unused", video_list_path="unused", annotation_type="target", test_batch_size=1, stride=4, batch_size=16,
+               lr=1e-4, weight_decay=0.05, num_epoch=1, optimizer="AdamW", loss="NONUNIFORM")
+    cfg_path = tmp_path / "cfg.yaml"
+    cfg_path.write_text(yaml.safe_dump(cfg))
+    monkeypatch.chdir(tmp_path)
+    mAP = pmain.main(["--config", str(cfg_path), "--eval", "synthetic", "--synthetic", "3", "--device", "cuda:0",
+                      "--aggregate_out", str(tmp_path / "agg.json")])
+    assert 0.0 <= mAP <= 1.0
+    frames = json.load(open(tmp_path / "output_miniRoad" / "output_miniROAD.json"))
+    agg = json.load(open(tmp_path / "agg.json"))
+    assert list(frames) == list(agg) == [f"synthetic_{i}" for i in range(3)]
+    model = synthetic.seeded_model(dict(synthetic.EPIC_TENT_O), seed=20)
+    sd = model.state_dict()
+    lengths = pmain.SyntheticFeatures.LENGTHS["EPIC-TENT-O"]
+    for i, vid in enumerate(frames):
+        T = lengths[i % len(lengths)]
+        rgb, flow = synthetic.features(i, T, "cpu", True)
+        probs, logits, _ = miniroad_np.forward(sd, rgb.numpy()[None], flow.numpy()[None], return_all=True)
+        ref = probs[0].argmax(-1)
+        got = np.array(frames[vid]["pred"])
+        margin = miniroad_np.top2_margin(logits[0])
+        assert len(got) == T and np.array_equal(got[margin > 1e-4], ref[margin > 1e-4]) and (got == ref).mean() >= 0.9999
+        assert frames[vid]["gt"] == synthetic.targets(i, T, 12).argmax(-1).tolist()
+        assert agg[vid] == aggregate_np.aggregate_video(frames[vid]["pred"], frames[vid]["gt"])
