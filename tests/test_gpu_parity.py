@@ -26,7 +26,7 @@ pytestmark = pytest.mark.gpu
 
 ALL_CASES = ["epic_b1_t300", "asm_b2_t160", "asm_b1_t64_zeroflow", "epic_b1_t96_rgbonly", "asm_b40_t24"]
 FP32_REL, BF16_REL, F16_REL = 1e-4, 1e-2, 2e-3
-REL = {"fp32": FP32_REL, "bf16": BF16_REL, "fp16": F16_REL}
+REL = {"fp32": FP32_REL, "fp16x3": FP32_REL, "bf16": BF16_REL, "fp16": F16_REL}
 
 
 @pytest.fixture(scope="module")
@@ -555,7 +555,7 @@ def test_16bit_features_bit_identical(dev, prec, B, T, chunk):
         model.infer(rgb16, flow16, precision="fp32")
 
 
-@pytest.mark.parametrize("prec,feat16", [("fp16", False), ("fp16", True), ("bf16", True), ("fp32", False)])
+@pytest.mark.parametrize("prec,feat16", [("fp16", False), ("fp16", True), ("bf16", True), ("fp32", False), ("fp16x3", False)])
 @pytest.mark.parametrize("B,T", [(128, 5), (3, 9)])
 def test_zero_flow_elision_bit_identical(dev, prec, feat16, B, T):
     """flow_is_zero (the shipped configs feed flow = 0, dataset.py:63-69): skipping the flow half of the projection
@@ -609,7 +609,7 @@ def test_non_shipped_shapes_vs_oracle(dev, H, K, B, T):
     sd = {k: v.cpu() for k, v in model.state_dict().items()}
     _, ref, _ = miniroad_np.forward(sd, rgb.cpu().numpy(), flow.cpu().numpy(), return_all=True)
     scale = np.abs(ref).max()
-    for prec in ("fp32", "fp16"):
+    for prec in ("fp32", "fp16", "fp16x3"):
         out = model.infer(rgb, flow, want_logits=True, precision=prec)["logits"].cpu().numpy()
         assert np.abs(out - ref).max() <= REL[prec] * scale, prec
     rows = min(B, 8)

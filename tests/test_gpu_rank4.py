@@ -18,7 +18,7 @@ from test_oracle_rank4 import ANT_NAMES, ant_case
 
 pytestmark = pytest.mark.gpu
 
-REL = {"fp32": 1e-4, "bf16": 1e-2, "fp16": 2e-3}
+REL = {"fp32": 1e-4, "fp16x3": 1e-4, "bf16": 1e-2, "fp16": 2e-3}
 AP_TOL = 1e-12
 
 
@@ -45,7 +45,7 @@ def _check_labels(labels, ref_logits, err, what):
     assert np.all(margin[bad] < 4 * err + 1e-6), f"{what}: label flip away from a near-tie"
 
 
-@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp16x3", "fp16", "bf16"])
 @pytest.mark.parametrize("name", ANT_NAMES)
 def test_anticipation_forward_matches_reference(dev, meta4, name, prec):
     cfg, m, rgb, flow, gold = ant_case(meta4, name)
@@ -59,7 +59,7 @@ def test_anticipation_forward_matches_reference(dev, meta4, name, prec):
     _check_labels(out["anticipation_labels"].cpu().numpy(), gold["ant_logits"], e1, "anticipation")
     ap = out["anticipation_probs"].cpu().numpy()
     assert ap.shape == gold["ant_probs"].shape and np.abs(ap.sum(-1) - 1).max() < 1e-5
-    assert np.abs(ap - gold["ant_probs"]).max() <= {"fp32": 2e-6, "fp16": 2e-3, "bf16": 1e-2}[prec]
+    assert np.abs(ap - gold["ant_probs"]).max() <= {"fp32": 2e-6, "fp16x3": 1e-5, "fp16": 2e-3, "bf16": 1e-2}[prec]
     # probabilities are the softmax of the returned logits; labels are their first maximum
     assert np.array_equal(out["anticipation_labels"].cpu().numpy(), ap.argmax(-1))
     assert m.device_error() == 0
