@@ -665,7 +665,7 @@ def run_ours(args, world, rank, local):
 
             e2e_run(2)
             barrier()
-            n_e2e = max(6, min(2 * K, 12))  # the first step cannot overlap its own staging: enough steps that the fill is < 10 %
+            n_e2e = max(8, min(3 * K, 24))  # the first step cannot overlap its own staging: enough steps that the fill is ~4 %
             t0 = time.perf_counter()
             e2e_run(n_e2e)
             dt = torch.tensor([time.perf_counter() - t0], device=dev)
@@ -697,7 +697,7 @@ def run_ours(args, world, rank, local):
 
             run(2)
             barrier()
-            n_e2e = max(6, min(2 * K, 12))  # the first step cannot overlap its own staging: enough steps that the fill is < 10 %
+            n_e2e = max(8, min(3 * K, 24))  # the first step cannot overlap its own staging: enough steps that the fill is ~4 %
             t0 = time.perf_counter()
             run(n_e2e)
             dt = torch.tensor([time.perf_counter() - t0], device=dev)
