@@ -233,7 +233,7 @@ struct Plan {
     int64_t xb2;           // second staging buffer: features of chunk c+1 are staged while chunk c computes (0 = none)
     int64_t ye;            // fp16 y -> 16-bit e in place, or fp32  [Mc, E]
     int64_t gi;            // [Mc, 3H] fp16 (batched 16-bit recurrence) or fp32
-    int64_t hseq;          // 16-bit [Tc+1, B, H]                   (batched 16-bit recurrence)
+    int64_t hseq;          // 16-bit [2, B, H]: operand copies of h_{t-1} / h_t, ping-pong (batched 16-bit recurrence)
     int64_t hrelu;         // 16-bit or fp32 [Mc, H]
     int64_t gh;            // fp32 [B, 3H]                          (fp32 batched recurrence)
     int64_t logits;        // fp32 [Mc, K]                          (fp32 head)
@@ -264,7 +264,7 @@ Plan make_plan(const prego_dims_t& d, int64_t B, int64_t Tc, int prec, bool doub
     p.xb2 = (h16 && double_xb && B > kLatencyMaxB) ? take(Mc * Din * 2) : 0;
     p.ye = take(Mc * E * (h16 ? 2 : 4));
     p.gi = take(Mc * 3 * H * ((h16 && batched) ? 2 : 4));
-    p.hseq = (h16 && batched) ? take(B * (Tc + 1) * H * 2) : 0;
+    p.hseq = (h16 && batched) ? take(B * 2 * H * 2) : 0;
     p.hrelu = take(Mc * H * (h16 ? 2 : 4));
     p.gh = (!h16 && batched) ? take(B * 3 * H * 4) : 0;
     p.logits = h16 ? 0 : take(Mc * K * 4);
@@ -658,12 +658,12 @@ int chunk_16(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8
 
     // 5. recurrence
     if (batched) {
-        f32_to_16<FMT><<<grid_for(B * H, 256, m->sm_count), 256, 0, s>>>(h_cur, hseq, B * H);  // history slot 0 = carried state
+        f32_to_16<FMT><<<grid_for(B * H, 256, m->sm_count), 256, 0, s>>>(h_cur, hseq, B * H);  // slot 0 = carried state
         float* h32t = reinterpret_cast<float*>(ws + p.h32t);
         h32_retile<<<grid_for((B + 127) / 128 * 128 * (H / 4), 256, m->sm_count), 256, 0, s>>>(h_cur, h32t, (int)B, H, 1);
         LAUNCH_CHECK("f32_to_16 (hseq slot 0) / h32_retile");
         CUtensorMap tmHseq, tmW, tmGi, tmHrelu;
-        RC_TRY(make_tmap_tm(&tmHseq, dt, hseq, H, B, tc + 1, 2));
+        RC_TRY(make_tmap_tm(&tmHseq, dt, hseq, H, B, 2, 2));
         RC_TRY(make_tmap_w(&tmW, dt, m->whh_16p[FMT], H, 3 * H, kGruTileN / 2));
         RC_TRY(make_tmap_tm(&tmGi, kF16, gi, 3 * H, B, tc, 2));
         RC_TRY(make_tmap_tm(&tmHrelu, dt, hrelu, H, B, tc, 2));

@@ -22,7 +22,10 @@
 // tile (28 KB per k-block), 6-deep pipeline.
 //
 // Layouts (time-major inside a chunk so one step touches contiguous rows):
-//   hseq  [Tc+1, B, H]  16-bit operand history, slot t = h_{t-1}
+//   hseq  [2, B, H]     16-bit operand copies of the state, ping-pong: step t reads slot t & 1 (h_{t-1}) and writes slot (t + 1) & 1.
+//                       Two slots suffice: the items (t, m, .) that overwrite the slot holding h_{t-2} of stream block m only start once
+//                       done[t-1][m] says every item (t-1, m, .) -- the readers of h_{t-2} -- has published.  16 MB at B = 4096: the
+//                       operand copy lives in L2 and never costs DRAM writes (a [Tc+1, B, H] history did: 0.54 GB per 64 steps)
 //   gi    [Tc,   B, 3H] fp16, gate-interleaved columns (tile n: [r(64) | z(64) | n(64)]); includes b_ih and the
 //                       r / z parts of b_hh (pre-summed; b_hn must stay inside r * (W_hn h + b_hn))
 //   hrelu [Tc,   B, H]  16-bit relu(h_t)
@@ -96,7 +99,7 @@ struct GruSeqArgs {
 // instantiation (DIAG = false) carries neither.
 template <int FMT, bool DIAG = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGruThreads, 1)
-gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1) 16-bit, box (64, 128, 1)
+gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, 2) 16-bit, box (64, 128, 1)
                const __grid_constant__ CUtensorMap tmW,      // 2-D (H, 3H) 16-bit, box (64, 96): half a tile
                const __grid_constant__ CUtensorMap tmGi,     // 3-D (3H, B, Tc) fp16, box (64, 128, 1)
                const __grid_constant__ CUtensorMap tmHrelu,  // 3-D (H, B, Tc) 16-bit, box (64, 128, 1)
@@ -191,7 +194,7 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
                     uint8_t* sa = smem + stage * kGruStageBytes;
                     const uint32_t tx = ((dbg & 64) ? 0u : 2u * kGruABytes) + ((dbg & 32) ? 0u : 2u * (kGruStageBytes - kGruABytes));
                     if (leader) { if (tx) ptx::mbar_expect_tx(&full_bar[stage], tx); else ptx::mbar_arrive(&full_bar[stage]); }
-                    if (!(dbg & 64)) ptx::tma_load_3d_2sm(&tmHseq, sa, &full_bar[stage], kb * kTileK, m0, t, ptx::kEvictNormal);
+                    if (!(dbg & 64)) ptx::tma_load_3d_2sm(&tmHseq, sa, &full_bar[stage], kb * kTileK, m0, t & 1, ptx::kEvictNormal);
                     if (!(dbg & 32)) ptx::tma_load_2d_2sm(&tmW, sa + kGruABytes, &full_bar[stage], kb * kTileK, n0, ptx::kEvictLast);
                     stage += 2;  // this thread's k-blocks are every other slot of the ring
                     if (stage >= kGruStages) {
@@ -252,7 +255,7 @@ gru_seq_kernel(const __grid_constant__ CUtensorMap tmHseq,   // 3-D (H, B, Tc+1)
             auto store_and_publish = [&](int i_prev) {
                 // results of item i_prev are staged (epi_done already observed): store, free the staging, publish
                 if (!(dbg & (8 | 256))) {
-                ptx::tma_store_3d(&tmHseq, out_smem, pnt * 64, pm0, pt + 1);
+                ptx::tma_store_3d(&tmHseq, out_smem, pnt * 64, pm0, (pt + 1) & 1);
                 ptx::tma_store_3d(&tmHrelu, out_smem + kGruBoxBytes, pnt * 64, pm0, pt);
                 ptx::tma_store_commit();
                 ptx::tma_store_wait_read();
