@@ -214,39 +214,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // issues one M = 256 MMA for both.  Per CTA a k-block costs 16 KB + TILE_N*64 B instead of
 // 16 KB + TILE_N*128 B, so the same shared memory holds more stages: the single-CTA kernel is bound
 // by (bytes in flight) / (TMA latency ~1 us), not by the tensor pipe (profiles/r01_ncu_full_summary.txt).
-// Tile schedule of the CTA-pair GEMM.  A row block (256 rows x K) is shared by the n_tiles column tiles of that block; it is
-// fetched from DRAM once only if those tiles run at about the same time (L2 holds ~126 MB, a pass over all pairs' operands is more).
-// Plain round-robin (tile = pair + i * pairs) lets row blocks straddle two rounds whenever the number of pairs is not a multiple
-// of n_tiles (74 pairs, 8 or 12 column tiles): ncu showed GEMM1 reading 7.4 GB from DRAM for 2.2 GB of operands.  Here the pairs
-// form G = pairs / n_tiles GROUPS that take one row block per round in lockstep (pair j of a group = column tile j), and the
-// S = pairs % n_tiles left-over pairs each take a whole row block on their own, column tile after column tile (2 MB, re-read
-// from L2).  Per n_tiles rounds the groups finish G * n_tiles row blocks and every solo pair one: all pairs stay busy.
-struct PairTileSched {
-    int n_tiles, m_tiles, pairs, G, S, SR, pair;
-    __device__ __forceinline__ PairTileSched(int n_tiles_, int m_tiles_, int pairs_, int pair_)
-        : n_tiles(n_tiles_), m_tiles(m_tiles_), pairs(pairs_), G(pairs_ / n_tiles_), S(pairs_ % n_tiles_), SR(0), pair(pair_) {
-        SR = G * n_tiles + S;
-    }
-    // tile number `it` of this pair -> (row block, column tile); false = this pair is done (row blocks grow with `it`)
-    __device__ __forceinline__ bool get(int it, int& mb, int& nt) const {
-        if (G == 0) {  // fewer pairs than column tiles: plain round-robin
-            const int tile = pair + it * pairs;
-            mb = tile / n_tiles;
-            nt = tile % n_tiles;
-            return tile < n_tiles * m_tiles;
-        }
-        const int sup = it / n_tiles, r = it % n_tiles;
-        if (pair < G * n_tiles) {
-            mb = sup * SR + r * G + pair / n_tiles;
-            nt = pair % n_tiles;
-        } else {
-            mb = sup * SR + G * n_tiles + (pair - G * n_tiles);
-            nt = r;
-        }
-        return mb < m_tiles;
-    }
-};
-
 template <int TILE_N>
 struct Gemm2Cfg {
     static constexpr int kABytes = kTileM * kTileK * 2;
@@ -285,8 +252,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int k_blocks = K / kElemsK;
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
-    const PairTileSched sched(n_tiles, m_tiles, num_clusters, cluster_id);
-    (void)total_tiles;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
@@ -316,10 +281,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            int mb, nt;
-            for (int ti = 0; sched.get(ti, mb, nt); ++ti) {
-                const int m0 = mb * (2 * kTileM) + static_cast<int>(rank) * kTileM;
-                const int n0 = nt * TILE_N + static_cast<int>(rank) * (TILE_N / 2);
+            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+                const int m0 = (tile / n_tiles) * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+                const int n0 = (tile % n_tiles) * TILE_N + static_cast<int>(rank) * (TILE_N / 2);
                 const int c1 = rows_per_c1 > 0 ? a_c1 + m0 / rows_per_c1 : a_c1;
                 const int mr = rows_per_c1 > 0 ? m0 % rows_per_c1 : m0;
                 for (int kb = 0; kb < k_blocks; ++kb) {
@@ -342,8 +306,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             constexpr uint32_t idesc = ptx::make_idesc(FMT, 2 * kTileM, TILE_N);
             int stage = 0, it = 0;
             uint32_t phase = 0;
-            int mb, nt;
-            for (; sched.get(it, mb, nt); ++it) {
+            for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
                 const int buf = it & 1;
                 ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
                 ptx::tc_fence_after();
@@ -371,11 +334,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else {
         const int quad = warp & 3;
         int it = 0;
-        int mb, nt;
-        for (; sched.get(it, mb, nt); ++it) {
+        for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
             const int buf = it & 1;
-            const int m0 = mb * (2 * kTileM) + static_cast<int>(rank) * kTileM;
-            const int n0 = nt * TILE_N;
+            const int m0 = (tile / n_tiles) * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+            const int n0 = (tile % n_tiles) * TILE_N;
             ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + buf * Cfg::kAccStride + (static_cast<uint32_t>(quad * 32) << 16);
