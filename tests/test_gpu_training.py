@@ -211,3 +211,15 @@ def test_two_forwards_before_backward_keep_their_own_activations(dev):
     for k, p in model.named_parameters():
         want = g1[k] + g2[k]
         assert (p.grad.cpu() - want).abs().max().item() <= 1e-5 * max(want.abs().max().item(), 1e-6), k
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (runs under `gpurun --gpus 2`; the single-GPU box skips it)")
+def test_overlapped_allreduce_equals_mean_of_local_gradients_nccl():
+    """scripts/ddp_check.py under torchrun on 2 GPUs: the bucketed all-reduce that runs inside the CUDA backward gives every
+    rank exactly the mean of the ranks' local gradients (evidence of the round: worst relative difference 0.0)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(root, "scripts", "ddp_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and '"overlapped_allreduce_equals_mean_of_local_gradients": true' in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
