@@ -128,6 +128,8 @@ int prego_online_step(prego_online_t* session, const float* rgb, const float* fl
  * on the one-kernel-per-frame path opened with `labels` in pinned host memory support it (PREGO_ERR_STATE otherwise):
  * device-resident sessions do not pay the per-frame PCIe store.  probs / logits in host memory are fenced first. */
 int prego_online_wait(prego_online_t* session);
+/* prego_online_step + prego_online_wait in one call (one foreign-function round trip per frame for bindings where that costs ~1 us). */
+int prego_online_step_wait(prego_online_t* session, const float* rgb, const float* flow, void* stream);
 int prego_online_close(prego_online_t* session);
 /* Diagnostics: SM-clock stamps of the phase boundaries of the last frame, out[ctas][16] (host memory), for sessions
  * opened with the environment variable PREGO_ONLINE_TRACE=1; *num_ctas = rows written (<= max_ctas). */

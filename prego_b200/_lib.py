@@ -96,6 +96,7 @@ SIGNATURES = {
                                     C.POINTER(C.c_void_p)]),
     "prego_online_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "prego_online_wait": (C.c_int, [C.c_void_p]),
+    "prego_online_step_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "prego_online_close": (C.c_int, [C.c_void_p]),
     "prego_online_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "prego_device_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),

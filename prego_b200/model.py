@@ -397,19 +397,24 @@ class OnlineSession:
                            else torch.empty(self.B, 1, dtype=torch.int32, device=device))
             self.labels_np = self.labels.numpy() if host_labels else None
             self.probs = torch.empty(self.B, 1, model.out_dim, dtype=torch.float32, device=device) if want_probs else None
-            torch.cuda.current_stream(device).synchronize()  # weight packing done before the graph is built
+            self.stream = torch.cuda.current_stream(device)
+            self._stream_ptr = self.stream.cuda_stream
+            self._step_wait = lib.prego_online_step_wait
+            self.stream.synchronize()  # weight packing done before the graph is built
             _lib.check(lib.prego_online_open(model._handle, self.B, _lib.PRECISIONS[prec_name], self.h.data_ptr(),
                                              self.probs.data_ptr() if want_probs else None, None, self.labels.data_ptr(),
                                              C.byref(self._session)), "prego_online_open")
 
     def step_wait(self, rgb_frame, flow_frame):
-        """``step`` + host-side completion without a stream synchronize (``prego_online_wait``): returns once the
+        """``step`` + host-side completion without a stream synchronize (``prego_online_step_wait``): returns once the
         frame's labels are readable.  For ``host_labels`` sessions this is the whole per-frame round trip; the labels
-        are also exposed as the numpy view ``labels_np`` (no torch dispatch on the per-frame path)."""
-        self.step(rgb_frame, flow_frame)
-        rc = self._lib.prego_online_wait(self._session)
+        are also exposed as the numpy view ``labels_np`` (no torch dispatch on the per-frame path).  One foreign call per
+        frame, launched on the stream that was current when the session was opened (``self.stream``; looking the current
+        stream up through torch costs more than a microsecond per frame)."""
+        rc = self._step_wait(self._session, rgb_frame.data_ptr() if rgb_frame is not None else None,
+                             flow_frame.data_ptr() if flow_frame is not None else None, self._stream_ptr)
         if rc:
-            _lib.check(rc, "prego_online_wait")
+            _lib.check(rc, "prego_online_step_wait")
         return self.labels
 
     def close(self):
