@@ -440,9 +440,69 @@ def library_baseline_leg(dev, B, Tc, local):
         except Exception as e:  # noqa: BLE001
             out[mode] = {"error": repr(e)[:200]}
     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32_before
+    out["train_step"] = library_train_step(dev, Ref)
     out["note"] = (f"torch {torch.__version__} (cuBLAS + cuDNN GRU), the reference's module structure, {B} streams x {Tc} frames per step resident in HBM, "
                    "eval mode, softmax + device argmax; same GPU, same process, right after this repo's legs")
     del m, rgb, flow
+    torch.cuda.empty_cache()
+    return out
+
+
+def library_train_step(dev, Ref):
+    """BASELINE configs[4] on the library stack: the reference's training step (trainer/train.py:10-23: forward in train mode,
+    last-frame multi-label CE of criterions/loss.py:15-34, zero_grad, backward, torch.optim.AdamW of main.py:62-67) on stock
+    torch modules, same shapes and zero flow as training_leg.  `torch_defaults` = what the reference runs as shipped (fp32
+    cuBLAS matmuls, cuDNN GRU free to use TF32); `tf32` = both on TF32; `amp_fp16` = main.py --amp (autocast + GradScaler)."""
+    out = {}
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    for mode in ("torch_defaults", "tf32", "amp_fp16"):
+        torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+        torch.backends.cudnn.allow_tf32 = True
+        for B in (16, 256):
+            T = 128
+            try:
+                torch.manual_seed(20)
+                m = Ref().to(dev).train()
+                opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=0.05)
+                scaler = torch.amp.GradScaler("cuda") if mode == "amp_fp16" else None
+                g = torch.Generator(device=dev).manual_seed(7)
+                rgb = torch.randn(B, T, 2048, generator=g, device=dev).abs_()
+                flow = torch.zeros(B, T, 2048, device=dev)
+                target = torch.nn.functional.one_hot(torch.randint(0, 86, (B, T), device=dev), 86).float()
+
+                def step():
+                    with torch.autocast("cuda", dtype=torch.float16, enabled=scaler is not None):
+                        x = m.layer1(torch.cat((rgb, flow), 2))
+                        ht, _ = m.gru(x, torch.zeros(1, B, 1024, device=dev, dtype=x.dtype))
+                        logits = m.fc(torch.relu(ht))[:, -1].float()
+                        tgt = target[:, -1]
+                        loss = (-(tgt / tgt.norm(dim=1, keepdim=True).clamp_min(1e-12)) * torch.log_softmax(logits, -1)).sum(1).mean()
+                    opt.zero_grad(set_to_none=True)
+                    if scaler is not None:
+                        scaler.scale(loss).backward()
+                        scaler.step(opt)
+                        scaler.update()
+                    else:
+                        loss.backward()
+                        opt.step()
+                    return loss
+
+                for _ in range(3):
+                    step()
+                torch.cuda.synchronize()
+                n = 5 if B == 16 else 3
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    loss = step()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / n
+                out[f"B{B}_T{T}_{mode}"] = {"ms_per_step": ms, "frames_per_s": B * T / ms * 1e3, "loss": float(loss.detach())}
+                del m, opt, rgb, flow, target
+            except Exception as e:  # noqa: BLE001
+                out[f"B{B}_T{T}_{mode}"] = {"error": repr(e)[:200]}
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
     torch.cuda.empty_cache()
     return out
 

@@ -105,6 +105,15 @@ int prego_model_destroy(prego_model_t* model);
  * library-owned operand formats (fp16 / bf16 copies, split-fp16 copies with a per-matrix power-of-two scale, gate-interleaved GRU
  * rows, padded head).  Synchronises `stream` once (the scale search reads three maxima back): not capturable into a CUDA graph. */
 int prego_model_load_weights(prego_model_t* model, const prego_weights_t* w, void* stream);
+/* The same for a subset of the operand formats (a training loop re-packs after every optimizer step and reads only the
+ * fp32 set: PREGO_PACK_F32 costs no synchronisation and ~0.1 ms instead of ~0.5 ms).  PREGO_PACK_F32 is always included.
+ * Formats not named become stale: prego_forward / prego_online_open in a precision whose format is stale return
+ * PREGO_ERR_STATE until it is packed again.  prego_model_load_weights = PREGO_PACK_ALL. */
+#define PREGO_PACK_F32 1u /* fp32 copies, gate-interleaved GRU rows: PREGO_PREC_FP32 inference and the training entry points */
+#define PREGO_PACK_16 2u  /* fp16 and bf16 operand copies (PREGO_PREC_F16 / BF16, online sessions, anticipation in 16 bits) */
+#define PREGO_PACK_X3 4u  /* split-fp16 copies (PREGO_PREC_F16X3); the scale search synchronises `stream` once */
+#define PREGO_PACK_ALL 7u
+int prego_model_load_weights_ex(prego_model_t* model, const prego_weights_t* w, uint32_t formats, void* stream);
 
 size_t prego_workspace_bytes(const prego_model_t* model, int64_t B, int64_t chunk_T, int32_t precision);
 
@@ -303,7 +312,8 @@ int prego_gemm16_stats_nt(const void* A, const void* W, const float* bias, void*
 int prego_gemm16_ln_nt(const void* Y, const float* rowstat, const float* gamma, const float* beta, const void* W,
                        const float* bias, float* C, int64_t M, int64_t N, int64_t K, int32_t precision, void* stream);
 /* Same contract with fp32 storage and TF32 tensor-core operands (CTA pairs); N % 256 == 0, K % 32 == 0;
- * accumulate != 0 adds into C.  Used by the PREGO_PREC_TF32 training step. */
+ * accumulate bit 0 adds into C, bit 8 (0x100) selects 64-column tiles (many small tiles: the per-time-step products of the
+ * training recurrence).  Used by the PREGO_PREC_TF32 training step. */
 int prego_gemm_tf32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,
                        int32_t accumulate, void* stream);
 /* Same contract in exact fp32 on CUDA cores (K % 16 == 0). */

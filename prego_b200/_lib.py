@@ -16,6 +16,7 @@ PREC_BF16 = 0
 PREC_FP32 = 1
 PREC_F16 = 2
 PREC_TF32 = 3  # training only
+PACK_F32, PACK_16, PACK_X3, PACK_ALL = 1, 2, 4, 7  # PREGO_PACK_* (include/prego_b200.h)
 PREC_F16X3 = 4  # fp32-class accuracy on the tensor cores (split fp16 operands)
 PRECISIONS = {"bf16": PREC_BF16, "fp32": PREC_FP32, "fp16": PREC_F16, "fp16x3": PREC_F16X3}
 TRAIN_PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32}
@@ -78,6 +79,7 @@ SIGNATURES = {
     "prego_model_create": (C.c_int, [C.POINTER(Dims), C.c_int32, C.POINTER(C.c_void_p)]),
     "prego_model_destroy": (C.c_int, [C.c_void_p]),
     "prego_model_load_weights": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_void_p]),
+    "prego_model_load_weights_ex": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_uint32, C.c_void_p]),
     "prego_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
     "prego_forward": (C.c_int, [C.c_void_p, C.POINTER(ForwardArgs), C.c_void_p]),
     "prego_model_load_anticipation": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -176,6 +176,7 @@ struct prego_model {
     int din = 0;
     int kpad = 0;  // padded class count of the tcgen05 head (96 or 128), 0 if unsupported
     bool loaded = false;
+    uint32_t packed = 0;  // PREGO_PACK_* formats that match the last loaded weights
     // fp32 (exact path + SIMT recurrence)
     float *w1_f32 = nullptr, *b1 = nullptr, *ln_g = nullptr, *ln_b = nullptr;
     float *wih_f32p = nullptr, *whh_f32p = nullptr, *bih_p = nullptr, *bhh_p = nullptr;
@@ -197,7 +198,7 @@ struct prego_model {
     unsigned* absmax = nullptr;               // [3] scratch of the scale search
     // latency-kernel exchange
     uint2* xchg = nullptr;
-    uint4* xchg_bwd = nullptr;  // [2][4][H] exchange words of the persistent BPTT kernel
+    uint4* xchg_bwd = nullptr;  // [2][8][H] exchange words of the persistent BPTT kernels
     int* err_flag = nullptr;
     uint32_t tag_base = 0;
     int64_t coop_fallbacks = 0;  // persistent recurrence launched WITHOUT the cooperative attribute (occupancy-checked)
@@ -336,11 +337,19 @@ int launch_gemm_xf(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N,
 }
 
 // C[M, N] (fp32, ldc) (+)= A[M, K] (lda) * W[N, K]^T (ldw) + bias, TF32 operands on CTA pairs.  N % 256 == 0, K % 32 == 0.
+// tile_n = 64: narrow tiles for the per-time-step products of the training recurrence (M = B rows only: 256-wide tiles
+// would leave most of the GPU idle).
 int gemm_tf32_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M,
-                 int N, int K, int accumulate, int sm_count, cudaStream_t s) {
+                 int N, int K, int accumulate, int sm_count, cudaStream_t s, int tile_n = 256) {
     if (N % 256 != 0 || K % 32 != 0 || lda % 4 != 0 || ldw % 4 != 0) return fail(PREGO_ERR_INVALID, "gemm_tf32_nt: need N %% 256 == 0, K %% 32 == 0 (got N=%d K=%d)", N, K);
     CUtensorMap tmA, tmB;
     RC_TRY(make_tmap_a32(&tmA, A, K, M, lda));
+    if (tile_n == 64) {
+        RC_TRY(make_tmap_w32(&tmB, W, K, N, ldw, 32));
+        EpiStore<64, -1> epi{C, bias, ldc, 0, 0, accumulate};
+        return launch_gemm_tc2<64, 8, 2>(tmA, tmB, M, N, K, 0, epi, sm_count, s, "gemm_tf32 n64 (2cta)");
+    }
+    if (tile_n != 256) return fail(PREGO_ERR_INVALID, "gemm_tf32_nt: tile_n must be 256 or 64 (got %d)", tile_n);
     RC_TRY(make_tmap_w32(&tmB, W, K, N, ldw, 128));
     EpiStore<256, -1> epi{C, bias, ldc, 0, 0, accumulate};
     return launch_gemm_tc2<256, 6, 2>(tmA, tmB, M, N, K, 0, epi, sm_count, s, "gemm_tf32 (2cta)");
@@ -1002,15 +1011,15 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
         if (m->kpad) ALLOC(m->wc_16p[f], (int64_t)m->kpad * H * 2);
     }
     ALLOC(m->w1_x3, E * 3 * din * 2); ALLOC(m->wih_x3, 3 * H * 3 * E * 2); ALLOC(m->whh_x3, 3 * H * 3 * H * 2); ALLOC(m->absmax, 3 * sizeof(unsigned));
-    ALLOC(m->xchg, 2 * 4 * H * sizeof(uint2)); ALLOC(m->err_flag, sizeof(int)); ALLOC(m->wct_f32, K * H * 4);
+    ALLOC(m->xchg, 2 * 8 * H * sizeof(uint2)); ALLOC(m->err_flag, sizeof(int)); ALLOC(m->wct_f32, K * H * 4);
     ALLOC(m->online_scratch, online_fused_scratch_floats((int)E, (int)K) * 4);
 #undef ALLOC
     CUDA_TRY(cudaMemset(m->online_scratch, 0, online_fused_scratch_floats((int)E, (int)K) * 4));
     if (online_fused_ok(m))
         for (int f = 0; f < 2; ++f) ALLOC2(m->online_stream[f], (size_t)m->sm_count * kFusedWarps * online_stream_loads(din / 1024) * 512);
-    CUDA_TRY(cudaMemset(m->xchg, 0, 2 * 4 * H * sizeof(uint2)));
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->xchg_bwd), 2 * 4 * H * sizeof(uint4)));
-    CUDA_TRY(cudaMemset(m->xchg_bwd, 0, 2 * 4 * H * sizeof(uint4)));
+    CUDA_TRY(cudaMemset(m->xchg, 0, 2 * 8 * H * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->xchg_bwd), 2 * 8 * H * sizeof(uint4)));
+    CUDA_TRY(cudaMemset(m->xchg_bwd, 0, 2 * 8 * H * sizeof(uint4)));
     CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
     CUDA_TRY(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&m->ev_begin, cudaEventDisableTiming));
@@ -1041,8 +1050,14 @@ int prego_model_destroy(prego_model_t* m) {
 }
 
 int prego_model_load_weights(prego_model_t* m, const prego_weights_t* w, void* stream_) {
+    return prego_model_load_weights_ex(m, w, PREGO_PACK_ALL, stream_);
+}
+
+int prego_model_load_weights_ex(prego_model_t* m, const prego_weights_t* w, uint32_t formats, void* stream_) {
     RC_TRY(check_model(m, false));
     if (w == nullptr) return fail(PREGO_ERR_INVALID, "weights is NULL");
+    if ((formats & ~static_cast<uint32_t>(PREGO_PACK_ALL)) != 0) return fail(PREGO_ERR_INVALID, "unknown PREGO_PACK_* bits 0x%x", formats);
+    formats |= PREGO_PACK_F32;
     const void* all[] = {w->layer1_0_weight, w->layer1_0_bias, w->layer1_1_weight, w->layer1_1_bias, w->gru_weight_ih_l0,
                          w->gru_weight_hh_l0, w->gru_bias_ih_l0, w->gru_bias_hh_l0, w->f_classification_0_weight,
                          w->f_classification_0_bias};
@@ -1066,9 +1081,11 @@ int prego_model_load_weights(prego_model_t* m, const prego_weights_t* w, void* s
     presum_gate_bias<<<g(3 * H), T, 0, s>>>(m->bih_p, m->bhh_p, m->bgi_p, 3 * H);
     transpose_f32<<<g((int64_t)K * H), T, 0, s>>>(w->f_classification_0_weight, m->wct_f32, K, H);
     LAUNCH_CHECK("fp32 weight packing");
-    RC_TRY(pack16<0>(m, w, s));
-    RC_TRY(pack16<1>(m, w, s));
-    {   // split-fp16 copies: power-of-two scale per matrix so that max |scale * w| sits near 2^14 (hi far from fp16's overflow, lo in
+    if (formats & PREGO_PACK_16) {
+        RC_TRY(pack16<0>(m, w, s));
+        RC_TRY(pack16<1>(m, w, s));
+    }
+    if (formats & PREGO_PACK_X3) {   // split-fp16 copies: power-of-two scale per matrix so that max |scale * w| sits near 2^14 (hi far from fp16's overflow, lo in
         // its normal range); one small synchronisation per load_state_dict
         const float* srcs[3] = {w->layer1_0_weight, w->gru_weight_ih_l0, w->gru_weight_hh_l0};
         const int64_t ns[3] = {(int64_t)E * din, (int64_t)3 * H * E, (int64_t)3 * H * H};
@@ -1092,6 +1109,7 @@ int prego_model_load_weights(prego_model_t* m, const prego_weights_t* w, void* s
         LAUNCH_CHECK("split-fp16 weight packing");
     }
     m->loaded = true;
+    m->packed = formats;
     return PREGO_OK;
 }
 
@@ -1117,6 +1135,9 @@ static int forward_impl(prego_model_t* m, const prego_forward_args_t* a, const p
     if (a->precision == PREGO_PREC_F16X3 && ((3 * d.hidden_dim) % 256 != 0 || m->din % 64 != 0))
         return fail(PREGO_ERR_INVALID, "PREGO_PREC_F16X3 needs 3 * hidden_dim %% 256 == 0 (got hidden_dim %d); use PREGO_PREC_FP32", d.hidden_dim);
     const bool h16 = !exact;
+    const uint32_t need = a->precision == PREGO_PREC_F16X3 ? PREGO_PACK_X3 : h16 ? PREGO_PACK_16 : PREGO_PACK_F32;
+    if ((m->packed & need) == 0)
+        return fail(PREGO_ERR_STATE, "the operand format of precision %d was not packed by the last prego_model_load_weights_ex (formats 0x%x)", a->precision, m->packed);
     if (h16 && m->kpad == 0) return fail(PREGO_ERR_INVALID, "16-bit paths support num_classes <= 128 (got %d); use PREGO_PREC_FP32", d.num_classes);
     const int64_t Tc = (a->chunk_T > 0 && a->chunk_T < T) ? a->chunk_T : T;
     if (B * Tc >= (int64_t(1) << 31) / 4) return fail(PREGO_ERR_INVALID, "B * chunk_T = %lld is too large for one pass; lower chunk_T", (long long)(B * Tc));
@@ -1413,7 +1434,9 @@ int prego_gemm_tf32_nt(const float* A, const float* W, const float* bias, float*
     int dev = 0, sms = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    return gemm_tf32_nt(A, K, W, K, bias, C, N, (int)M, (int)N, (int)K, accumulate, sms, static_cast<cudaStream_t>(stream));
+    // accumulate bit 8 (0x100) selects the narrow 64-column tiles (test hook for the training recurrence's per-step products)
+    return gemm_tf32_nt(A, K, W, K, bias, C, N, (int)M, (int)N, (int)K, accumulate & 1, sms, static_cast<cudaStream_t>(stream),
+                        (accumulate & 0x100) ? 64 : 256);
 }
 
 int prego_gemm_f32_nt(const float* A, const float* W, const float* bias, float* C, int64_t M, int64_t N, int64_t K,

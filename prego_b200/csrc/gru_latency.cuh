@@ -102,7 +102,7 @@ gru_latency_kernel(GruLatencyArgs a) {
             const uint32_t want = a.tag_base + static_cast<uint32_t>(t);
             const uint2* xs = a.xchg + ((t - 1) & 1) * NB * H;
             // all of this thread's words are requested in one batch per poll round: the step costs ~one L2 round trip
-            constexpr int PW = REGW ? NB * 1024 / kLatThreads : 4;  // words per thread per batch
+            constexpr int PW = REGW ? (NB * 1024 / kLatThreads < 16 ? NB * 1024 / kLatThreads : 16) : 4;  // words per thread per batch
             for (int idx = tid; idx < NB * H; idx += PW * kLatThreads) {
                 uint2 v[PW];
                 long long spins = 0;
@@ -315,6 +315,146 @@ gru_bptt_kernel(GruBpttArgs a) {
 #pragma unroll
         for (int s = 0; s < NB; ++s)
             if (lane == s) mine = acc[s];
+        dh_carry = dhz + mine;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same BPTT step with the contraction split over the THREADS of the CTA instead of over the lanes of one warp: thread
+// `tid` keeps W_hh'[p, u] for its 12 rows p = 1024 j + 4 tid + c and ALL 8 units of the CTA (96 registers), so every
+// d gh value read from shared memory feeds 8 FMAs (the warp-per-unit mapping above reads one value per FMA and is bound by
+// shared-memory bandwidth: 96 KB per warp per step and stream).  The 8 x NB partial sums per thread are reduced with a
+// halving butterfly (V - V/32 shuffles for V values) and one pass through shared memory across the 8 warps.  Saved gates of
+// step t - 1 are requested before the exchange of step t is polled (one L2 round trip off the critical path).
+// NB = 4 or 8 streams per launch.
+template <int NB>
+__global__ void __launch_bounds__(kLatThreads, 1)
+gru_bptt2_kernel(GruBpttArgs a) {
+    constexpr int H = 1024, H3 = 3 * H, U = kLatUnitsPerCta, V = U * NB;
+    static_assert(V % 32 == 0 && kLatThreads * 4 == H, "thread t owns rows 4t..4t+3 of each gate block");
+    extern __shared__ float smem_f[];
+    float* db = smem_f;             // [NB][3H] d gh of this step, packed column order
+    float* red = smem_f + NB * H3;  // [8 warps][V] per-warp partial sums
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int u0 = blockIdx.x * U, u = u0 + warp;
+    const int pcol = (u / 64) * 192 + (u % 64);
+    float w[3][4][U];
+#pragma unroll
+    for (int k = 0; k < U; ++k)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(a.whhT + static_cast<int64_t>(u0 + k) * H3 + 1024 * j + 4 * tid));
+            w[j][0][k] = q.x; w[j][1][k] = q.y; w[j][2][k] = q.z; w[j][3][k] = q.w;
+        }
+    const bool live = lane < a.nb;
+    float pr = 0.f, pz = 0.f, pn = 0.f, pghn = 0.f, ph_t = 0.f, ph_prev = 0.f, pdhr = 0.f;  // saved values of the step about to run
+    auto fetch = [&](int t) {
+        const int64_t si = (static_cast<int64_t>(t) * a.B + a.b0 + lane) * H + u;
+        pr = __ldcs(a.r + si); pz = __ldcs(a.z + si); pn = __ldcs(a.n + si); pghn = __ldcs(a.ghn + si);
+        ph_t = __ldcs(a.hall + si + static_cast<int64_t>(a.B) * H); ph_prev = __ldcs(a.hall + si);
+        pdhr = __ldcs(a.dhrelu + si);
+    };
+    if (live) fetch(a.T - 1);
+    float dh_carry = 0.f;
+    for (int step = 0; step < a.T; ++step) {
+        const int t = a.T - 1 - step;
+        float dhz = 0.f;
+        if (live) {
+            const float r = pr, z = pz, n = pn, ghn = pghn;
+            const float dh = dh_carry + (ph_t > 0.f ? pdhr : 0.f);
+            const float dn = dh * (1.0f - z);
+            const float dz = dh * (ph_prev - n);
+            const float dan = dn * (1.0f - n * n);
+            const float dar = dan * ghn * r * (1.0f - r);
+            const float daz = dz * z * (1.0f - z);
+            const float danr = dan * r;
+            dhz = dh * z;
+            ptx::st_volatile_u128(a.xchg + (static_cast<int64_t>(step & 1) * NB + lane) * H + u,
+                                  make_uint4(__float_as_uint(dar), __float_as_uint(daz), __float_as_uint(danr),
+                                             a.tag_base + static_cast<uint32_t>(step) + 1u));
+            const int64_t gi = (static_cast<int64_t>(t) * a.B + a.b0 + lane) * H3 + pcol;
+            a.dgi[gi] = dar; a.dgi[gi + 64] = daz; a.dgi[gi + 128] = dan;
+            a.dgh[gi] = dar; a.dgh[gi + 64] = daz; a.dgh[gi + 128] = danr;
+        }
+        if (t == 0) break;  // d h_{-1} is not needed (h0 is a constant, rnn.py:49)
+        if (live) fetch(t - 1);
+        // gather d gh_t of all units into shared memory
+        const uint32_t want = a.tag_base + static_cast<uint32_t>(step) + 1u;
+        const uint4* xs = a.xchg + static_cast<int64_t>(step & 1) * NB * H;
+        int timed_out = 0;
+        constexpr int WORDS = NB * H / kLatThreads;  // words per thread
+        constexpr int PW = WORDS < 16 ? WORDS : 16;  // requested in one batch per poll round
+#pragma unroll 1
+        for (int c0 = 0; c0 < WORDS; c0 += PW) {
+            uint4 v[PW];
+            long long spins = 0;
+            bool done;
+            do {
+                done = true;
+#pragma unroll
+                for (int j = 0; j < PW; ++j) {
+                    const int ii = tid + (c0 + j) * kLatThreads;
+                    v[j] = (ii / H) < a.nb ? ptx::ld_volatile_u128(xs + ii) : make_uint4(0u, 0u, 0u, want);
+                }
+#pragma unroll
+                for (int j = 0; j < PW; ++j) done = done && (v[j].w == want);
+                if (!done && ++spins > (1ll << 22)) {
+                    *a.err_flag = 2;
+                    timed_out = 1;
+                    done = true;
+                }
+            } while (!done);
+#pragma unroll
+            for (int j = 0; j < PW; ++j) {
+                const int ii = tid + (c0 + j) * kLatThreads;
+                const int sidx = ii / H, uu = ii % H;
+                float* d = db + sidx * H3 + (uu / 64) * 192 + (uu % 64);
+                d[0] = __uint_as_float(v[j].x);
+                d[64] = __uint_as_float(v[j].y);
+                d[128] = __uint_as_float(v[j].z);
+            }
+        }
+        if (__syncthreads_or(timed_out)) return;
+        // partial products of this thread's 12 rows for the CTA's 8 units
+        float acc[V];  // index k * NB + s
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int s = 0; s < NB; ++s) {
+            if (s < a.nb) {
+                const float* ds = db + s * H3 + 4 * tid;
+                const float4 d0 = *reinterpret_cast<const float4*>(ds);
+                const float4 d1 = *reinterpret_cast<const float4*>(ds + 1024);
+                const float4 d2 = *reinterpret_cast<const float4*>(ds + 2048);
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    float x = w[0][0][k] * d0.x;
+                    x = fmaf(w[0][1][k], d0.y, x); x = fmaf(w[0][2][k], d0.z, x); x = fmaf(w[0][3][k], d0.w, x);
+                    x = fmaf(w[1][0][k], d1.x, x); x = fmaf(w[1][1][k], d1.y, x); x = fmaf(w[1][2][k], d1.z, x); x = fmaf(w[1][3][k], d1.w, x);
+                    x = fmaf(w[2][0][k], d2.x, x); x = fmaf(w[2][1][k], d2.y, x); x = fmaf(w[2][2][k], d2.z, x); x = fmaf(w[2][3][k], d2.w, x);
+                    acc[k * NB + s] = x;
+                }
+            }
+        }
+        // halving butterfly over the 32 lanes: afterwards lane l holds the warp totals of indices l * V/32 .. + V/32 - 1
+#pragma unroll
+        for (int off = 16, n = V / 2; off >= 1; off >>= 1, n >>= 1) {
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const float send = hi ? acc[i] : acc[i + n];
+                const float keep = hi ? acc[i + n] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < V / 32; ++i) red[warp * V + lane * (V / 32) + i] = acc[i];
+        __syncthreads();
+        float mine = 0.f;
+        if (lane < NB) {
+#pragma unroll
+            for (int ww = 0; ww < kLatUnitsPerCta; ++ww) mine += red[ww * V + warp * NB + lane];
+        }
         dh_carry = dhz + mine;
     }
 }

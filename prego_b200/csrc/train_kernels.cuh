@@ -25,8 +25,15 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 sgemm_gen_f32(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm, int64_t ldb,
               const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N, int K, int accumulate,
-              int a_time_major_B, int a_T, int b_time_major_B, int b_T) {
+              int a_time_major_B, int a_T, int b_time_major_B, int b_T, int k_chunk, int64_t c_split_stride) {
     constexpr int BM = 128, BN = 128, BK = 16;
+    // split-K (k_chunk > 0, a multiple of BK): slice blockIdx.z contracts over [z * k_chunk, (z + 1) * k_chunk) and writes its
+    // partial product to C + z * c_split_stride; splitk_reduce_f32 sums the slices in a fixed order (deterministic)
+    const int k_begin = k_chunk > 0 ? static_cast<int>(blockIdx.z) * k_chunk : 0;
+    if (k_chunk > 0) {
+        K = min(K, k_begin + k_chunk);
+        C += static_cast<int64_t>(blockIdx.z) * c_split_stride;
+    }
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -38,7 +45,7 @@ sgemm_gen_f32(const float* __restrict__ A, int64_t lda, const float* __restrict_
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int k0 = k_begin; k0 < K; k0 += BK) {
         // ---- A tile -> As[k][m]
         if constexpr (!TA) {
             const int lr = tid / 4, lk = (tid % 4) * 4;
@@ -331,29 +338,64 @@ gru_gates_train_bwd(const float* __restrict__ dh_carry, const float* __restrict_
     }
 }
 
-// out[c] (+)= sum_r in[r, c] (* mul[r, c])   (bias / LayerNorm-affine gradients).  One block per 32 columns,
-// 8 row-lanes.
+// C[m, n] = (bias[n]) + sum_z part[z][m][n]   (second half of a split-K product; slices summed in z order)
+__global__ void __launch_bounds__(256)
+splitk_reduce_f32(const float* __restrict__ part, int splits, int64_t split_stride, const float* __restrict__ bias,
+                  float* __restrict__ C, int64_t ldc, int M, int N) {
+    const int64_t total = static_cast<int64_t>(M) * N;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int m = static_cast<int>(i / N), n = static_cast<int>(i % N);
+        float s = bias != nullptr ? __ldg(bias + n) : 0.f;
+        for (int z = 0; z < splits; ++z) s += part[z * split_stride + i];
+        C[static_cast<int64_t>(m) * ldc + n] = s;
+    }
+}
+
+// out[y][c] = sum over the rows of slab y of in[r, c] (* mul[r, c])   (bias / LayerNorm-affine gradients).  One block per
+// 32 columns x row slab, 8 row-lanes; gridDim.y slabs of rows_per_slab rows.  With gridDim.y == 1 `out` is the result;
+// otherwise colsum_final_f32 adds the slabs in order.
 __global__ void __launch_bounds__(256)
 colsum_f32(const float* __restrict__ in, const float* __restrict__ mul, int64_t ld, float* __restrict__ out,
-           int64_t rows, int cols, int accumulate) {
+           int64_t rows, int cols, int64_t rows_per_slab) {
     __shared__ float part[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int rl = threadIdx.x >> 5;
-    float s = 0.f;
+    const int64_t r0 = blockIdx.y * rows_per_slab;
+    const int64_t r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
+    float s0 = 0.f, s1 = 0.f;
     if (c < cols) {
-        if (mul != nullptr)
-            for (int64_t r = rl; r < rows; r += 8) s += in[r * ld + c] * mul[r * ld + c];
-        else
-            for (int64_t r = rl; r < rows; r += 8) s += in[r * ld + c];
+        int64_t r = r0 + rl;
+        if (mul != nullptr) {
+            for (; r + 8 < r1; r += 16) {
+                s0 = fmaf(in[r * ld + c], mul[r * ld + c], s0);
+                s1 = fmaf(in[(r + 8) * ld + c], mul[(r + 8) * ld + c], s1);
+            }
+            if (r < r1) s0 = fmaf(in[r * ld + c], mul[r * ld + c], s0);
+        } else {
+            for (; r + 8 < r1; r += 16) {
+                s0 += in[r * ld + c];
+                s1 += in[(r + 8) * ld + c];
+            }
+            if (r < r1) s0 += in[r * ld + c];
+        }
     }
-    part[rl][threadIdx.x & 31] = s;
+    part[rl][threadIdx.x & 31] = s0 + s1;
     __syncthreads();
     if (rl == 0 && c < cols) {
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x & 31];
-        out[c] = accumulate ? out[c] + t : t;
+        out[static_cast<int64_t>(blockIdx.y) * cols + c] = t;
     }
+}
+
+__global__ void colsum_final_f32(const float* __restrict__ part, int slabs, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int y = 0; y < slabs; ++y) s += part[static_cast<int64_t>(y) * cols + c];
+    out[c] = s;
 }
 
 // Packed -> original row order for GRU weight / bias gradients:  dst[orig_row, :] = src[packed_row, :].

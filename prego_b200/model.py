@@ -83,6 +83,7 @@ class MROAD(nn.Module):
         self._handle = None
         self._handle_device = None
         self._packed_key = None
+        self._packed_formats = 0
         self._workspace = None
         self._ant_workspace = None
         self.last_labels = None  # int32 [B, T] labels of the last forward (fused argmax)
@@ -93,6 +94,7 @@ class MROAD(nn.Module):
             _lib.load().prego_model_destroy(self._handle)
             self._handle = None
             self._packed_key = None
+            self._packed_formats = 0
 
     def __del__(self):
         try:
@@ -116,21 +118,25 @@ class MROAD(nn.Module):
         return (l1.weight, l1.bias, ln.weight, ln.bias, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0,
                 fc.weight, fc.bias)  # order of _STATE_KEYS / prego_weights_t
 
-    def _sync_weights(self, lib, device):
+    def _sync_weights(self, lib, device, formats=_lib.PACK_ALL):
         """Re-pack the ten tensors into the library handle when any of them changed (in-place update,
-        load_state_dict, .to()).  Cheap when nothing changed: ten (data_ptr, version) pairs."""
+        load_state_dict, .to()) or when a format this call needs is stale.  Cheap when nothing changed: ten
+        (data_ptr, version) pairs.  ``formats``: the PREGO_PACK_* set the caller reads -- the training step passes the
+        fp32 set only (it re-packs after every optimizer step); inference packs everything, once."""
         tensors = self._param_tensors()
         key = tuple((t.data_ptr(), t._version) for t in tensors)
-        if key == self._packed_key:
+        if key == self._packed_key and (self._packed_formats & formats) == formats:
             return
         for k, t in zip(_STATE_KEYS, tensors):
             if t.device != device or t.dtype != torch.float32:
                 raise RuntimeError(f"parameter {k} must be fp32 on {device} (got {t.dtype} on {t.device}); call model.to(device)")
+        if key == self._packed_key:
+            formats |= self._packed_formats  # same weights: what is already packed stays valid (the call marks the rest stale)
         keep = [t.detach().contiguous() for t in tensors]
         w = _lib.Weights(*[t.data_ptr() for t in keep])
         stream = torch.cuda.current_stream(device).cuda_stream
-        _lib.check(lib.prego_model_load_weights(self._handle, C.byref(w), stream), "prego_model_load_weights")
-        self._packed_key = key
+        _lib.check(lib.prego_model_load_weights_ex(self._handle, C.byref(w), formats, stream), "prego_model_load_weights_ex")
+        self._packed_key, self._packed_formats = key, formats | _lib.PACK_F32
 
     def _get_workspace(self, nbytes: int, device):
         ws = self._workspace
@@ -331,6 +337,7 @@ class MROADA(MROAD):
         self._handle = None
         self._handle_device = None
         self._packed_key = None
+        self._packed_formats = 0
         self._ant_key = None
         self._workspace = None
         self._ant_workspace = None
@@ -342,8 +349,8 @@ class MROADA(MROAD):
         super()._release()
         self._ant_key = None
 
-    def _sync_weights(self, lib, device):
-        super()._sync_weights(lib, device)
+    def _sync_weights(self, lib, device, formats=_lib.PACK_ALL):
+        super()._sync_weights(lib, device, formats)
         lin = self.anticipation_layer[0]
         key = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
         if key == self._ant_key:

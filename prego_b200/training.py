@@ -53,7 +53,7 @@ class MiniROADTrainFn(torch.autograd.Function):
         B, T = int(ref.shape[0]), int(ref.shape[1])
         with torch.cuda.device(device):
             module._ensure_handle(device)
-            module._sync_weights(lib, device)
+            module._sync_weights(lib, device, _lib.PACK_F32)  # the training entry points read the fp32 set only
             need = lib.prego_train_workspace_bytes(module._handle, B, T)
             # the saved activations (gates, h_t, e, y, masks) belong to THIS forward: one workspace per call, kept alive
             # by ctx until its backward ran, so a second train-mode forward before the first backward (gradient

@@ -88,9 +88,11 @@ def test_gemm16_2cta(dev, lib, tile_n, N, M, K, prec):
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
 
 
+@pytest.mark.parametrize("narrow", [0, 0x100])
 @pytest.mark.parametrize("M,N,K", [(16, 3072, 1024), (300, 1024, 3072), (2048, 2048, 4096), (3072, 4096, 2048)])
-def test_gemm_tf32_2cta(dev, lib, M, N, K):
-    """TF32 operands (fp32 storage) on the CTA-pair kernel, plain and accumulating epilogue."""
+def test_gemm_tf32_2cta(dev, lib, M, N, K, narrow):
+    """TF32 operands (fp32 storage) on the CTA-pair kernel, plain and accumulating epilogue; ``narrow``: the 64-column
+    tiles of the training recurrence's per-step products (bit 8 of ``accumulate``)."""
     from prego_b200 import _lib
     g = torch.Generator(device=dev).manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g, device=dev)
@@ -98,13 +100,13 @@ def test_gemm_tf32_2cta(dev, lib, M, N, K):
     bias = torch.randn(N, generator=g, device=dev)
     C0 = torch.randn(M, N, generator=g, device=dev)
     Cout = C0.clone()
-    _lib.check(lib.prego_gemm_tf32_nt(A.data_ptr(), W.data_ptr(), bias.data_ptr(), Cout.data_ptr(), M, N, K, 1, _stream()),
+    _lib.check(lib.prego_gemm_tf32_nt(A.data_ptr(), W.data_ptr(), bias.data_ptr(), Cout.data_ptr(), M, N, K, 1 | narrow, _stream()),
                "prego_gemm_tf32_nt")
     torch.cuda.synchronize()
     ref = (A.double() @ W.double().T + bias.double() + C0.double()).float()
     assert torch.isfinite(Cout).all()
     assert (Cout - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
-    _lib.check(lib.prego_gemm_tf32_nt(A.data_ptr(), W.data_ptr(), None, Cout.data_ptr(), M, N, K, 0, _stream()), "prego_gemm_tf32_nt")
+    _lib.check(lib.prego_gemm_tf32_nt(A.data_ptr(), W.data_ptr(), None, Cout.data_ptr(), M, N, K, narrow, _stream()), "prego_gemm_tf32_nt")
     torch.cuda.synchronize()
     ref = (A.double() @ W.double().T).float()
     assert (Cout - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()

@@ -51,7 +51,7 @@ def test_gradients_match_reference_golden(dev, golden_meta):
         assert abs(g.norm().item() - gold[k + ".stats"][2]) <= 1e-3 * gold[k + ".stats"][2], k
 
 
-@pytest.mark.parametrize("B,T,K", [(5, 17, 86), (16, 128, 86)])
+@pytest.mark.parametrize("B,T,K", [(5, 17, 86), (12, 9, 86), (16, 128, 86)])
 def test_gradients_match_torch_autograd(dev, B, T, K):
     cfg = dict(synthetic.ASSEMBLY101_O, dropout=0.0, num_classes=K)
     M_rows = B * T
