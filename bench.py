@@ -288,7 +288,7 @@ def training_leg(dev, world):
     from prego_b200 import build_optimizer
     opt = build_optimizer({"optimizer": "AdamW", "lr": 1e-4, "weight_decay": 0.05}, model)  # one-launch fused AdamW
     out = {}
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", "tf32x3", "tf32"):
         model.train_precision = prec
         for B in (16, 256):
             T = 128
@@ -309,7 +309,7 @@ def training_leg(dev, world):
             ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
             if world > 1:
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            out[f"B{B}_T{T}" + ("" if prec == "fp32" else "_tf32")] = {"ms_per_step": float(ms), "frames_per_s": world * B * T / float(ms) * 1e3,
+            out[f"B{B}_T{T}" + ("" if prec == "fp32" else "_" + prec)] = {"ms_per_step": float(ms), "frames_per_s": world * B * T / float(ms) * 1e3,
                                                                        "loss": float(loss)}
             del rgb, flow, target
     if world > 1:
@@ -333,8 +333,10 @@ def training_leg(dev, world):
                                          "Inside the timed training steps above the gradients are reduced IN the backward instead: two buckets of one flat buffer, the "
                                          "gru / classifier bucket on a side stream under the layer1 backward (prego_b200.training.enable_overlapped_allreduce)"}
     out["note"] = ("fwd + BPTT + fused AdamW (one launch), dropout 0.2, flow = 0; recurrence (forward and BPTT) on the persistent exact-fp32 kernels "
-                   "for B <= 64; plain keys: every GEMM exact fp32 on CUDA cores (parity mode); *_tf32: large projections and their "
-                   "gradients on tcgen05 kind::tf32; grads all-reduced (NCCL) when n_gpus > 1")
+                   "for B <= 64 in every mode; plain keys: every GEMM exact fp32 on CUDA cores (parity mode); *_tf32x3: the projections and their "
+                   "gradients on tcgen05 kind::tf32 with every operand split hi + lo, three terms in one product over 3K (fp32-class: passes the exact "
+                   "mode's gradient bounds); *_tf32: plain TF32 operands; grads all-reduced (NCCL) when n_gpus > 1.  The stock-torch step on the same "
+                   "GPU is library_baseline.train_step")
     return out
 
 

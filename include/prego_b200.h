@@ -31,6 +31,9 @@ extern "C" {
 #define PREGO_PREC_BF16 0       /* tcgen05 kind::f16, bf16 operands, fp32 accumulate (throughput path) */
 #define PREGO_PREC_FP32 1       /* exact fp32 FFMA path (1e-4 parity mode) */
 #define PREGO_PREC_TF32 3       /* training only: fp32 storage, tcgen05 kind::tf32 operands, fp32 accumulate */
+#define PREGO_PREC_TF32X3 5     /* training only: fp32-class products on the tensor cores -- every operand split as a = hi + lo (TF32 each),
+                                 * hi hi + lo hi + hi lo contracted in one kind::tf32 product over 3K (error ~2^-21 per term); the
+                                 * persistent recurrence kernels (B <= 64) are exact fp32 in every mode */
 #define PREGO_PREC_F16X3 4      /* fp32-class accuracy ON the tensor cores: every fp32 operand travels as fp16 hi + fp16 lo (22 bits),
                                    x.w = x_hi w_hi + x_lo w_hi + x_hi w_lo in one tcgen05 kind::f16 GEMM over 3 K, fp32 accumulate;
                                    LayerNorm, gates, state, softmax in fp32.  Same 1e-4 logit bound as PREGO_PREC_FP32 at a
@@ -197,6 +200,8 @@ typedef struct prego_train_args {
 } prego_train_args_t;
 
 size_t prego_train_workspace_bytes(const prego_model_t* model, int64_t B, int64_t T);
+/* The same for a given training precision (PREGO_PREC_TF32X3 adds the split-operand scratch). */
+size_t prego_train_workspace_bytes_ex(const prego_model_t* model, int64_t B, int64_t T, int32_t precision);
 int prego_train_forward(prego_model_t* model, const prego_train_args_t* args, void* stream);
 int prego_train_backward(prego_model_t* model, const prego_train_args_t* args, void* stream);
 

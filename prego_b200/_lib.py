@@ -19,7 +19,8 @@ PREC_TF32 = 3  # training only
 PACK_F32, PACK_16, PACK_X3, PACK_ALL = 1, 2, 4, 7  # PREGO_PACK_* (include/prego_b200.h)
 PREC_F16X3 = 4  # fp32-class accuracy on the tensor cores (split fp16 operands)
 PRECISIONS = {"bf16": PREC_BF16, "fp32": PREC_FP32, "fp16": PREC_F16, "fp16x3": PREC_F16X3}
-TRAIN_PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32}
+PREC_TF32X3 = 5  # training only: three-term TF32 split, fp32-class
+TRAIN_PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
 PHASES = ("stage", "gemm1", "layernorm", "gemm2", "recurrence", "head")
 
 
@@ -104,6 +105,7 @@ SIGNATURES = {
     "prego_device_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "prego_recurrence_fallbacks": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "prego_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64]),
+    "prego_train_workspace_bytes_ex": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32]),
     "prego_train_forward": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
     "prego_train_backward": (C.c_int, [C.c_void_p, C.POINTER(TrainArgs), C.c_void_p]),
     "prego_adamw_step": (C.c_int, [C.POINTER(AdamWArgs), C.c_void_p]),

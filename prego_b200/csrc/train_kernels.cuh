@@ -408,6 +408,37 @@ __global__ void unpack_rows_f32(const float* __restrict__ src, float* __restrict
     }
 }
 
+// Operand split of the 3xTF32 products (PREGO_PREC_TF32X3): every fp32 value a = hi + lo with hi = a rounded to TF32 (10-bit
+// mantissa) and lo = a - hi (exact in fp32; the tensor core reads its leading 11 bits).  The contraction is cut into chunks of
+// kc original columns; chunk c of an activation-side row is stored as [lo | hi | hi] (3 kc values), of a weight-side row as
+// [hi | lo | hi], so ONE kind::tf32 product over the 3 kc columns of a chunk sums lo hi + hi lo + hi hi -- the two small
+// terms FIRST, while the accumulator is still small.  Measured (scripts/diag_x3_accuracy.py, K = 2048): the tensor core's
+// accumulator drops low bits of what is added to a large running sum -- one product over 3K with the small terms last: 2.1e-5
+// relative (Frobenius); small terms first: 4.9e-6; chunks of 1024 added in fp32 by the epilogue: ~1e-6 = cuBLAS fp32 (8e-7).
+// src [rows, K] with row stride lds -> dst [rows, 3K]; K % kc == 0, kc % 4 == 0, lds % 4 == 0.
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__global__ void __launch_bounds__(256)
+split3_tf32(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t rows, int K, int kc, int weight_side) {
+    const int k4 = K / 4;
+    const int64_t total = rows * k4;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / k4;
+        const int c = static_cast<int>(i % k4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + r * lds + c);
+        const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        float* d = dst + r * 3 * K + static_cast<int64_t>(c / kc) * 3 * kc + (c % kc);
+        *reinterpret_cast<float4*>(d) = weight_side ? hi : lo;
+        *reinterpret_cast<float4*>(d + kc) = weight_side ? lo : hi;
+        *reinterpret_cast<float4*>(d + 2 * kc) = hi;
+    }
+}
+
 // dst[c, r] = src[r, c] through 32 x 32 shared-memory tiles (both sides coalesced).  The TN / NN operand forms of the
 // backward pass become the K-major NT form of the tensor-core GEMM through these (a few hundred MB per step, HBM-bound).
 __global__ void __launch_bounds__(256)

@@ -54,7 +54,8 @@ class MiniROADTrainFn(torch.autograd.Function):
         with torch.cuda.device(device):
             module._ensure_handle(device)
             module._sync_weights(lib, device, _lib.PACK_F32)  # the training entry points read the fp32 set only
-            need = lib.prego_train_workspace_bytes(module._handle, B, T)
+            prec = _lib.TRAIN_PRECISIONS[getattr(module, "train_precision", "fp32")]
+            need = lib.prego_train_workspace_bytes_ex(module._handle, B, T, prec)
             # the saved activations (gates, h_t, e, y, masks) belong to THIS forward: one workspace per call, kept alive
             # by ctx until its backward ran, so a second train-mode forward before the first backward (gradient
             # accumulation, two views, a loss over several batches) cannot overwrite or free them; torch's caching
