@@ -12,8 +12,9 @@ tensor cores, so the labels in the JSON are the reference's; ``fp16`` is the thr
 synthetic videos (no dataset ships with the repo); ``--eval synthetic`` keeps the seeded default weights.
 Without ``--eval`` the reference's training loop runs (main.py:59-115): sliding-window train loader
 (dataset.py:96-135), ``OadLoss``, AdamW (fused), ``train_one_epoch`` + evaluation every epoch, ``best.pth`` kept and
-renamed to ``best_<mAP>.pth`` at the end.  ``--amp`` selects ``train_precision = 'tf32'`` (this implementation's
-reduced-precision training mode); ``--tensorboard`` / ``--lr_scheduler`` are accepted for CLI compatibility
+renamed to ``best_<mAP>.pth`` at the end.  Training precision: ``'tf32x3'`` by default (fp32-class forward on the tensor cores), ``--amp`` selects ``'tf32'``
+(this implementation's reduced-precision mode), ``train_precision: fp32`` in the YAML the exact CUDA-core mode;
+``--tensorboard`` / ``--lr_scheduler`` are accepted for CLI compatibility
 (the reference's scheduler path raises KeyError on both shipped configs).
 """
 from __future__ import annotations
@@ -140,6 +141,10 @@ def main(argv=None):
     cfg.update({k: v for k, v in vars(args).items() if k not in ("precision", "num_epoch", "output_path", "aggregate_out") or v is not None})
     if args.amp:
         cfg["train_precision"] = "tf32"
+    elif "train_precision" not in cfg:
+        # fp32-class forward on the tensor cores; gradients 7x closer to ATen fp32 than the reference's own GPU run with
+        # torch's default flags (cuDNN GRU in TF32), 2.2x faster than the exact CUDA-core mode (profiles/r02_train_modes.txt)
+        cfg["train_precision"] = "tf32x3"
     if args.eval is not None and "precision" not in cfg:
         # the JSON feeds the 200-frame mode vote and the anticipation branch: pay ~3x the fp16 path for fp32-class logits
         # (1e-4 bound, 0 label flips in 131 072 frames vs the reference; tests/test_gpu_long.py) instead of 99.95 % agreement

@@ -50,7 +50,8 @@ class MROAD(nn.Module):
     """B200-native MiniROAD.  Extra (optional) cfg keys: ``precision`` ('fp16' default: throughput | 'bf16' | 'fp16x3': fp32-class
     accuracy on the tensor cores (fp16 hi + lo operands) | 'fp32': exact CUDA-core FFMA),
     ``chunk_frames`` (frames per pass over all streams; bounds the workspace), ``train_precision`` ('fp32' default:
-    exact CUDA-core GEMMs | 'tf32': the large projections and their gradients on tcgen05 kind::tf32)."""
+    exact CUDA-core GEMMs | 'tf32x3': the large projections and their gradients on tcgen05 kind::tf32 over split hi + lo operands,
+    fp32-class forward | 'tf32': plain TF32 operands, the accuracy of stock torch's default cuDNN GRU)."""
 
     def __init__(self, cfg):
         super().__init__()
