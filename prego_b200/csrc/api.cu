@@ -192,13 +192,13 @@ struct prego_model {
     // 16-bit operands of the tcgen05 path, [0] = fp16, [1] = bf16
     void *w1_16[2] = {nullptr, nullptr}, *wih_16p[2] = {nullptr, nullptr}, *whh_16p[2] = {nullptr, nullptr},
          *wc_16p[2] = {nullptr, nullptr};
-    // split-fp16 (PREGO_PREC_F16X3) weights: rows [hi | hi | lo] of scale * W (fp16, [N, 3 K]), gate-interleaved like the 16-bit copies
+    // split-fp16 (PREGO_PREC_F16X3) weights: rows [hi | lo | hi] of scale * W (fp16, [N, 3 K]), gate-interleaved like the 16-bit copies
     __half *w1_x3 = nullptr, *wih_x3 = nullptr, *whh_x3 = nullptr;
     float inv_scale_x3[3] = {1.f, 1.f, 1.f};  // 1 / scale of w1, wih, whh (powers of two)
     unsigned* absmax = nullptr;               // [3] scratch of the scale search
     // latency-kernel exchange
     uint2* xchg = nullptr;
-    uint4* xchg_bwd = nullptr;  // [2][8][H] exchange words of the persistent BPTT kernels
+    uint4* xchg_bwd = nullptr;  // [2 groups][2][8][H] exchange words of the persistent BPTT kernels
     int* err_flag = nullptr;
     uint32_t tag_base = 0;
     int64_t coop_fallbacks = 0;  // persistent recurrence launched WITHOUT the cooperative attribute (occupancy-checked)
@@ -427,10 +427,10 @@ int check_model(const prego_model* m, bool need_weights) {
     return PREGO_OK;
 }
 
-template <int NB, bool REGW>
+template <int NB, bool REGW, int G = 1>
 int launch_latency_impl(const GruLatencyArgs& a, int H, cudaStream_t stream) {
-    auto kfn = gru_latency_kernel<NB, REGW>;
-    const size_t smem = ((REGW ? 0 : 3 * kLatUnitsPerCta * H) + 2 * NB * H) * sizeof(float);
+    auto kfn = gru_latency_kernel<NB, REGW, G>;
+    const size_t smem = ((REGW ? 0 : 3 * kLatUnitsPerCta * H) + G * 2 * NB * H) * sizeof(float);
     RC_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(kfn), (int)smem));
     GruLatencyArgs args = a;
     void* params[] = {&args};
@@ -875,7 +875,7 @@ int chunk_f32(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint
 }
 
 // One time chunk of the split-fp16 mode (PREGO_PREC_F16X3): the exact-fp32 path's structure (stream-major rows, fp32 LayerNorm /
-// gates / state / softmax) with every large GEMM on tcgen05 over [hi | lo | hi] x [hi | hi | lo] operands (simt_kernels.cuh).
+// gates / state / softmax) with every large GEMM on tcgen05 over [lo | hi | hi] x [hi | lo | hi] operands, small terms first (simt_kernels.cuh).
 int chunk_x3(prego_model* m, const prego_forward_args_t* a, const Plan& p, uint8_t* ws, float*& h_cur, float*& h_alt, int64_t t0, int tc,
              cudaStream_t s, const prego_anticipation_args_t* ant = nullptr) {
     const prego_dims_t& d = m->d;
@@ -1011,15 +1011,15 @@ int prego_model_create(const prego_dims_t* dims, int32_t device, prego_model_t**
         if (m->kpad) ALLOC(m->wc_16p[f], (int64_t)m->kpad * H * 2);
     }
     ALLOC(m->w1_x3, E * 3 * din * 2); ALLOC(m->wih_x3, 3 * H * 3 * E * 2); ALLOC(m->whh_x3, 3 * H * 3 * H * 2); ALLOC(m->absmax, 3 * sizeof(unsigned));
-    ALLOC(m->xchg, 2 * 8 * H * sizeof(uint2)); ALLOC(m->err_flag, sizeof(int)); ALLOC(m->wct_f32, K * H * 4);
+    ALLOC(m->xchg, 2 * 16 * H * sizeof(uint2)); ALLOC(m->err_flag, sizeof(int)); ALLOC(m->wct_f32, K * H * 4);
     ALLOC(m->online_scratch, online_fused_scratch_floats((int)E, (int)K) * 4);
 #undef ALLOC
     CUDA_TRY(cudaMemset(m->online_scratch, 0, online_fused_scratch_floats((int)E, (int)K) * 4));
     if (online_fused_ok(m))
         for (int f = 0; f < 2; ++f) ALLOC2(m->online_stream[f], (size_t)m->sm_count * kFusedWarps * online_stream_loads(din / 1024) * 512);
-    CUDA_TRY(cudaMemset(m->xchg, 0, 2 * 8 * H * sizeof(uint2)));
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->xchg_bwd), 2 * 8 * H * sizeof(uint4)));
-    CUDA_TRY(cudaMemset(m->xchg_bwd, 0, 2 * 8 * H * sizeof(uint4)));
+    CUDA_TRY(cudaMemset(m->xchg, 0, 2 * 16 * H * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->xchg_bwd), 2 * 16 * H * sizeof(uint4)));
+    CUDA_TRY(cudaMemset(m->xchg_bwd, 0, 2 * 16 * H * sizeof(uint4)));
     CUDA_TRY(cudaMemset(m->err_flag, 0, sizeof(int)));
     CUDA_TRY(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&m->ev_begin, cudaEventDisableTiming));

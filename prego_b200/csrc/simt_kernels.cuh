@@ -427,7 +427,9 @@ __global__ void f32_to_16(const float* __restrict__ src, typename Op16<FMT>::T* 
 // Split-fp16 operands ("fp16x3", the fp32-class tensor-core mode): an fp32 value v is carried as hi = fp16(v) and
 // lo = fp16(v - hi) (22 significant bits together), and a product x . w is evaluated as
 //     x_hi w_hi + x_lo w_hi + x_hi w_lo                 (the lo . lo term, 2^-22 relative, is dropped)
-// by ONE tcgen05 GEMM over a three times longer K: activation rows [hi | lo | hi], weight rows [hi | hi | lo].
+// by ONE tcgen05 GEMM over a three times longer K: activation rows [lo | hi | hi], weight rows [hi | lo | hi] -- the two
+// small terms are contracted FIRST, while the accumulator is still small: the tensor core's accumulator drops low bits of
+// what is added to a large running sum (scripts/diag_x3_accuracy.py: 4x smaller error than with the small terms last).
 // fp16 x fp16 products are exact in the fp32 accumulator.  Weights are pre-scaled by a power of two so that their lo
 // parts stay in fp16's normal range; the epilogue multiplies the accumulator by the inverse (exact).
 __device__ __forceinline__ void split_hi_lo(float v, __half& hi, __half& lo) {
@@ -436,7 +438,7 @@ __device__ __forceinline__ void split_hi_lo(float v, __half& hi, __half& lo) {
     lo = __float2half_rn(c - __half2float(hi));
 }
 
-// dst[m, 0:K] = hi, dst[m, K:2K] = lo, dst[m, 2K:3K] = hi of src[m, :] (row-major fp32 [M, K]); 4 elements per thread.
+// dst[m, 0:K] = lo, dst[m, K:2K] = hi, dst[m, 2K:3K] = hi of src[m, :] (row-major fp32 [M, K]); 4 elements per thread.
 __global__ void __launch_bounds__(256)
 split3_rows_f32(const float* __restrict__ src, __half* __restrict__ dst, int64_t M, int K) {
     const int vec = K / 4;
@@ -448,14 +450,14 @@ split3_rows_f32(const float* __restrict__ src, __half* __restrict__ dst, int64_t
         __half h[4], l[4];
         split_hi_lo(v.x, h[0], l[0]); split_hi_lo(v.y, h[1], l[1]); split_hi_lo(v.z, h[2], l[2]); split_hi_lo(v.w, h[3], l[3]);
         __half* d = dst + m * 3 * static_cast<int64_t>(K) + c;
-        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(h);
-        *reinterpret_cast<uint2*>(d + K) = *reinterpret_cast<const uint2*>(l);
+        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(l);
+        *reinterpret_cast<uint2*>(d + K) = *reinterpret_cast<const uint2*>(h);
         *reinterpret_cast<uint2*>(d + 2 * K) = *reinterpret_cast<const uint2*>(h);
     }
 }
 
 // Feature staging of the split mode: chunk row m (STREAM-major, m = b * Tc + t, as in the exact-fp32 path) of [rgb | flow]
-// -> [hi | lo | hi] of width 3 D.
+// -> [lo | hi | hi] of width 3 D.
 __global__ void __launch_bounds__(256)
 stage_features_split3(const float* __restrict__ rgb, const float* __restrict__ flow, __half* __restrict__ dst, int64_t Mc, int Dr,
                       int Df, int Tc, int T, int t0) {
@@ -471,13 +473,13 @@ stage_features_split3(const float* __restrict__ rgb, const float* __restrict__ f
         __half h[4], l[4];
         split_hi_lo(v.x, h[0], l[0]); split_hi_lo(v.y, h[1], l[1]); split_hi_lo(v.z, h[2], l[2]); split_hi_lo(v.w, h[3], l[3]);
         __half* d = dst + m * 3 * static_cast<int64_t>(D) + c;
-        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(h);
-        *reinterpret_cast<uint2*>(d + D) = *reinterpret_cast<const uint2*>(l);
+        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(l);
+        *reinterpret_cast<uint2*>(d + D) = *reinterpret_cast<const uint2*>(h);
         *reinterpret_cast<uint2*>(d + 2 * D) = *reinterpret_cast<const uint2*>(h);
     }
 }
 
-// Weights of the split mode: dst[p, 0:K] = hi, [K:2K] = hi, [2K:3K] = lo of scale * src[row(p), :]; rows optionally in the
+// Weights of the split mode: dst[p, 0:K] = hi, [K:2K] = lo, [2K:3K] = hi of scale * src[row(p), :]; rows optionally in the
 // packed gate-interleaved order; columns [0, col_limit) of src only (zero-flow elision is not offered in this mode: col_limit = cols).
 __global__ void pack_rows_split3(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols, int H, int permute, float scale) {
     const int64_t total = static_cast<int64_t>(rows) * cols;
@@ -488,8 +490,8 @@ __global__ void pack_rows_split3(const float* __restrict__ src, __half* __restri
         split_hi_lo(src[static_cast<int64_t>(r) * cols + c] * scale, hi, lo);
         __half* d = dst + static_cast<int64_t>(p) * 3 * cols + c;
         d[0] = hi;
-        d[cols] = hi;
-        d[2 * cols] = lo;
+        d[cols] = lo;
+        d[2 * cols] = hi;
     }
 }
 
