@@ -334,8 +334,8 @@ def training_leg(dev, world):
                                          "gru / classifier bucket on a side stream under the layer1 backward (prego_b200.training.enable_overlapped_allreduce)"}
     out["note"] = ("fwd + BPTT + fused AdamW (one launch), dropout 0.2, flow = 0; recurrence (forward and BPTT) on the persistent exact-fp32 kernels "
                    "for B <= 64 in every mode; plain keys: every GEMM exact fp32 on CUDA cores (parity mode); *_tf32x3: the projections and their "
-                   "gradients on tcgen05 kind::tf32 with every operand split hi + lo, three terms in one product over 3K (fp32-class: passes the exact "
-                   "mode's gradient bounds); *_tf32: plain TF32 operands; grads all-reduced (NCCL) when n_gpus > 1.  The stock-torch step on the same "
+                   "gradients on tcgen05 kind::tf32 with every operand split hi + lo, three terms per 1 024-column chunk, small terms first, chunks added in fp32 (fp32-class forward: "
+                   "logits 2.3e-6 of ATen's; gradients through the hard ReLU gates within 3e-3 Frobenius, profiles/r02_train_modes.txt); *_tf32: plain TF32 operands; grads all-reduced (NCCL) when n_gpus > 1.  The stock-torch step on the same "
                    "GPU is library_baseline.train_step")
     return out
 
@@ -926,6 +926,16 @@ def run_ours(args, world, rank, local):
     if not args.no_library and world == 1:
         torch.cuda.empty_cache()
         library = library_baseline_leg(dev, B, Tc, local)
+
+    if library is not None and train is not None and "train_step" in library:
+        # same GPU, same process: this repo's training step against the stock-torch step of the same accuracy class
+        lt = library["train_step"]
+        pairs = {"tf32_vs_library_tf32": ("_tf32", "_tf32"), "tf32_vs_library_amp_fp16": ("_tf32", "_amp_fp16"),
+                 "tf32x3_vs_library_as_shipped": ("_tf32x3", "_torch_defaults"), "exact_fp32_vs_library_as_shipped": ("", "_torch_defaults")}
+        train["speedup_vs_library"] = {
+            f"B{b}_{name}": lt[f"B{b}_T128{lk}"]["ms_per_step"] / train[f"B{b}_T128{ok}"]["ms_per_step"]
+            for b in (16, 256) for name, (ok, lk) in pairs.items()
+            if f"B{b}_T128{ok}" in train and "ms_per_step" in lt.get(f"B{b}_T128{lk}", {})}
 
     cpu = None
     if not args.no_cpu and world == 1:

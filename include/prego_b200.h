@@ -25,7 +25,7 @@ extern "C" {
 #define PREGO_ERR_INVALID 1     /* bad argument / unsupported shape */
 #define PREGO_ERR_CUDA 2        /* a CUDA runtime / driver call failed */
 #define PREGO_ERR_WORKSPACE 3   /* workspace too small */
-#define PREGO_ERR_STATE 4       /* weights not loaded */
+#define PREGO_ERR_STATE 4       /* weights not loaded, or not packed in the operand format this call reads */
 
 /* Compute precision of the projection / recurrence / head GEMMs. */
 #define PREGO_PREC_BF16 0       /* tcgen05 kind::f16, bf16 operands, fp32 accumulate (throughput path) */

@@ -12,3 +12,8 @@ ncu --set full --clock-control none --import-source on -k regex:"stage_features_
 echo "full set rc=$?"
 ncu -i gpurun_out/r02_prof_step.ncu-rep --page raw --csv > gpurun_out/r02_prof_step_raw.csv 2>/dev/null
 ls -la gpurun_out/r02_prof_step* gpurun_out/r02_launches*
+#  3. --set full of the persistent recurrence kernels of ONE training step (B 16 x T 128, tf32 mode): forward + BPTT
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"gru_bptt2_kernel|gru_latency_kernel" -c 2 -f \
+    -o gpurun_out/r02_prof_train python scripts/train_profile.py 16 tf32 > gpurun_out/r02_prof_train.log 2>&1
+echo "training recurrence full set rc=$?"
+ncu -i gpurun_out/r02_prof_train.ncu-rep --page raw --csv > gpurun_out/r02_prof_train_raw.csv 2>/dev/null

@@ -171,6 +171,47 @@ def test_dropout_mask_and_training_loop(dev):
     assert l2[-1] < l2[0] and max(abs(a - b) for a, b in zip(l2, l3)) < 5e-3 * max(l3), (l2, l3)
 
 
+def test_training_packs_the_fp32_set_only_and_inference_repacks(dev):
+    """A training step re-packs only the fp32 operand set (prego_model_load_weights_ex(PREGO_PACK_F32)); the 16-bit and split
+    copies go stale, the C ABI refuses to run on a stale format, and the next inference call of the module re-packs what it
+    needs -- its result must follow the UPDATED weights (checked against the numpy oracle on those weights)."""
+    import ctypes as C
+
+    from oracle import miniroad_np
+    from prego_b200 import _lib
+    cfg = dict(synthetic.EPIC_TENT_O, dropout=0.0)
+    B, T, K = 8, 16, 12
+    rgb, flow = synthetic.feature_batch(list(range(B)), T, dev, False)
+    target = torch.stack([synthetic.targets(s, T, K) for s in range(B)]).to(dev)
+    model = synthetic.seeded_model(cfg, seed=20, device=dev)
+    before = model.infer(rgb, flow, want_probs=False, want_logits=True, precision="fp16")["logits"].clone()
+    assert model._packed_formats == _lib.PACK_ALL
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=0.0)
+    model.train()
+    train_one_step(model, OadLoss(cfg), opt, rgb, flow, target)
+    train_one_step(model, OadLoss(cfg), opt, rgb, flow, target)   # second step: packs the weights the first step wrote
+    assert model._packed_formats == _lib.PACK_F32
+    lib = _lib.load()
+    ws = torch.empty(lib.prego_workspace_bytes(model._handle, B, T, _lib.PREC_F16) + 1024, dtype=torch.uint8, device=dev)
+    labels = torch.empty(B, T, dtype=torch.int32, device=dev)
+    args = _lib.ForwardArgs()
+    args.rgb, args.flow, args.B, args.T, args.chunk_T = rgb.data_ptr(), flow.data_ptr(), B, T, T
+    args.labels = labels.data_ptr()
+    args.workspace, args.workspace_bytes = ws.data_ptr() + (-ws.data_ptr()) % 1024, ws.numel() - 1024
+    args.precision = _lib.PREC_F16
+    rc = lib.prego_forward(model._handle, C.byref(args), torch.cuda.current_stream(dev).cuda_stream)
+    assert rc == 4, (rc, lib.prego_last_error())  # PREGO_ERR_STATE
+    model.eval()
+    out = model.infer(rgb, flow, want_probs=False, want_logits=True, precision="fp16")
+    torch.cuda.synchronize()
+    assert model._packed_formats == _lib.PACK_ALL
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    _, ref_logits, _ = miniroad_np.forward(sd, rgb.cpu().numpy(), flow.cpu().numpy(), return_all=True)
+    scale = float(np.abs(ref_logits).max())
+    assert np.abs(out["logits"].cpu().numpy() - ref_logits).max() <= 2e-3 * scale
+    assert (out["logits"] - before).abs().max().item() > 1e-2 * scale, "the update must be visible"
+
+
 def test_fused_adamw_matches_torch(dev):
     """prego_adamw_step (one launch for all tensors) against torch.optim.AdamW over 5 steps, ragged tensor sizes."""
     from prego_b200 import FusedAdamW
