@@ -141,10 +141,9 @@ def main(argv=None):
     cfg.update({k: v for k, v in vars(args).items() if k not in ("precision", "num_epoch", "output_path", "aggregate_out") or v is not None})
     if args.amp:
         cfg["train_precision"] = "tf32"
-    elif "train_precision" not in cfg:
-        # fp32-class forward on the tensor cores; gradients 7x closer to ATen fp32 than the reference's own GPU run with
-        # torch's default flags (cuDNN GRU in TF32), 2.2x faster than the exact CUDA-core mode (profiles/r02_train_modes.txt)
-        cfg["train_precision"] = "tf32x3"
+    # otherwise the module's default, 'tf32x3': fp32-class forward on the tensor cores; gradients 7x closer to ATen fp32 than the
+    # reference's own GPU run with torch's default flags (cuDNN GRU in TF32), 2.2x faster than the exact CUDA-core mode
+    # (profiles/r02_train_modes.txt)
     if args.eval is not None and "precision" not in cfg:
         # the JSON feeds the 200-frame mode vote and the anticipation branch: pay ~3x the fp16 path for fp32-class logits
         # (1e-4 bound, 0 label flips in 131 072 frames vs the reference; tests/test_gpu_long.py) instead of 99.95 % agreement

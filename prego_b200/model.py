@@ -49,9 +49,10 @@ _STATE_KEYS = (
 class MROAD(nn.Module):
     """B200-native MiniROAD.  Extra (optional) cfg keys: ``precision`` ('fp16' default: throughput | 'bf16' | 'fp16x3': fp32-class
     accuracy on the tensor cores (fp16 hi + lo operands) | 'fp32': exact CUDA-core FFMA),
-    ``chunk_frames`` (frames per pass over all streams; bounds the workspace), ``train_precision`` ('fp32' default:
-    exact CUDA-core GEMMs | 'tf32x3': the large projections and their gradients on tcgen05 kind::tf32 over split hi + lo operands,
-    fp32-class forward | 'tf32': plain TF32 operands, the accuracy of stock torch's default cuDNN GRU)."""
+    ``chunk_frames`` (frames per pass over all streams; bounds the workspace), ``train_precision`` ('tf32x3' default:
+    the large projections and their gradients on tcgen05 kind::tf32 over split hi + lo operands, fp32-class forward, 1.6x the stock
+    torch step | 'fp32': exact CUDA-core GEMMs, the gradient-parity mode | 'tf32': plain TF32 operands, the accuracy of stock torch's
+    default cuDNN GRU; shapes the tensor-core GEMM does not take (B*T % 32 != 0) run the exact kernels in every mode)."""
 
     def __init__(self, cfg):
         super().__init__()
@@ -79,7 +80,7 @@ class MROAD(nn.Module):
         self.h0 = torch.zeros(self.num_layers, 1, self.hidden_dim)  # rnn.py:49 (not in state_dict)
 
         self.precision = cfg.get("precision", "fp16")
-        self.train_precision = cfg.get("train_precision", "fp32")
+        self.train_precision = cfg.get("train_precision", "tf32x3")
         self.chunk_frames = int(cfg.get("chunk_frames", 1 << 17))
         self._handle = None
         self._handle_device = None
@@ -333,7 +334,7 @@ class MROADA(MROAD):
         self.anticipation_layer = nn.Sequential(nn.Linear(self.hidden_dim, self.anticipation_length * self.hidden_dim))
 
         self.precision = cfg.get("precision", "fp16")
-        self.train_precision = cfg.get("train_precision", "fp32")
+        self.train_precision = cfg.get("train_precision", "tf32x3")
         self.chunk_frames = int(cfg.get("chunk_frames", 1 << 17))
         self._handle = None
         self._handle_device = None

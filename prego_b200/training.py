@@ -54,7 +54,7 @@ class MiniROADTrainFn(torch.autograd.Function):
         with torch.cuda.device(device):
             module._ensure_handle(device)
             module._sync_weights(lib, device, _lib.PACK_F32)  # the training entry points read the fp32 set only
-            prec = _lib.TRAIN_PRECISIONS[getattr(module, "train_precision", "fp32")]
+            prec = _lib.TRAIN_PRECISIONS[getattr(module, "train_precision", "tf32x3")]
             need = lib.prego_train_workspace_bytes_ex(module._handle, B, T, prec)
             # the saved activations (gates, h_t, e, y, masks) belong to THIS forward: one workspace per call, kept alive
             # by ctx until its backward ran, so a second train-mode forward before the first backward (gradient
@@ -68,7 +68,7 @@ class MiniROADTrainFn(torch.autograd.Function):
             args = _lib.TrainArgs(rgb_c.data_ptr() if rgb_c is not None else None,
                                   flow_c.data_ptr() if flow_c is not None else None, B, T, logits.data_ptr(), None, None,
                                   ws_ptr, need, float(module.layer1[3].p), int(seed),
-                                  _lib.TRAIN_PRECISIONS[getattr(module, "train_precision", "fp32")])
+                                  _lib.TRAIN_PRECISIONS[getattr(module, "train_precision", "tf32x3")])
             stream = torch.cuda.current_stream(device).cuda_stream
             _lib.check(lib.prego_train_forward(module._handle, C.byref(args), stream), "prego_train_forward")
         ctx.module, ctx.rgb, ctx.flow, ctx.seed = module, rgb_c, flow_c, int(seed)

@@ -26,6 +26,7 @@ def dev():
 
 
 def _grads_cuda(cfg, rgb, flow, target, dev):
+    cfg = dict(cfg, train_precision="fp32")  # the exact CUDA-core mode: the gradient-parity bounds below are its bounds
     model = synthetic.seeded_model(cfg, seed=20, device=dev).train()
     out = model(rgb.to(dev), flow.to(dev))
     assert out["logits"].requires_grad and tuple(out["logits"].shape) == (rgb.shape[0], rgb.shape[1], cfg["num_classes"])
@@ -53,7 +54,7 @@ def test_gradients_match_reference_golden(dev, golden_meta):
 
 @pytest.mark.parametrize("B,T,K", [(5, 17, 86), (12, 9, 86), (16, 128, 86)])
 def test_gradients_match_torch_autograd(dev, B, T, K):
-    cfg = dict(synthetic.ASSEMBLY101_O, dropout=0.0, num_classes=K)
+    cfg = dict(synthetic.ASSEMBLY101_O, dropout=0.0, num_classes=K, train_precision="fp32")
     M_rows = B * T
     rgb, flow = synthetic.feature_batch(list(range(100, 100 + B)), T, "cpu", False)
     # a loss that touches EVERY frame (the reference loss only touches the last one)
@@ -278,7 +279,7 @@ def test_two_forwards_before_backward_keep_their_own_activations(dev):
     t2 = torch.stack([synthetic.targets(s, 23, 12) for s in (72, 73, 74, 75, 76)])
     _, _, g1, _ = _grads_cuda(cfg, r1, f1, t1, dev)
     _, _, g2, _ = _grads_cuda(cfg, r2, f2, t2, dev)
-    model = synthetic.seeded_model(cfg, seed=20, device=dev).train()
+    model = synthetic.seeded_model(dict(cfg, train_precision="fp32"), seed=20, device=dev).train()
     l1 = crit(model(r1.to(dev), f1.to(dev)), t1.to(dev))
     l2 = crit(model(r2.to(dev), f2.to(dev)), t2.to(dev))   # second forward BEFORE the first backward
     (l1 + l2).backward()
