@@ -34,6 +34,16 @@ def test_header_symbols_all_exported(lib):
     assert lib.prego_abi_version() == 4
 
 
+def test_every_entry_point_is_mapped_to_the_reference_in_integration_md():
+    """The drop-in boundary is documented function by function: every symbol include/prego_b200.h declares must appear in
+    INTEGRATION.md's table (entry point -> the reference file:line it replaces)."""
+    header = open(os.path.join(ROOT, "include", "prego_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    declared = sorted(set(re.findall(r"\b(prego_[a-z0-9_]+)\s*\(", header)))
+    missing = [n for n in declared if f"`{n}`" not in doc]
+    assert not missing, f"declared in the header but absent from INTEGRATION.md: {missing}"
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_create_fails_loudly_without_gpu(lib):
     dims = _lib.Dims(2048, 2048, 2048, 1024, 86)
