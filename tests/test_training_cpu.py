@@ -205,3 +205,38 @@ def test_gradient_bucket_layout():
         lo, hi = (a0, a1) if i >= 4 else (b0, b1)   # _param_tensors(): layer1 first, then gru, then the classifier
         assert lo <= o and o + n <= hi
     assert sum(numel[4:]) == 3072 * 2048 + 3072 * 1024 + 2 * 3072 + 86 * 1024 + 86
+
+
+def test_weight_repack_tracks_the_operand_formats(monkeypatch):
+    """Host logic of MROAD._sync_weights (no GPU: the C call is recorded by a stub): inference packs every operand format
+    once, a training step re-packs the fp32 set only after each in-place weight update, and the next inference call packs
+    what went stale -- never nothing, never more than needed."""
+    from prego_b200 import _lib
+    from prego_b200.model import MROAD
+
+    calls = []
+
+    class StubLib:
+        def prego_model_load_weights_ex(self, handle, w, formats, stream):
+            calls.append(int(formats))
+            return 0
+
+    class StubStream:
+        cuda_stream = 0
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: StubStream())
+    m = MROAD(dict(synthetic.EPIC_TENT_O))
+    m._handle = object()
+    lib, cpu = StubLib(), torch.device("cpu")
+    m._sync_weights(lib, cpu)                       # first inference call: everything
+    m._sync_weights(lib, cpu)                       # nothing changed: no call
+    assert calls == [_lib.PACK_ALL] and m._packed_formats == _lib.PACK_ALL
+    with torch.no_grad():
+        m.layer1[0].weight.add_(1.0)                # optimizer step (in place: bumps the version counter)
+    m._sync_weights(lib, cpu, _lib.PACK_F32)        # training forward: the fp32 set only
+    m._sync_weights(lib, cpu, _lib.PACK_F32)
+    assert calls == [_lib.PACK_ALL, _lib.PACK_F32] and m._packed_formats == _lib.PACK_F32
+    m._sync_weights(lib, cpu)                       # inference again: the stale formats are packed (same weights)
+    assert calls[-1] == _lib.PACK_ALL and m._packed_formats == _lib.PACK_ALL and len(calls) == 3
+    m._sync_weights(lib, cpu, _lib.PACK_F32 | _lib.PACK_16)
+    assert len(calls) == 3                          # a subset of what is packed: no call
